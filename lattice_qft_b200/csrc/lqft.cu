@@ -1,0 +1,1008 @@
+// lqft.cu — the C ABI of include/lqft.h: handle management, launch schedules, CUDA graphs,
+// NCCL / peer-memory halo exchange.  All arithmetic that touches the field runs in the CUDA
+// kernels of kernels_v1.cuh / kernels_tiled.cuh; this file contains no CPU implementation of
+// the sweep or of the observables.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lqft.h"
+#include "kernels_tiled.cuh"
+#include "kernels_v1.cuh"
+#include "spec.cuh"
+
+using namespace lqft;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static lqft_status fail(lqft_status s, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return s;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(LQFT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define ST(call)                        \
+    do {                                \
+        lqft_status s_ = (call);        \
+        if (s_ != LQFT_OK) return s_;   \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that the library loads (and single-GPU handles work) without it
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static lqft_status nccl_load() {
+    if (g_nccl.lib) return LQFT_OK;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(LQFT_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                          \
+    *(void**)(&g_nccl.field) = dlsym(lib, name);                                  \
+    if (!g_nccl.field) return fail(LQFT_ERR_NCCL, "libnccl lacks symbol %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = lib;
+    return LQFT_OK;
+}
+
+#define NC(call)                                                                                 \
+    do {                                                                                         \
+        ncclResult_t r_ = (call);                                                                \
+        if (r_ != ncclSuccess)                                                                   \
+            return fail(LQFT_ERR_NCCL, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), \
+                        __FILE__, __LINE__);                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct GraphKey {
+    uint32_t energy_every, normalize_every, cycle;
+    bool operator<(const GraphKey& o) const {
+        if (energy_every != o.energy_every) return energy_every < o.energy_every;
+        if (normalize_every != o.normalize_every) return normalize_every < o.normalize_every;
+        return cycle < o.cycle;
+    }
+};
+struct GraphVal {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t kernels = 0;
+};
+
+struct lqft_handle {
+    lqft_config cfg{};
+    Geom g{};
+    uint64_t n_slab = 0;       // sites of this rank's slab (per chain)
+    uint64_t n_global = 0;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_bnd = nullptr, ev_comm = nullptr;
+    bool timed = false;
+    int32_t* field[2] = {nullptr, nullptr};
+    std::vector<ChainDev> chains_h;
+    std::vector<double> beta;
+    std::vector<uint8_t> configured;
+    std::vector<uint32_t> thr_h;
+    ChainDev* chains_d = nullptr;
+    uint32_t* thr_d = nullptr;
+    bool params_dirty = true;
+    bool any_wilson = false;
+    uint32_t max_thr = 0;
+    unsigned long long* acc_d = nullptr;   // [n_chains][kAccSlots]
+    unsigned long long* obs_d = nullptr;   // [n_chains][2]
+    unsigned long long* mom_d = nullptr;   // [n_chains][T][2]
+    int32_t* shift_d = nullptr;            // [n_chains]
+    int32_t* staging_d = nullptr;          // [n_slab] lexicographic
+    uint64_t* sweep_ctr_d = nullptr;       // device sweep counter for graph replays
+    uint32_t* n_meas_d = nullptr;
+    long long* elog_d = nullptr;
+    uint32_t elog_cap = 0;
+    uint64_t* sites_d = nullptr;
+    long long* gathered_d = nullptr;
+    uint32_t sites_cap = 0;
+    std::vector<double*> diff_sum, diff_comp;
+    std::vector<uint64_t> diff_count;
+    bool ghosts_valid = false;
+    uint64_t launches = 0;
+    ncclComm_t comm = nullptr;
+    int sm_count = 148;
+    std::map<GraphKey, GraphVal> graphs;
+    TiledPlan tiled{};
+};
+
+static lqft_status use_device(lqft_handle* h) {
+    CU(cudaSetDevice(h->cfg.device));
+    return LQFT_OK;
+}
+
+static lqft_status upload_params(lqft_handle* h) {
+    if (!h->params_dirty) return LQFT_OK;
+    const uint32_t nc = h->cfg.n_chains;
+    for (uint32_t c = 0; c < nc; ++c)
+        if (!h->configured[c])
+            return fail(LQFT_ERR_STATE, "chain %u has no parameters: call lqft_set_chain first", c);
+    CU(cudaMemcpyAsync(h->chains_d, h->chains_h.data(), sizeof(ChainDev) * nc,
+                       cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->thr_d, h->thr_h.data(), sizeof(uint32_t) * (size_t)nc * kThrStride,
+                       cudaMemcpyHostToDevice, h->stream));
+    // the async copies read pageable std::vector storage: fence before it can change
+    CU(cudaStreamSynchronize(h->stream));
+    h->any_wilson = false;
+    h->max_thr = 0;
+    for (uint32_t c = 0; c < nc; ++c) {
+        if (h->chains_h[c].wil_w && h->chains_h[c].wil_h) h->any_wilson = true;
+        h->max_thr = std::max(h->max_thr, h->chains_h[c].n_thr);
+    }
+    h->params_dirty = false;
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();
+    return LQFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host spec functions
+// ---------------------------------------------------------------------------------------------
+extern "C" uint32_t lqft_version(void) { return (LQFT_VERSION_MAJOR << 16) | LQFT_VERSION_MINOR; }
+extern "C" const char* lqft_last_error(void) { return g_err.c_str(); }
+
+extern "C" int32_t lqft_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" void lqft_host_philox4x32(uint64_t seed, const uint32_t ctr[4], uint32_t out[4]) {
+    u32x4 r = philox4x32(ctr[0], ctr[1], ctr[2], ctr[3], (uint32_t)seed, (uint32_t)(seed >> 32));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+extern "C" uint32_t lqft_host_site_word(uint64_t seed, uint64_t idx, uint32_t colour, uint64_t sweep) {
+    const uint64_t grp = idx >> 3;
+    u32x4 r = philox4x32((uint32_t)grp, colour | ((uint32_t)(grp >> 32) << 8), (uint32_t)sweep,
+                         (uint32_t)(sweep >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+    return word_of(r, (uint32_t)((idx >> 1) & 3u));
+}
+
+extern "C" uint32_t lqft_host_threshold_table(double beta, uint32_t* thr, uint32_t capacity) {
+    if (!(beta > 0.0) || !thr) return 0;
+    for (uint32_t k = 0; k < capacity; ++k) {
+        const int m = (int)k - 3;
+        // (old_action - new_action) as f64 * temp, then exp: algorithm.rs:152
+        const double prob = exp((double)(-(6 + 2 * m)) * beta);
+        const double scaled = floor(prob * 2147483648.0);
+        const uint32_t t = scaled >= 2147483647.0 ? 2147483647u : (uint32_t)scaled;
+        thr[k] = t;
+        if (t == 0u) return k + 1;
+    }
+    return 0;  // did not reach a zero entry within capacity
+}
+
+extern "C" uint64_t lqft_host_pick_site(uint64_t seed, uint32_t stream, uint64_t counter,
+                                        uint32_t rep, uint64_t n_sites) {
+    return pick_site((uint32_t)seed, (uint32_t)(seed >> 32), stream, counter, rep, n_sites);
+}
+
+extern "C" int32_t lqft_host_hot_value(uint64_t seed, uint64_t idx) {
+    return hot_value((uint32_t)seed, (uint32_t)(seed >> 32), idx);
+}
+
+extern "C" uint64_t lqft_host_index(uint32_t X, uint32_t Y, uint32_t T, uint32_t x, uint32_t y,
+                                    uint32_t t) {
+    return (uint64_t)(x % X) + (uint64_t)X * ((uint64_t)(y % Y) + (uint64_t)Y * (uint64_t)(t % T));
+}
+
+extern "C" void lqft_host_coords(uint32_t X, uint32_t Y, uint32_t T, uint64_t idx, uint32_t xyz[3]) {
+    xyz[0] = (uint32_t)(idx % X);
+    xyz[1] = (uint32_t)((idx / X) % Y);
+    xyz[2] = (uint32_t)((idx / ((uint64_t)X * Y)) % T);
+}
+
+extern "C" void lqft_host_neighbours(uint32_t X, uint32_t Y, uint32_t T, uint64_t idx, uint64_t nbr[6]) {
+    uint32_t c[3];
+    lqft_host_coords(X, Y, T, idx, c);
+    nbr[0] = lqft_host_index(X, Y, T, c[0] + 1, c[1], c[2]);
+    nbr[1] = lqft_host_index(X, Y, T, c[0], c[1] + 1, c[2]);
+    nbr[2] = lqft_host_index(X, Y, T, c[0], c[1], c[2] + 1);
+    nbr[3] = lqft_host_index(X, Y, T, c[0] + X - 1, c[1], c[2]);
+    nbr[4] = lqft_host_index(X, Y, T, c[0], c[1] + Y - 1, c[2]);
+    nbr[5] = lqft_host_index(X, Y, T, c[0], c[1], c[2] + T - 1);
+}
+
+extern "C" int32_t lqft_host_wilson_offset(uint32_t Y, uint32_t x, uint32_t y, uint32_t t,
+                                           uint32_t width, uint32_t height) {
+    return wilson_offset(Y, x, y, t, width, height);
+}
+
+extern "C" lqft_status lqft_host_slab(uint32_t T, uint32_t ws, uint32_t rank, uint32_t* t0,
+                                      uint32_t* nt) {
+    if (ws == 0 || rank >= ws) return fail(LQFT_ERR_INVALID, "rank %u outside world of %u", rank, ws);
+    if (T % ws != 0 || (ws > 1 && (T / ws) % 2 != 0))
+        return fail(LQFT_ERR_INVALID, "T=%u does not split into %u slabs of an even plane count", T, ws);
+    if (t0) *t0 = rank * (T / ws);
+    if (nt) *nt = T / ws;
+    return LQFT_OK;
+}
+
+extern "C" uint64_t lqft_run_measurements(uint64_t first_step, uint64_t n_steps, uint32_t every) {
+    if (every == 0 || n_steps == 0) return 0;
+    // multiples of `every` in [first_step, first_step + n_steps)
+    const uint64_t last = first_step + n_steps - 1;
+    const uint64_t lo = (first_step + every - 1) / every;
+    const uint64_t hi = last / every;
+    return hi >= lo ? hi - lo + 1 : 0;
+}
+
+extern "C" lqft_status lqft_comm_unique_id(uint8_t id[128]) {
+    ST(nccl_load());
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    static_assert(sizeof(u) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id, &u, 128);
+    return LQFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+extern "C" lqft_status lqft_destroy(lqft_handle* h) {
+    if (!h) return LQFT_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    tiled_release(h->tiled);
+    cudaFree(h->field[0]); cudaFree(h->field[1]);
+    cudaFree(h->chains_d); cudaFree(h->thr_d); cudaFree(h->acc_d); cudaFree(h->obs_d);
+    cudaFree(h->mom_d); cudaFree(h->shift_d); cudaFree(h->staging_d); cudaFree(h->sweep_ctr_d);
+    cudaFree(h->n_meas_d); cudaFree(h->elog_d); cudaFree(h->sites_d); cudaFree(h->gathered_d);
+    for (auto p : h->diff_sum) cudaFree(p);
+    for (auto p : h->diff_comp) cudaFree(p);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
+    if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    delete h;
+    return LQFT_OK;
+}
+
+static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
+    h->cfg = *cfg;
+    const uint32_t X = cfg->x, Y = cfg->y, T = cfg->t, ws = cfg->world_size ? cfg->world_size : 1;
+    h->cfg.world_size = ws;
+    if (X < 2 || Y < 2 || T < 2 || (X & 1) || (Y & 1) || (T & 1))
+        return fail(LQFT_ERR_INVALID, "extents %ux%ux%u must be even and >= 2 (red-black order)", X, Y, T);
+    if (cfg->n_chains == 0 || cfg->n_chains > 65535)
+        return fail(LQFT_ERR_INVALID, "n_chains=%u outside [1,65535]", cfg->n_chains);
+    if (cfg->dtype != LQFT_I32)
+        return fail(LQFT_ERR_INVALID, "dtype %u: only LQFT_I32 fields are implemented", cfg->dtype);
+    if ((uint64_t)X * Y / 2 >= (1ull << 31))
+        return fail(LQFT_ERR_INVALID, "a t-plane of %ux%u exceeds 2^31 elements per colour", X, Y);
+    if ((uint64_t)X * Y * T >= (1ull << 40))
+        return fail(LQFT_ERR_INVALID, "lattice of %llu sites is too large",
+                    (unsigned long long)X * Y * T);
+    uint32_t t0 = 0, nt = T;
+    ST(lqft_host_slab(T, ws, cfg->rank, &t0, &nt));
+    if (ws > 1 && nt > 65535) return fail(LQFT_ERR_INVALID, "slab of %u planes exceeds grid limits", nt);
+    if (T > 65535) return fail(LQFT_ERR_INVALID, "T=%u exceeds grid limits", T);
+
+    int ndev = lqft_device_count();
+    if (ndev <= 0)
+        return fail(LQFT_ERR_CUDA, "no CUDA device is visible; liblqft has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(LQFT_ERR_INVALID, "device %d outside [0,%d)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10)
+        return fail(LQFT_ERR_CUDA, "device %d is sm_%d%d; liblqft is built for sm_100a only",
+                    cfg->device, prop.major, prop.minor);
+    h->sm_count = prop.multiProcessorCount;
+
+    Geom& g = h->g;
+    g.X = X; g.Y = Y; g.T = T; g.Xh = X / 2;
+    g.Tl = nt; g.t0 = t0;
+    g.ghost = ws > 1 ? 1 : 0;
+    g.plane = g.Xh * Y;
+    g.chain_stride = (uint64_t)g.plane * (g.Tl + 2 * g.ghost);
+    h->n_slab = (uint64_t)X * Y * nt;
+    h->n_global = (uint64_t)X * Y * T;
+
+    const uint32_t nc = cfg->n_chains;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev_start));
+    CU(cudaEventCreate(&h->ev_stop));
+    CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+    const size_t fbytes = sizeof(int32_t) * g.chain_stride * nc;
+    for (int c = 0; c < 2; ++c) {
+        if (cudaMalloc(&h->field[c], fbytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(LQFT_ERR_NOMEM, "cannot allocate %zu bytes of device memory for the field", fbytes);
+        }
+        CU(cudaMemsetAsync(h->field[c], 0, fbytes, h->stream));
+    }
+    CU(cudaMalloc(&h->chains_d, sizeof(ChainDev) * nc));
+    CU(cudaMalloc(&h->thr_d, sizeof(uint32_t) * (size_t)nc * kThrStride));
+    CU(cudaMalloc(&h->acc_d, sizeof(unsigned long long) * (size_t)nc * kAccSlots));
+    CU(cudaMalloc(&h->obs_d, sizeof(unsigned long long) * (size_t)nc * 2));
+    CU(cudaMalloc(&h->mom_d, sizeof(unsigned long long) * (size_t)nc * T * 2));
+    CU(cudaMalloc(&h->shift_d, sizeof(int32_t) * nc));
+    CU(cudaMalloc(&h->sweep_ctr_d, sizeof(uint64_t)));
+    CU(cudaMalloc(&h->n_meas_d, sizeof(uint32_t)));
+    CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * (size_t)nc * kAccSlots, h->stream));
+    CU(cudaMemsetAsync(h->obs_d, 0, sizeof(unsigned long long) * (size_t)nc * 2, h->stream));
+    CU(cudaMemsetAsync(h->sweep_ctr_d, 0, sizeof(uint64_t), h->stream));
+    CU(cudaMemsetAsync(h->n_meas_d, 0, sizeof(uint32_t), h->stream));
+    h->chains_h.assign(nc, ChainDev{});
+    h->beta.assign(nc, 0.0);
+    h->configured.assign(nc, 0);
+    h->thr_h.assign((size_t)nc * kThrStride, 0u);
+    h->diff_sum.assign(nc, nullptr);
+    h->diff_comp.assign(nc, nullptr);
+    h->diff_count.assign(nc, 0);
+
+    if (ws > 1) {
+        ST(nccl_load());
+        ncclUniqueId id;
+        memcpy(&id, cfg->nccl_id, 128);
+        NC(g_nccl.CommInitRank(&h->comm, (int)ws, id, (int)cfg->rank));
+    }
+    CU(tiled_prepare(h->tiled, g, nc, h->sm_count, (cfg->flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1)) != 0));
+    CU(cudaStreamSynchronize(h->stream));
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_create(const lqft_config* cfg, lqft_handle** out) {
+    if (!cfg || !out) return fail(LQFT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    lqft_handle* h = new (std::nothrow) lqft_handle();
+    if (!h) return fail(LQFT_ERR_NOMEM, "out of host memory");
+    lqft_status s = create_impl(cfg, h);
+    if (s != LQFT_OK) {
+        std::string keep = g_err;
+        lqft_destroy(h);
+        g_err = keep;
+        return s;
+    }
+    *out = h;
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_set_chain(lqft_handle* h, uint32_t chain, double beta, uint64_t seed,
+                                      uint32_t wil_w, uint32_t wil_h) {
+    if (!h) return fail(LQFT_ERR_INVALID, "null handle");
+    if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    if (wil_w > h->cfg.x || wil_h > h->cfg.t)
+        return fail(LQFT_ERR_INVALID, "wilson loop %ux%u does not fit the %ux%u x-t plane", wil_w, wil_h,
+                    h->cfg.x, h->cfg.t);
+    uint32_t* thr = h->thr_h.data() + (size_t)chain * kThrStride;
+    const uint32_t n = lqft_host_threshold_table(beta, thr, kThrStride);
+    if (n == 0)
+        return fail(LQFT_ERR_INVALID,
+                    "beta=%g is not representable: need beta > 0 and at most %u threshold entries", beta,
+                    kThrStride);
+    ChainDev& cd = h->chains_h[chain];
+    cd.k0 = (uint32_t)seed;
+    cd.k1 = (uint32_t)(seed >> 32);
+    cd.n_thr = n;
+    cd.wil_w = (wil_w && wil_h) ? wil_w : 0;
+    cd.wil_h = (wil_w && wil_h) ? wil_h : 0;
+    h->beta[chain] = beta;
+    h->configured[chain] = 1;
+    h->params_dirty = true;
+    return LQFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// halo exchange (world_size > 1): colour-c boundary planes -> neighbours' ghost planes
+// ---------------------------------------------------------------------------------------------
+static lqft_status exchange_halo_nccl(lqft_handle* h, int colour, cudaStream_t s) {
+    const Geom& g = h->g;
+    const int ws = (int)h->cfg.world_size, r = (int)h->cfg.rank;
+    const int lo = (r + ws - 1) % ws, hi = (r + 1) % ws;
+    NC(g_nccl.GroupStart());
+    for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
+        int32_t* f = h->field[colour] + (size_t)c * g.chain_stride;
+        // my first owned plane is the lower neighbour's upper ghost; my last owned plane is the
+        // upper neighbour's lower ghost.
+        NC(g_nccl.Send(f + (size_t)1 * g.plane, g.plane, ncclInt32, lo, h->comm, s));
+        NC(g_nccl.Send(f + (size_t)g.Tl * g.plane, g.plane, ncclInt32, hi, h->comm, s));
+        NC(g_nccl.Recv(f + (size_t)(g.Tl + 1) * g.plane, g.plane, ncclInt32, hi, h->comm, s));
+        NC(g_nccl.Recv(f, g.plane, ncclInt32, lo, h->comm, s));
+    }
+    NC(g_nccl.GroupEnd());
+    return LQFT_OK;
+}
+
+static lqft_status refresh_ghosts(lqft_handle* h) {
+    if (h->cfg.world_size <= 1 || h->ghosts_valid) return LQFT_OK;
+    ST(exchange_halo_nccl(h, 0, h->stream));
+    ST(exchange_halo_nccl(h, 1, h->stream));
+    h->ghosts_valid = true;
+    return LQFT_OK;
+}
+
+static lqft_status allreduce_i64(lqft_handle* h, void* buf, size_t n) {
+    if (h->cfg.world_size <= 1) return LQFT_OK;
+    NC(g_nccl.AllReduce(buf, buf, n, ncclInt64, ncclSum, h->comm, h->stream));
+    return LQFT_OK;
+}
+static lqft_status allreduce_i32(lqft_handle* h, void* buf, size_t n) {
+    if (h->cfg.world_size <= 1) return LQFT_OK;
+    NC(g_nccl.AllReduce(buf, buf, n, ncclInt32, ncclSum, h->comm, h->stream));
+    return LQFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+static inline uint32_t block_for(uint32_t units) {
+    uint32_t b = (units + 31u) & ~31u;
+    return std::min(256u, std::max(32u, b));
+}
+
+// One half-sweep of colour `colour` over local planes tl_first .. tl_first + n_planes - 1.
+static lqft_status launch_half_v1(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr,
+                                  uint32_t tl_first, uint32_t n_planes, cudaStream_t s) {
+    if (n_planes == 0) return LQFT_OK;
+    const Geom& g = h->g;
+    const bool vec = (g.X % 8 == 0) && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC);
+    const uint32_t units = vec ? g.plane / 4 : g.plane;
+    const uint32_t bd = block_for(units);
+    dim3 grid((units + bd - 1) / bd, n_planes, h->cfg.n_chains);
+    const size_t smem = sizeof(uint32_t) * h->max_thr;
+    int32_t* own = h->field[colour];
+    const int32_t* oth = h->field[colour ^ 1];
+    (void)ctr;
+#define LAUNCH(K)                                                                                    \
+    K<<<grid, bd, smem, s>>>(g, colour, sweep, ctr, tl_first, own, oth, h->chains_d, h->thr_d, h->acc_d)
+    if (vec) {
+        if (h->any_wilson) LAUNCH(k_sweep_vec4<true>); else LAUNCH(k_sweep_vec4<false>);
+    } else {
+        if (h->any_wilson) LAUNCH(k_sweep_generic<true>); else LAUNCH(k_sweep_generic<false>);
+    }
+#undef LAUNCH
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return LQFT_OK;
+}
+
+// One full red-black sweep.  `sweep` + (*ctr if ctr) is the RNG sweep counter.
+static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* ctr) {
+    const Geom& g = h->g;
+    if (h->cfg.world_size <= 1) {
+        if (h->tiled.enabled) {
+            CU(tiled_sweep(h->tiled, g, h->field, sweep, ctr, h->chains_d, h->thr_d, h->acc_d, h->max_thr,
+                           h->any_wilson, h->stream, &h->launches));
+            return LQFT_OK;
+        }
+        ST(launch_half_v1(h, 0, sweep, ctr, 0, g.Tl, h->stream));
+        ST(launch_half_v1(h, 1, sweep, ctr, 0, g.Tl, h->stream));
+        return LQFT_OK;
+    }
+    // slab: boundary planes first, exchange on the comm stream while the interior updates
+    for (int colour = 0; colour < 2; ++colour) {
+        ST(launch_half_v1(h, colour, sweep, ctr, 0, 1, h->stream));
+        ST(launch_half_v1(h, colour, sweep, ctr, g.Tl - 1, 1, h->stream));
+        CU(cudaEventRecord(h->ev_bnd, h->stream));
+        CU(cudaStreamWaitEvent(h->comm_stream, h->ev_bnd, 0));
+        ST(exchange_halo_nccl(h, colour, h->comm_stream));
+        CU(cudaEventRecord(h->ev_comm, h->comm_stream));
+        ST(launch_half_v1(h, colour, sweep, ctr, 1, g.Tl - 2, h->stream));
+        CU(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    }
+    return LQFT_OK;
+}
+
+static lqft_status launch_observe(lqft_handle* h, bool moments) {
+    const Geom& g = h->g;
+    const uint32_t bd = block_for(g.plane);
+    dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
+    k_observe<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->obs_d, moments ? h->mom_d : nullptr);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return LQFT_OK;
+}
+
+static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint64_t* ctr,
+                                    int64_t explicit_site, int32_t only_chain) {
+    const Geom& g = h->g;
+    const uint32_t nc = h->cfg.n_chains;
+    k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d, nc,
+                                                         counter, ctr, explicit_site, only_chain, h->shift_d);
+    CU(cudaGetLastError());
+    ST(allreduce_i32(h, h->shift_d, nc));
+    const uint64_t n4 = g.chain_stride / 4 + 1;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n4 + 255) / 256, (uint64_t)h->sm_count * 8);
+    dim3 grid(blocks, 1, nc);
+    k_shift<<<grid, 256, 0, h->stream>>>(g.chain_stride, h->field[0], h->field[1], h->shift_d);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    return LQFT_OK;
+}
+
+static lqft_status ready(lqft_handle* h) {
+    if (!h) return fail(LQFT_ERR_INVALID, "null handle");
+    ST(use_device(h));
+    ST(upload_params(h));
+    ST(refresh_ghosts(h));
+    return LQFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// field I/O
+// ---------------------------------------------------------------------------------------------
+extern "C" lqft_status lqft_init_hot(lqft_handle* h) {
+    if (!h) return fail(LQFT_ERR_INVALID, "null handle");
+    ST(use_device(h));
+    ST(upload_params(h));
+    const Geom& g = h->g;
+    const uint32_t bd = block_for(g.plane);
+    dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
+    k_init_hot<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->ghosts_valid = false;
+    return LQFT_OK;
+}
+
+static lqft_status need_staging(lqft_handle* h) {
+    if (!h->staging_d) {
+        if (cudaMalloc(&h->staging_d, sizeof(int32_t) * h->n_slab) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(LQFT_ERR_NOMEM, "cannot allocate the %llu-byte staging buffer",
+                        (unsigned long long)(sizeof(int32_t) * h->n_slab));
+        }
+    }
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_upload(lqft_handle* h, uint32_t chain, const void* values) {
+    if (!h || !values) return fail(LQFT_ERR_INVALID, "null argument");
+    if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    ST(use_device(h));
+    ST(need_staging(h));
+    const Geom& g = h->g;
+    CU(cudaMemcpyAsync(h->staging_d, values, sizeof(int32_t) * h->n_slab, cudaMemcpyHostToDevice, h->stream));
+    const uint32_t bd = block_for(g.plane);
+    dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
+    k_split<<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
+                                        h->field[1] + (size_t)chain * g.chain_stride);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->ghosts_valid = false;
+    CU(cudaStreamSynchronize(h->stream));  // the host buffer may be reused on return
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_download(lqft_handle* h, uint32_t chain, void* values) {
+    if (!h || !values) return fail(LQFT_ERR_INVALID, "null argument");
+    if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    ST(use_device(h));
+    ST(need_staging(h));
+    const Geom& g = h->g;
+    const uint32_t bd = block_for(g.plane);
+    dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
+    k_merge<<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
+                                        h->field[1] + (size_t)chain * g.chain_stride);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    CU(cudaMemcpyAsync(values, h->staging_d, sizeof(int32_t) * h->n_slab, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LQFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// update
+// ---------------------------------------------------------------------------------------------
+static lqft_status read_accepted(lqft_handle* h, uint64_t* accepted) {
+    const uint32_t nc = h->cfg.n_chains;
+    std::vector<unsigned long long> slots((size_t)nc * kAccSlots);
+    CU(cudaMemcpyAsync(slots.data(), h->acc_d, sizeof(unsigned long long) * slots.size(),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * slots.size(), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (uint32_t c = 0; c < nc; ++c) {
+        uint64_t tot = 0;
+        for (int s = 0; s < kAccSlots; ++s) tot += slots[(size_t)c * kAccSlots + s];
+        accepted[c] = tot;
+    }
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_sweep(lqft_handle* h, uint64_t first_sweep, uint32_t n_sweeps, uint64_t* accepted) {
+    ST(ready(h));
+    if (accepted) CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * (size_t)h->cfg.n_chains * kAccSlots, h->stream));
+    CU(cudaEventRecord(h->ev_start, h->stream));
+    for (uint32_t s = 0; s < n_sweeps; ++s) ST(launch_sweep(h, first_sweep + s, nullptr));
+    CU(cudaEventRecord(h->ev_stop, h->stream));
+    h->timed = true;
+    if (accepted) ST(read_accepted(h, accepted));
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_normalize(lqft_handle* h, uint64_t sweep_index) {
+    ST(ready(h));
+    return launch_normalize(h, sweep_index, nullptr, -1, -1);
+}
+
+extern "C" lqft_status lqft_normalize_site(lqft_handle* h, uint32_t chain, uint64_t site) {
+    ST(ready(h));
+    if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    if (site >= h->n_global) return fail(LQFT_ERR_INVALID, "site %llu outside the lattice", (unsigned long long)site);
+    return launch_normalize(h, 0, nullptr, (int64_t)site, (int32_t)chain);
+}
+
+extern "C" lqft_status lqft_shift_values(lqft_handle* h, uint32_t chain, double shift) {
+    ST(ready(h));
+    if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    const int32_t s = (int32_t)shift;
+    if ((double)s != shift) return fail(LQFT_ERR_INVALID, "shift %g is not an i32 value", shift);
+    std::vector<int32_t> sh(h->cfg.n_chains, 0);
+    sh[chain] = s;
+    CU(cudaMemcpyAsync(h->shift_d, sh.data(), sizeof(int32_t) * sh.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const Geom& g = h->g;
+    const uint64_t n4 = g.chain_stride / 4 + 1;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n4 + 255) / 256, (uint64_t)h->sm_count * 8);
+    dim3 grid(blocks, 1, h->cfg.n_chains);
+    k_shift<<<grid, 256, 0, h->stream>>>(g.chain_stride, h->field[0], h->field[1], h->shift_d);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return LQFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// observables
+// ---------------------------------------------------------------------------------------------
+static lqft_status measure(lqft_handle* h, bool moments, std::vector<long long>& obs) {
+    const uint32_t nc = h->cfg.n_chains;
+    CU(cudaMemsetAsync(h->obs_d, 0, sizeof(unsigned long long) * (size_t)nc * 2, h->stream));
+    if (moments) CU(cudaMemsetAsync(h->mom_d, 0, sizeof(unsigned long long) * (size_t)nc * h->g.T * 2, h->stream));
+    ST(launch_observe(h, moments));
+    ST(allreduce_i64(h, h->obs_d, (size_t)nc * 2));
+    if (moments) ST(allreduce_i64(h, h->mom_d, (size_t)nc * h->g.T * 2));
+    obs.resize((size_t)nc * 2);
+    CU(cudaMemcpyAsync(obs.data(), h->obs_d, sizeof(long long) * obs.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_energy(lqft_handle* h, int64_t* e_int, double* e_obs) {
+    ST(ready(h));
+    std::vector<long long> obs;
+    ST(measure(h, false, obs));
+    for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
+        if (e_int) e_int[c] = obs[(size_t)c * 2];
+        if (e_obs) e_obs[c] = h->beta[c] * (double)obs[(size_t)c * 2];  // fields.rs:669-671
+    }
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_action(lqft_handle* h, int64_t* s_int, double* s_obs) {
+    ST(ready(h));
+    std::vector<long long> obs;
+    ST(measure(h, false, obs));
+    for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
+        if (s_int) s_int[c] = obs[(size_t)c * 2 + 1];
+        if (s_obs) s_obs[c] = h->beta[c] * (double)obs[(size_t)c * 2 + 1];  // fields.rs:665-667
+    }
+    return LQFT_OK;
+}
+
+static lqft_status fetch_moments(lqft_handle* h, uint32_t chain, std::vector<long long>& mom) {
+    std::vector<long long> obs;
+    ST(measure(h, true, obs));
+    const uint32_t T = h->g.T;
+    mom.resize((size_t)T * 2);
+    CU(cudaMemcpyAsync(mom.data(), h->mom_d + (size_t)chain * T * 2, sizeof(long long) * T * 2,
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_slice_moments(lqft_handle* h, uint32_t chain, int64_t* s1, int64_t* s2) {
+    ST(ready(h));
+    if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    std::vector<long long> mom;
+    ST(fetch_moments(h, chain, mom));
+    for (uint32_t t = 0; t < h->g.T; ++t) {
+        if (s1) s1[t] = mom[(size_t)t * 2];
+        if (s2) s2[t] = mom[(size_t)t * 2 + 1];
+    }
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_correlator(lqft_handle* h, uint32_t chain, const uint64_t* ref_sites,
+                                       uint32_t reps, uint64_t sweep_index, double* c_of_tau) {
+    ST(ready(h));
+    if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    if (!c_of_tau) return fail(LQFT_ERR_INVALID, "null output");
+    const Geom& g = h->g;
+    const uint32_t T = g.T;
+    std::vector<uint64_t> sites(reps);
+    const ChainDev& cd = h->chains_h[chain];
+    for (uint32_t r = 0; r < reps; ++r) {
+        sites[r] = ref_sites ? ref_sites[r]
+                             : pick_site(cd.k0, cd.k1, LQFT_STREAM_CORRELATOR, sweep_index, r, h->n_global);
+        if (sites[r] >= h->n_global)
+            return fail(LQFT_ERR_INVALID, "reference site %llu outside the lattice", (unsigned long long)sites[r]);
+    }
+    std::vector<long long> mom;
+    ST(fetch_moments(h, chain, mom));
+    std::vector<long long> hx(reps, 0);
+    if (reps) {
+        if (reps > h->sites_cap) {
+            cudaFree(h->sites_d); cudaFree(h->gathered_d);
+            h->sites_d = nullptr; h->gathered_d = nullptr; h->sites_cap = 0;
+            CU(cudaMalloc(&h->sites_d, sizeof(uint64_t) * reps));
+            CU(cudaMalloc(&h->gathered_d, sizeof(long long) * reps));
+            h->sites_cap = reps;
+        }
+        CU(cudaMemcpyAsync(h->sites_d, sites.data(), sizeof(uint64_t) * reps, cudaMemcpyHostToDevice, h->stream));
+        k_gather_sites<<<(reps + 127) / 128, 128, 0, h->stream>>>(
+            g, h->field[0] + (size_t)chain * g.chain_stride, h->field[1] + (size_t)chain * g.chain_stride,
+            h->sites_d, reps, h->gathered_d);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        ST(allreduce_i64(h, h->gathered_d, reps));
+        CU(cudaMemcpyAsync(hx.data(), h->gathered_d, sizeof(long long) * reps, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    // C[tau] = sum_rep sum_{y in slice t_x+tau} (h_x - h_y)^2 = A h_x^2 - 2 h_x S1 + S2   (exact, int64)
+    const long long A = (long long)g.X * g.Y;
+    std::vector<long long> c(T, 0);
+    for (uint32_t r = 0; r < reps; ++r) {
+        const uint32_t tx = (uint32_t)(sites[r] / ((uint64_t)g.X * g.Y));
+        const long long v = hx[r];
+        for (uint32_t tau = 0; tau < T; ++tau) {
+            const uint32_t t = (tx + tau) % T;
+            c[tau] += A * v * v - 2 * v * mom[(size_t)t * 2] + mom[(size_t)t * 2 + 1];
+        }
+    }
+    for (uint32_t tau = 0; tau < T; ++tau) c_of_tau[tau] = (double)c[tau];
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_difference_update(lqft_handle* h, uint32_t chain) {
+    ST(ready(h));
+    if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    const Geom& g = h->g;
+    const size_t bytes = sizeof(double) * 3 * h->n_slab;
+    if (!h->diff_sum[chain]) {
+        if (cudaMalloc(&h->diff_sum[chain], bytes) != cudaSuccess || cudaMalloc(&h->diff_comp[chain], bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(LQFT_ERR_NOMEM, "cannot allocate %zu bytes for the difference plot", 2 * bytes);
+        }
+        CU(cudaMemsetAsync(h->diff_sum[chain], 0, bytes, h->stream));
+        CU(cudaMemsetAsync(h->diff_comp[chain], 0, bytes, h->stream));
+    }
+    const uint32_t bd = block_for(g.plane);
+    dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
+    k_difference_update<<<grid, bd, 0, h->stream>>>(g, h->field[0] + (size_t)chain * g.chain_stride,
+                                                    h->field[1] + (size_t)chain * g.chain_stride,
+                                                    h->diff_sum[chain], h->diff_comp[chain]);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->diff_count[chain] += 1;
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_difference_read(lqft_handle* h, uint32_t chain, double* mean, uint64_t* count) {
+    if (!h) return fail(LQFT_ERR_INVALID, "null handle");
+    ST(use_device(h));
+    if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    const uint64_t n = h->diff_count[chain];
+    if (count) *count = n;
+    if (!mean) return LQFT_OK;
+    const size_t elems = 3 * h->n_slab;
+    if (!h->diff_sum[chain]) {
+        for (size_t i = 0; i < elems; ++i) mean[i] = 0.0;  // WelfordsAlgorithm64::get_mean with 0 entries
+        return LQFT_OK;
+    }
+    CU(cudaMemcpyAsync(mean, h->diff_sum[chain], sizeof(double) * elems, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < elems; ++i) mean[i] = mean[i] / (double)n;  // kahan.rs:90-95
+    return LQFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused schedule (computation.rs:229-270, 313-340)
+// ---------------------------------------------------------------------------------------------
+static lqft_status launch_energy_log(lqft_handle* h) {
+    ST(launch_observe(h, false));
+    ST(allreduce_i64(h, h->obs_d, (size_t)h->cfg.n_chains * 2));
+    k_energy_log<<<1, 128, 0, h->stream>>>(h->obs_d, h->elog_d, h->elog_cap, h->cfg.n_chains, h->n_meas_d);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return LQFT_OK;
+}
+
+// One step of the schedule: sweep, then energy if due, then normalize if due.
+static lqft_status launch_step(lqft_handle* h, const lqft_schedule* s, uint64_t step_arg,
+                               uint64_t step_for_gating, const uint64_t* ctr) {
+    ST(launch_sweep(h, s->sweep_base + step_arg, ctr));
+    if (s->energy_every && step_for_gating % s->energy_every == 0) ST(launch_energy_log(h));
+    if (s->normalize_every && step_for_gating % s->normalize_every == 0)
+        ST(launch_normalize(h, s->sweep_base + step_arg, ctr, -1, -1));
+    return LQFT_OK;
+}
+
+static uint64_t gcd64(uint64_t a, uint64_t b) { return b ? gcd64(b, a % b) : a; }
+
+extern "C" lqft_status lqft_run(lqft_handle* h, const lqft_schedule* s, double* e_obs, int64_t* e_int,
+                                uint64_t* accepted) {
+    if (!s) return fail(LQFT_ERR_INVALID, "null schedule");
+    ST(ready(h));
+    const uint32_t nc = h->cfg.n_chains;
+    const uint64_t n_meas = lqft_run_measurements(s->first_step, s->n_steps, s->energy_every);
+    if (n_meas > 0xffffffffull) return fail(LQFT_ERR_INVALID, "too many measurements in one run");
+    if (n_meas > h->elog_cap) {
+        cudaFree(h->elog_d);
+        h->elog_d = nullptr;
+        h->elog_cap = 0;
+        if (cudaMalloc(&h->elog_d, sizeof(long long) * (size_t)nc * n_meas) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(LQFT_ERR_NOMEM, "cannot allocate the energy log");
+        }
+        h->elog_cap = (uint32_t)n_meas;
+        for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+        h->graphs.clear();  // graphs bake the log pointer and capacity
+    }
+    CU(cudaMemsetAsync(h->n_meas_d, 0, sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->obs_d, 0, sizeof(unsigned long long) * (size_t)nc * 2, h->stream));
+    if (accepted) CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * (size_t)nc * kAccSlots, h->stream));
+
+    const uint64_t ee = s->energy_every ? s->energy_every : 1, ne = s->normalize_every ? s->normalize_every : 1;
+    const uint64_t cycle = ee / gcd64(ee, ne) * ne;
+    const bool use_graph = !(h->cfg.flags & LQFT_FLAG_NO_GRAPH) && h->cfg.world_size <= 1 && cycle <= 64 &&
+                           s->n_steps >= 2 * cycle;
+
+    CU(cudaEventRecord(h->ev_start, h->stream));
+    uint64_t step = s->first_step;
+    const uint64_t end = s->first_step + s->n_steps;
+    if (use_graph) {
+        while (step < end && step % cycle != 0) {
+            ST(launch_step(h, s, step, step, nullptr));
+            ++step;
+        }
+        const uint64_t n_cycles = (end - step) / cycle;
+        if (n_cycles) {
+            GraphKey key{s->energy_every, s->normalize_every, (uint32_t)cycle};
+            auto it = h->graphs.find(key);
+            if (it == h->graphs.end()) {
+                // capture one cycle; every kernel reads the sweep counter from device memory
+                const uint64_t before = h->launches;
+                lqft_schedule rel = *s;
+                rel.sweep_base = 0;
+                cudaGraph_t graph = nullptr;
+                CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                lqft_status st = LQFT_OK;
+                for (uint64_t i = 0; i < cycle && st == LQFT_OK; ++i) st = launch_step(h, &rel, i, i, h->sweep_ctr_d);
+                if (st == LQFT_OK) {
+                    k_tick<<<1, 1, 0, h->stream>>>(h->sweep_ctr_d, cycle);
+                    h->launches += 1;
+                }
+                cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                if (st != LQFT_OK) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return st;
+                }
+                if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+                GraphVal val;
+                val.kernels = h->launches - before;
+                h->launches = before;
+                ce = cudaGraphInstantiate(&val.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+                it = h->graphs.emplace(key, val).first;
+            }
+            const uint64_t base = s->sweep_base + step;
+            CU(cudaMemcpyAsync(h->sweep_ctr_d, &base, sizeof base, cudaMemcpyHostToDevice, h->stream));
+            for (uint64_t c = 0; c < n_cycles; ++c) CU(cudaGraphLaunch(it->second.exec, h->stream));
+            h->launches += it->second.kernels * n_cycles;
+            step += n_cycles * cycle;
+        }
+    }
+    while (step < end) {
+        ST(launch_step(h, s, step, step, nullptr));
+        ++step;
+    }
+    CU(cudaEventRecord(h->ev_stop, h->stream));
+    h->timed = true;
+
+    if (n_meas && (e_obs || e_int)) {
+        std::vector<long long> log((size_t)nc * h->elog_cap);
+        CU(cudaMemcpyAsync(log.data(), h->elog_d, sizeof(long long) * log.size(), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (uint32_t c = 0; c < nc; ++c)
+            for (uint64_t m = 0; m < n_meas; ++m) {
+                const long long e = log[(size_t)c * h->elog_cap + m];
+                if (e_int) e_int[(size_t)c * n_meas + m] = e;
+                if (e_obs) e_obs[(size_t)c * n_meas + m] = h->beta[c] * (double)e;
+            }
+    }
+    if (accepted) ST(read_accepted(h, accepted));
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_synchronize(lqft_handle* h) {
+    if (!h) return fail(LQFT_ERR_INVALID, "null handle");
+    ST(use_device(h));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->comm_stream));
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_last_device_ms(lqft_handle* h, float* ms) {
+    if (!h || !ms) return fail(LQFT_ERR_INVALID, "null argument");
+    if (!h->timed) return fail(LQFT_ERR_STATE, "no timed call yet");
+    ST(use_device(h));
+    CU(cudaEventSynchronize(h->ev_stop));
+    CU(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_kernel_launches(lqft_handle* h, uint64_t* n) {
+    if (!h || !n) return fail(LQFT_ERR_INVALID, "null argument");
+    *n = h->launches;
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_stream(lqft_handle* h, void** stream) {
+    if (!h || !stream) return fail(LQFT_ERR_INVALID, "null argument");
+    *stream = (void*)h->stream;
+    return LQFT_OK;
+}
