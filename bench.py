@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — site updates/sec of the red-black Metropolis sweep (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N = 1 : the throughput micro-config of SURVEY.md §8(d): one 256^3 i32 chain, beta = 0.25,
+        pre-thermalised by 200 sweeps from the seeded hot start.
+N > 1 : the same 256 x 256 cross-section, 256 t-planes per GPU (lattice 256 x 256 x 256N),
+        slab-decomposed along t with halo exchange: weak scaling of the headline config.
+A "step" is SWEEPS_PER_STEP full sweeps of the whole lattice.  `value` is measured with the field
+resident in HBM; `e2e` goes through the C ABI with host buffers (upload from pinned memory, the
+Simulation::run loop body with energy every 10th sweep, download of field + energies).
+
+--impl reference times the CPU restatement of the reference's own data path (oracle/, "port": the
+reference is Rust and cannot be built here) on all host cores, one independent chain per core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+X = Y = 256
+T_PER_GPU = 256
+BETA = 0.25
+SEED = 0xC0FFEE
+THERMALISE = 200
+SWEEPS_PER_STEP = 100
+BYTES_PER_UPDATE = 8  # one i32 read + one i32 write per site update
+METRIC = "site updates/sec"
+UNIT = "site-updates/s"
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_sample(threads: int, sweeps: int, x: int, y: int, t: int):
+    """Oracle port of the reference data path, one independent chain per thread."""
+    from oracle import oracle as O
+    lat = O.Lattice([x, y, t])
+    secs, _ = O.bench_chains(lat, BETA, SEED, sweeps, 10, threads)
+    updates = float(threads) * sweeps * lat.n_sites
+    return updates / secs, secs
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    # bounded sample of the 256^3 workload: each step = one lexicographic sweep of a 256 x 256 x 16
+    # slab-sized lattice per core (same row/plane strides as 256^3; the full 805 MB neighbour table of
+    # 256^3 would only add build time), all cores busy, like sim.rs's rayon pool.
+    t_sample = 16
+    lat = O.Lattice([X, Y, t_sample])
+    for _ in range(args.warmup):
+        O.bench_chains(lat, BETA, SEED, 1, 10, cores)
+    t0 = time.time()
+    secs = 0.0
+    for _ in range(args.steps):
+        s, _ = O.bench_chains(lat, BETA, SEED, 1, 10, cores)
+        secs += s
+    updates = float(cores) * args.steps * lat.n_sites
+    value = updates / secs
+    sample = (f"{cores} independent chains x {args.steps} lexicographic sweeps of {X}x{Y}x{t_sample} "
+              f"(neighbour-table i32 path of algorithm.rs:117-157), wall {time.time() - t0:.1f}s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int):
+    t = T_PER_GPU * n_gpus
+    return {
+        "workload": f"{X}x{Y}x{t} periodic lattice, 1 chain, i32 heights, beta={BETA}, red-black Metropolis, "
+                    f"{SWEEPS_PER_STEP} sweeps per step, pre-thermalised {THERMALISE} sweeps from seeded hot start",
+        "lattice": [X, Y, t], "sweeps_per_step": SWEEPS_PER_STEP, "beta": BETA,
+        "decomposition": "none" if n_gpus == 1 else f"t-slabs of {T_PER_GPU} planes per GPU, halo exchange per colour",
+        "l2": "L2 flushed (256 MiB write) between timed steps; the 64 MiB/GPU field itself is L2-resident by nature",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="LQFT_FLAG_* for experiments")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lattice_qft_b200 import Engine
+    from lattice_qft_b200 import engine as E
+
+    if not torch.cuda.is_available() or E.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: lattice_qft_b200 has no CPU fallback")
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} must be launched with torchrun --nproc-per-node {args.gpus}")
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.tensor(list(E.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        nccl_id = bytes(buf.cpu().tolist())
+
+    t_global = T_PER_GPU * world
+    eng = Engine(X, Y, t_global, n_chains=1, device=local_rank, world_size=world, rank=rank, nccl_id=nccl_id,
+                 flags=args.flags)
+    eng.set_chain(0, BETA, SEED)
+    eng.init_hot()
+    eng.sweep(0, THERMALISE)
+    eng.synchronize()
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    n_local = eng.n_slab
+    sweep_ctr = THERMALISE
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    # ---------------- device-resident value -------------------------------------------------------
+    for _ in range(args.warmup):
+        eng.sweep(sweep_ctr, SWEEPS_PER_STEP)
+        sweep_ctr += SWEEPS_PER_STEP
+    launches0 = eng.kernel_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    for a, b in ev:
+        flush_l2()
+        a.record(stream)
+        eng.sweep(sweep_ctr, SWEEPS_PER_STEP)
+        b.record(stream)
+        sweep_ctr += SWEEPS_PER_STEP
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.kernel_launches() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    total_updates = float(X) * Y * t_global * SWEEPS_PER_STEP * args.steps
+    value = total_updates / (ms * 1e-3)
+
+    # ---------------- end to end through the C ABI with host buffers ---------------------------------
+    host_in = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+    host_out = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+    np_in, np_out = host_in.numpy(), host_out.numpy()
+    eng.download(0, np_in)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step(base):
+        eng.upload(0, np_in)                                   # H2D from pinned memory
+        e_obs, _, _ = eng.run(SWEEPS_PER_STEP, first_step=0, sweep_base=base, energy_every=10, normalize_every=10)
+        eng.download(0, np_out)                                # D2H of the step's result
+        return e_obs
+
+    for i in range(2):
+        e2e_step(sweep_ctr)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e_obs = e2e_step(sweep_ctr + i * SWEEPS_PER_STEP)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = float(X) * Y * t_global * SWEEPS_PER_STEP * e2e_steps / float(te.item())
+    h2d = n_local * 4
+    d2h = n_local * 4 + int(e_obs.size) * 8
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        n_sweep_launches = 2 * SWEEPS_PER_STEP * args.steps  # per rank, dominant kernel: half-sweep
+        per_launch_s = (ms * 1e-3) / n_sweep_launches
+        alg_bytes_per_launch = BYTES_PER_UPDATE * (n_local / 2)
+        achieved = alg_bytes_per_launch / per_launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "i32", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps,
+                    "what": "lqft_upload(pinned host field) + lqft_run(100 steps: sweep, energy every 10th, "
+                            "normalize every 10th) + lqft_download(field) per step, wall clock"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "half-sweep (one colour) of the red-black Metropolis sweep",
+                         "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                         "avg_launch_us": per_launch_s * 1e6},
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, secs = cpu_baseline_sample(cores, 2, X, Y, 16)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{cores} independent chains x 2 lexicographic sweeps of {X}x{Y}x16 ({secs:.1f}s); "
+                          "C restatement of the reference's neighbour-table i32 path (oracle/lqft_oracle.c)"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

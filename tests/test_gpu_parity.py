@@ -1,0 +1,308 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: bit-exact post-sweep fields on
+the same seeded inputs and the same per-site uniforms, exact integer observables, committed golden
+vectors, and size-independent properties at BASELINE.json's full sizes."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from lattice_qft_b200 import Engine, _lib
+from lattice_qft_b200 import engine as E
+from oracle import oracle as O
+from conftest import seeded_field
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _golden():
+    with open(os.path.join(GOLDEN, "sweep_golden.json")) as fh:
+        return json.load(fh)
+
+
+def oracle_sweeps(size, v, beta, seed, first, n, wilson=(0, 0)):
+    lat = O.Lattice(size)
+    wil = O.Wilson(lat, *wilson) if wilson[0] and wilson[1] else None
+    acc = 0
+    for s in range(first, first + n):
+        acc += O.sweep(lat, v, beta, seed, s, order=1, wilson=wil)
+    return acc
+
+
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC, _lib.FLAG_FORCE_V1])
+@pytest.mark.parametrize("name", sorted(_golden()))
+def test_sweep_matches_golden_vectors(name, flags):
+    g = _golden()[name]
+    X, Y, T = g["size"]
+    with Engine(X, Y, T, flags=flags) as eng:
+        eng.set_chain(0, g["beta"], g["seed"], *g["wilson"])
+        eng.upload(0, seeded_field(X * Y * T))
+        acc = [eng.sweep(s, 1, want_accepted=True)[0] for s in range(g["sweeps"])]
+        v = eng.download(0)
+        assert acc == g["accepted"]
+        assert hashlib.sha256(v.tobytes()).hexdigest() == g["field_sha256"]
+        assert int(eng.energy()[0][0]) == g["e_int"]
+        assert float(eng.action()[0][0]) == g["s_float"]
+        assert eng.correlator(0, ref_sites=g["corr_sites"]).tolist() == g["corr"]
+        assert eng.correlator(0, reps=5, sweep_index=7).tolist() == g["corr"]  # device-side site picks
+
+
+@pytest.mark.parametrize("size,beta,wilson", [
+    ((16, 16, 16), 0.2, (0, 0)), ((8, 8, 8), 0.29, (0, 0)), ((4, 6, 8), 0.25, (0, 0)),
+    ((32, 16, 8), 0.22, (0, 0)), ((10, 12, 6), 0.4, (0, 0)), ((54, 2, 4), 0.24, (0, 0)),
+    ((16, 16, 16), 0.26, (8, 16)), ((24, 6, 4), 0.21, (13, 3)), ((8, 2, 2), 0.3, (8, 2)),
+    ((64, 4, 4), 0.25, (21, 4)), ((2, 2, 2), 0.2, (1, 1)),
+])
+def test_sweep_bit_exact_vs_oracle(size, beta, wilson):
+    X, Y, T = size
+    seed = 0xC0FFEE + X
+    v0 = seeded_field(X * Y * T, seed=X * 1000 + Y)
+    want = v0.copy()
+    want_acc = oracle_sweeps(size, want, beta, seed, 3, 4, wilson)
+    for flags in (0, _lib.FLAG_FORCE_GENERIC):
+        with Engine(X, Y, T, flags=flags) as eng:
+            eng.set_chain(0, beta, seed, *wilson)
+            eng.upload(0, v0)
+            got_acc = eng.sweep(3, 4, want_accepted=True)[0]
+            got = eng.download(0)
+        assert (got == want).all(), f"{int((got != want).sum())} sites differ (flags={flags})"
+        assert got_acc == want_acc
+
+
+def test_hot_start_matches_oracle():
+    with Engine(16, 8, 4) as eng:
+        eng.set_chain(0, 0.2, 99)
+        eng.init_hot()
+        got = eng.download(0)
+    want = O.init_hot(O.Lattice([16, 8, 4]), 99)
+    assert (got == want).all() and got.min() >= -128 and got.max() <= 127
+
+
+def test_upload_download_roundtrip_and_edge_values():
+    v = seeded_field(8 * 6 * 4, lo=-2**20, hi=2**20)
+    with Engine(8, 6, 4) as eng:
+        eng.set_chain(0, 0.2, 1)
+        eng.upload(0, v)
+        assert (eng.download(0) == v).all()
+
+
+def test_batched_chains_are_independent():
+    """64 chains in one handle (config 2 layout) == 64 single-chain oracles."""
+    X = Y = T = 8
+    n_chains = 6
+    betas = [0.20 + 0.005 * c for c in range(n_chains)]
+    seeds = [0xC0FFEE + c for c in range(n_chains)]
+    with Engine(X, Y, T, n_chains=n_chains) as eng:
+        for c in range(n_chains):
+            eng.set_chain(c, betas[c], seeds[c], 3 if c == 4 else 0, 4 if c == 4 else 0)
+        eng.init_hot()
+        acc = eng.sweep(0, 3, want_accepted=True)
+        e_int, e_obs = eng.energy()
+        s_int, _ = eng.action()
+        for c in range(n_chains):
+            lat = O.Lattice([X, Y, T])
+            want = O.init_hot(lat, seeds[c])
+            wacc = oracle_sweeps((X, Y, T), want, betas[c], seeds[c], 0, 3, (3, 4) if c == 4 else (0, 0))
+            assert (eng.download(c) == want).all(), c
+            assert acc[c] == wacc
+            assert int(e_int[c]) == O.integer_energy(lat, want)[0]
+            assert e_obs[c] == O.energy_observable(lat, want, betas[c])
+            assert float(s_int[c]) == O.float_action(lat, want)
+
+
+def test_observables_exact():
+    X, Y, T = 12, 10, 8
+    lat = O.Lattice([X, Y, T])
+    v = seeded_field(lat.n_sites, seed=5)
+    with Engine(X, Y, T) as eng:
+        eng.set_chain(0, 0.27, 1)
+        eng.upload(0, v)
+        e_int, e_obs = eng.energy()
+        s_int, s_obs = eng.action()
+        s1, s2 = eng.slice_moments(0)
+    assert int(e_int[0]) == O.integer_energy(lat, v)[0]
+    assert e_obs[0] == O.energy_observable(lat, v, 0.27)
+    assert float(s_int[0]) == O.float_action(lat, v) and s_obs[0] == O.action_observable(lat, v, 0.27)
+    f = v.reshape(T, Y * X).astype(np.int64)
+    assert (s1 == f.sum(axis=1)).all() and (s2 == (f * f).sum(axis=1)).all()
+
+
+def test_energy_int64_superset_of_i32_quirk():
+    """Q5: the reference's i32 accumulator holds the low 32 bits of the exact sum."""
+    X = Y = T = 8
+    v = (np.arange(512, dtype=np.int64) % 2 * 40000).astype(np.int32)
+    lat = O.Lattice([X, Y, T])
+    exact, wrapped = O.integer_energy(lat, v)
+    with Engine(X, Y, T) as eng:
+        eng.set_chain(0, 0.2, 1)
+        eng.upload(0, v)
+        e = int(eng.energy()[0][0])
+    assert e == exact and np.int64(e).astype(np.int32) == wrapped != exact
+
+
+def test_correlator_matches_reference_loop():
+    X, Y, T = 8, 6, 10
+    lat = O.Lattice([X, Y, T])
+    v = seeded_field(lat.n_sites, seed=8)
+    sites = [int(s) for s in np.random.default_rng(4).integers(0, lat.n_sites, 100)]
+    with Engine(X, Y, T) as eng:
+        eng.set_chain(0, 0.25, 321)
+        eng.upload(0, v)
+        got = eng.correlator(0, ref_sites=sites)
+        got_auto = eng.correlator(0, reps=100, sweep_index=40)
+    assert (got == O.correlator(lat, v, sites)).all()
+    auto_sites = [O.pick_site(321, 4, 40, r, lat.n_sites) for r in range(100)]
+    assert (got_auto == O.correlator(lat, v, auto_sites)).all()
+
+
+def test_normalize_and_shift():
+    X, Y, T = 8, 8, 4
+    lat = O.Lattice([X, Y, T])
+    v = seeded_field(lat.n_sites, seed=6)
+    with Engine(X, Y, T, n_chains=2) as eng:
+        eng.set_chain(0, 0.2, 10)
+        eng.set_chain(1, 0.2, 11)
+        eng.upload(0, v)
+        eng.upload(1, v)
+        eng.normalize(17)
+        for c, seed in ((0, 10), (1, 11)):
+            site = O.pick_site(seed, 2, 17, 0, lat.n_sites)
+            want = v.copy()
+            O.shift_values(want, int(v[site]))
+            got = eng.download(c)
+            assert (got == want).all() and got[site] == 0
+        eng.upload(0, v)
+        eng.normalize_site(0, 5)
+        assert (eng.download(0) == v - v[5]).all() and (eng.download(1) == v - v[O.pick_site(11, 2, 17, 0, lat.n_sites)]).all()
+        eng.upload(0, v)
+        eng.shift_values(0, 3)  # fields.rs:851-861
+        assert (eng.download(0) == v - 3).all()
+
+
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_GRAPH])
+@pytest.mark.parametrize("first_step,n_steps,energy_every", [(0, 50, 10), (3, 44, 10), (0, 25, 1), (7, 30, 4), (0, 12, 0)])
+def test_run_schedule_matches_oracle(first_step, n_steps, energy_every, flags):
+    """lqft_run == loop body of Simulation::run (computation.rs:249-270), graph replay included."""
+    X, Y, T = 8, 8, 8
+    lat = O.Lattice([X, Y, T])
+    beta, seed, base = 0.23, 555, 1000
+    want = O.init_hot(lat, seed)
+    we, wacc = O.run(lat, want, beta, seed, base, first_step, n_steps, energy_every, 10, order=1)
+    with Engine(X, Y, T, flags=flags) as eng:
+        eng.set_chain(0, beta, seed)
+        eng.init_hot()
+        e_obs, e_int, acc = eng.run(n_steps, first_step=first_step, sweep_base=base, energy_every=energy_every,
+                                    normalize_every=10, want_accepted=True)
+        got = eng.download(0)
+    assert (got == want).all()
+    assert e_obs.shape == (1, len(we)) and (e_obs[0] == we).all()
+    assert acc[0] == wacc
+
+
+def test_run_wilson_chain_measures_plain_field():
+    """WilsonSim: Wilson-shifted sampling, energy of the plain field every step (quirks Q3, Q4)."""
+    X, Y, T = 8, 8, 8
+    lat = O.Lattice([X, Y, T])
+    wil = O.Wilson(lat, 4, 8)
+    want = O.init_hot(lat, 9)
+    we, _ = O.run(lat, want, 0.26, 9, 0, 0, 30, 1, 10, order=1, wilson=wil)
+    with Engine(X, Y, T) as eng:
+        eng.set_chain(0, 0.26, 9, 4, 8)
+        eng.init_hot()
+        e_obs, _, _ = eng.run(30, energy_every=1)
+        assert (eng.download(0) == want).all()
+    assert (e_obs[0] == we).all()
+
+
+def test_difference_plot_matches_welford():
+    X, Y, T = 6, 4, 4
+    lat = O.Lattice([X, Y, T])
+    v = seeded_field(lat.n_sites, seed=12)
+    wel = O.new_welford_cells(3 * lat.n_sites)
+    with Engine(X, Y, T) as eng:
+        eng.set_chain(0, 0.2, 4)
+        eng.upload(0, v)
+        for s in range(7):
+            eng.sweep(s, 1)
+            cur = eng.download(0)
+            eng.difference_update(0)
+            O.difference_update(lat, cur, wel)
+        mean, count = eng.difference_read(0)
+    assert count == 7
+    assert (mean.reshape(-1) == O.difference_means(lat, wel)).all()
+
+
+def test_generic_and_vector_kernels_agree_at_64cubed():
+    X = Y = T = 64
+    with Engine(X, Y, T) as a, Engine(X, Y, T, flags=_lib.FLAG_FORCE_GENERIC) as b, \
+            Engine(X, Y, T, flags=_lib.FLAG_FORCE_V1) as c:
+        for e in (a, b, c):
+            e.set_chain(0, 0.25, 2024, 21, 32)
+            e.init_hot()
+            e.sweep(0, 6)
+        va, vb, vc = a.download(0), b.download(0), c.download(0)
+        assert (va == vb).all() and (va == vc).all()
+        assert a.energy()[0][0] == b.energy()[0][0]
+
+
+def test_oracle_parity_at_64cubed_one_sweep():
+    X = Y = T = 64
+    lat = O.Lattice([X, Y, T])
+    want = O.init_hot(lat, 31337)
+    acc_w = O.sweep(lat, want, 0.25, 31337, 0, order=1)
+    with Engine(X, Y, T) as eng:
+        eng.set_chain(0, 0.25, 31337)
+        eng.init_hot()
+        acc = eng.sweep(0, 1, want_accepted=True)[0]
+        assert (eng.download(0) == want).all() and acc == acc_w
+
+
+# ---- full-size, size-independent properties -------------------------------------------------------
+def test_256cubed_properties():
+    X = Y = T = 256
+    n = X * Y * T
+    with Engine(X, Y, T) as eng, Engine(X, Y, T, flags=_lib.FLAG_FORCE_GENERIC) as ref:
+        for e in (eng, ref):
+            e.set_chain(0, 0.25, 7)
+            e.init_hot()
+        v0 = eng.download(0)
+        assert v0.min() == -128 and v0.max() == 127
+        # round trip of the layout conversion at full size
+        eng.upload(0, v0)
+        assert (eng.download(0) == v0).all()
+        acc = eng.sweep(0, 3, want_accepted=True)[0]
+        ref.sweep(0, 3)
+        v = eng.download(0)
+        assert (v == ref.download(0)).all()           # two independent kernels agree bit for bit
+        assert 0 < acc <= 3 * n
+        assert np.abs(v.astype(np.int64) - v0).max() <= 3  # +-1 per sweep
+        # shift invariance of every observable (the action only sees differences)
+        e0, s0 = int(eng.energy()[0][0]), int(eng.action()[0][0])
+        s1, s2 = eng.slice_moments(0)
+        assert s1.sum() == int(v.astype(np.int64).sum()) and s2.sum() == int((v.astype(np.int64) ** 2).sum())
+        eng.normalize(0)
+        assert int(eng.energy()[0][0]) == e0 and int(eng.action()[0][0]) == s0
+        # RNG keyed by (seed, sweep, site): same sweep index twice from the same state == same result
+        eng.upload(0, v0)
+        eng.sweep(0, 3)
+        assert (eng.download(0) == v).all()
+
+
+def test_error_behaviour():
+    from lattice_qft_b200 import LqftError
+    with pytest.raises(LqftError) as ei:
+        Engine(15, 16, 16)
+    assert ei.value.status == _lib.LQFT_ERR_INVALID
+    with Engine(4, 4, 4) as eng:
+        with pytest.raises(LqftError) as ei:
+            eng.sweep(0, 1)  # chain not configured
+        assert ei.value.status == _lib.LQFT_ERR_STATE
+        with pytest.raises(LqftError):
+            eng.set_chain(0, -1.0, 0)
+        with pytest.raises(LqftError):
+            eng.set_chain(1, 0.2, 0)
+        eng.set_chain(0, 0.2, 0)
+        with pytest.raises(LqftError):
+            eng.normalize_site(0, 64)
