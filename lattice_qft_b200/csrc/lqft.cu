@@ -494,18 +494,26 @@ static inline uint32_t block_for(uint32_t units) {
 }
 
 // One half-sweep of colour `colour` over local planes tl_first .. tl_first + n_planes - 1.
-static lqft_status launch_half_v1(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr,
-                                  uint32_t tl_first, uint32_t n_planes, cudaStream_t s) {
+static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr,
+                               uint32_t tl_first, uint32_t n_planes, cudaStream_t s) {
     if (n_planes == 0) return LQFT_OK;
     const Geom& g = h->g;
+    int32_t* own = h->field[colour];
+    const int32_t* oth = h->field[colour ^ 1];
+    if (h->tiled.enabled) {
+        RoundKeys rk;
+        const bool single = h->cfg.n_chains == 1;
+        if (single) rk = make_round_keys(h->chains_h[0].k0, h->chains_h[0].k1);
+        CU(tiled_half(h->tiled, g, colour, sweep, ctr, tl_first, n_planes, h->cfg.n_chains, own, oth, h->chains_d,
+                      h->thr_d, h->acc_d, h->max_thr, h->any_wilson, single ? &rk : nullptr, s));
+        h->launches += 1;
+        return LQFT_OK;
+    }
     const bool vec = (g.X % 8 == 0) && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC);
     const uint32_t units = vec ? g.plane / 4 : g.plane;
     const uint32_t bd = block_for(units);
     dim3 grid((units + bd - 1) / bd, n_planes, h->cfg.n_chains);
     const size_t smem = sizeof(uint32_t) * h->max_thr;
-    int32_t* own = h->field[colour];
-    const int32_t* oth = h->field[colour ^ 1];
-    (void)ctr;
 #define LAUNCH(K)                                                                                    \
     K<<<grid, bd, smem, s>>>(g, colour, sweep, ctr, tl_first, own, oth, h->chains_d, h->thr_d, h->acc_d)
     if (vec) {
@@ -523,24 +531,19 @@ static lqft_status launch_half_v1(lqft_handle* h, int colour, uint64_t sweep, co
 static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* ctr) {
     const Geom& g = h->g;
     if (h->cfg.world_size <= 1) {
-        if (h->tiled.enabled) {
-            CU(tiled_sweep(h->tiled, g, h->field, sweep, ctr, h->chains_d, h->thr_d, h->acc_d, h->max_thr,
-                           h->any_wilson, h->stream, &h->launches));
-            return LQFT_OK;
-        }
-        ST(launch_half_v1(h, 0, sweep, ctr, 0, g.Tl, h->stream));
-        ST(launch_half_v1(h, 1, sweep, ctr, 0, g.Tl, h->stream));
+        ST(launch_half(h, 0, sweep, ctr, 0, g.Tl, h->stream));
+        ST(launch_half(h, 1, sweep, ctr, 0, g.Tl, h->stream));
         return LQFT_OK;
     }
     // slab: boundary planes first, exchange on the comm stream while the interior updates
     for (int colour = 0; colour < 2; ++colour) {
-        ST(launch_half_v1(h, colour, sweep, ctr, 0, 1, h->stream));
-        ST(launch_half_v1(h, colour, sweep, ctr, g.Tl - 1, 1, h->stream));
+        ST(launch_half(h, colour, sweep, ctr, 0, 1, h->stream));
+        ST(launch_half(h, colour, sweep, ctr, g.Tl - 1, 1, h->stream));
         CU(cudaEventRecord(h->ev_bnd, h->stream));
         CU(cudaStreamWaitEvent(h->comm_stream, h->ev_bnd, 0));
         ST(exchange_halo_nccl(h, colour, h->comm_stream));
         CU(cudaEventRecord(h->ev_comm, h->comm_stream));
-        ST(launch_half_v1(h, colour, sweep, ctr, 1, g.Tl - 2, h->stream));
+        ST(launch_half(h, colour, sweep, ctr, 1, g.Tl - 2, h->stream));
         CU(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
     }
     return LQFT_OK;
