@@ -25,22 +25,12 @@ namespace lqft {
 
 constexpr int kMarchWarps = 4;  // warps (= t-planes) per block
 
-// Round keys of Philox4x32-10 (key + r * W).  For single-chain handles they travel as a kernel
-// parameter, so every LOP3 of the cipher reads its key straight from the constant bank.
+// Round keys of Philox4x32-10 (key + r * W), computed once per thread and kept in registers.
 struct RoundKeys {
     uint32_t k[kPhiloxRounds][2];
 };
 
-inline RoundKeys make_round_keys(uint32_t k0, uint32_t k1) {
-    RoundKeys rk;
-    for (int r = 0; r < kPhiloxRounds; ++r) {
-        rk.k[r][0] = k0 + (uint32_t)r * kPhiloxW0;
-        rk.k[r][1] = k1 + (uint32_t)r * kPhiloxW1;
-    }
-    return rk;
-}
-
-__device__ __forceinline__ RoundKeys make_round_keys_dev(uint32_t k0, uint32_t k1) {
+__device__ __forceinline__ RoundKeys make_round_keys(uint32_t k0, uint32_t k1) {
     RoundKeys rk;
 #pragma unroll
     for (int r = 0; r < kPhiloxRounds; ++r) {
@@ -63,13 +53,12 @@ __device__ __forceinline__ u32x4 philox4x32_rk(uint32_t c0, uint32_t c1, uint32_
     return u32x4{c0, c1, c2, c3};
 }
 
-// Two-sided threshold table in shared memory, indexed by the clamped d = 6v - sum_n + off:
-//   s_tab[0][d + kc] (coin = down, m = -d) = thr(-d)
-//   s_tab[1][d + kc] (coin = up,   m = +d) = thr(+d) | 0x80000000
-// so that "u <= thr[clamp(m+3)]" becomes the single unsigned compare  r <= s_tab[coin][d + kc]
-// (for coin = up bit 31 of r is set on both sides).  Same decisions as metropolis_delta.
-__device__ __forceinline__ uint32_t build_two_sided(uint32_t* s_tab, const uint32_t* __restrict__ thr,
-                                                    uint32_t n_thr) {
+// Two-sided decision table in shared memory, indexed by (coin, clamped d = 6v - sum_n + off):
+//   down half, entry d + kc : { thr(m = -d),              -1 }
+//   up   half, entry d + kc : { thr(m = +d) | 0x80000000, +1 }
+// so "u <= thr[clamp(m+3)]" is the single unsigned compare  r <= entry.x  (for coin = up bit 31 of
+// r is set on both sides) and the accepted step is entry.y.  Same decisions as metropolis_delta.
+__device__ __forceinline__ int build_two_sided(uint2* s_tab, const uint32_t* __restrict__ thr, uint32_t n_thr) {
     const int kc = max((int)n_thr - 1, 3);
     const int width = 2 * kc + 1;
     for (int i = threadIdx.x; i < 2 * width; i += blockDim.x) {
@@ -77,39 +66,96 @@ __device__ __forceinline__ uint32_t build_two_sided(uint32_t* s_tab, const uint3
         const int d = (up ? i - width : i) - kc;
         const int m = up ? d : -d;
         const int k = min(max(m + 3, 0), (int)n_thr - 1);
-        s_tab[i] = thr[k] | (up ? 0x80000000u : 0u);
+        s_tab[i] = make_uint2(thr[k] | (up ? 0x80000000u : 0u), up ? 1u : 0xffffffffu);
     }
     __syncthreads();
-    return (uint32_t)kc;
+    return kc;
 }
 
-__device__ __forceinline__ int metropolis_delta2(int v, int nsum, int off, uint32_t r,
-                                                 const uint32_t* __restrict__ s_dn,
-                                                 const uint32_t* __restrict__ s_up, int kc) {
+template <bool COUNT>
+__device__ __forceinline__ int metropolis_update2(int v, int nsum, int off, uint32_t r,
+                                                  const uint2* __restrict__ s_dn, const uint2* __restrict__ s_up,
+                                                  int kc, int& accepted) {
     const int d = min(max(6 * v - nsum + off, -kc), kc);
-    const bool up = (int)r < 0;
-    const uint32_t t = (up ? s_up : s_dn)[d];
-    return r <= t ? (up ? 1 : -1) : 0;
+    const uint2 t = ((int)r < 0 ? s_up : s_dn)[d];
+    if (r <= t.x) {
+        v += (int)t.y;
+        if (COUNT) accepted += 1;
+    }
+    return v;
 }
 
-template <int G, int MARCH, bool WILSON, bool SINGLE>
+// MARCH rows of one quad column; P0 = x parity of the first row's sites (alternates row by row).
+template <int G, int MARCH, bool WILSON, bool COUNT, uint32_t P0>
+__device__ __forceinline__ void march_rows(int4* __restrict__ p_own, const int4* __restrict__ p_oc,
+                                           const int4* __restrict__ p_ta, const int4* __restrict__ p_tb,
+                                           const int4* __restrict__ p_first, const int4* __restrict__ p_last,
+                                           const unsigned int lanes, const uint32_t src_up, const uint32_t src_dn,
+                                           const uint32_t grp, const uint32_t colour, const uint64_t sweep,
+                                           const RoundKeys& rk, const uint2* __restrict__ s_dn,
+                                           const uint2* __restrict__ s_up, const int kc, const uint32_t y0,
+                                           const uint32_t Y, const uint32_t kq, const bool wil_plane,
+                                           const uint32_t wil_w, int& accepted) {
+    int4 om = __ldg(p_first);
+    int4 oc = __ldg(p_oc);
+#pragma unroll
+    for (uint32_t s = 0; s < MARCH; ++s) {
+        constexpr uint32_t dummy = 0;
+        (void)dummy;
+        const bool p = ((P0 ^ s) & 1u) != 0u;  // compile time after unrolling
+        const int4 v = p_own[s * G];
+        const int4 on = __ldg(s + 1 < MARCH ? p_oc + (s + 1) * G : p_last);
+        const int4 ta = __ldg(p_ta + s * G);
+        const int4 tb = __ldg(p_tb + s * G);
+        // x neighbour outside the quad: p -> element k0+4 (next lane's .x), else k0-1 (previous lane's .w)
+        const int e = __shfl_sync(lanes, p ? oc.x : oc.w, p ? src_up : src_dn);
+        int4 ns;
+        ns.x = oc.x + (p ? oc.y : e);
+        ns.y = oc.y + (p ? oc.z : oc.x);
+        ns.z = oc.z + (p ? oc.w : oc.y);
+        ns.w = oc.w + (p ? e : oc.z);
+        ns.x += om.x + on.x; ns.y += om.y + on.y; ns.z += om.z + on.z; ns.w += om.w + on.w;
+        ns.x += ta.x + tb.x; ns.y += ta.y + tb.y; ns.z += ta.z + tb.z; ns.w += ta.w + tb.w;
+        const u32x4 r = philox4x32_rk(grp + s * G, colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);
+        int4 off = make_int4(0, 0, 0, 0);
+        if (WILSON) {
+            const uint32_t y = y0 + s;
+            if (wil_plane && (y == 0u || y == 1u % Y)) {
+                const int sgn = (y == 0u ? 1 : 0) - (y == 1u % Y ? 1 : 0);
+                const uint32_t x0 = 8u * kq + (p ? 1u : 0u);
+                off.x = x0 < wil_w ? sgn : 0;
+                off.y = x0 + 2u < wil_w ? sgn : 0;
+                off.z = x0 + 4u < wil_w ? sgn : 0;
+                off.w = x0 + 6u < wil_w ? sgn : 0;
+            }
+        }
+        int4 w;
+        w.x = metropolis_update2<COUNT>(v.x, ns.x, off.x, r.x, s_dn, s_up, kc, accepted);
+        w.y = metropolis_update2<COUNT>(v.y, ns.y, off.y, r.y, s_dn, s_up, kc, accepted);
+        w.z = metropolis_update2<COUNT>(v.z, ns.z, off.z, r.z, s_dn, s_up, kc, accepted);
+        w.w = metropolis_update2<COUNT>(v.w, ns.w, off.w, r.w, s_dn, s_up, kc, accepted);
+        p_own[s * G] = w;
+        om = oc;
+        oc = on;
+    }
+}
+
+template <int G, int MARCH, bool WILSON, bool COUNT>
 __global__ void __launch_bounds__(kMarchWarps * 32)
 k_sweep_march(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr,
               const uint32_t tl_first, const uint32_t n_planes, int32_t* __restrict__ own_base,
               const int32_t* __restrict__ oth_base, const ChainDev* __restrict__ chains,
-              const uint32_t* __restrict__ thr_all, unsigned long long* __restrict__ acc,
-              const __grid_constant__ RoundKeys rk_param) {
-    constexpr uint32_t XH = 4u * G;      // elements per row per colour
+              const uint32_t* __restrict__ thr_all, unsigned long long* __restrict__ acc) {
     constexpr uint32_t R = 32u / G;      // rows handled side by side by one warp
-    extern __shared__ uint32_t s_tab[];
+    extern __shared__ uint2 s_tab2[];
     __shared__ unsigned int s_cnt;
     const uint32_t chain = blockIdx.z;
     const ChainDev cd = chains[chain];
     if (ctr) sweep += *ctr;
-    if (threadIdx.x == 0) s_cnt = 0;
-    const int kc = (int)build_two_sided(s_tab, thr_all + (size_t)chain * kThrStride, cd.n_thr);
-    const uint32_t* s_dn = s_tab + kc;
-    const uint32_t* s_up = s_tab + 3 * kc + 1;
+    if (COUNT && threadIdx.x == 0) s_cnt = 0;
+    const int kc = build_two_sided(s_tab2, thr_all + (size_t)chain * kThrStride, cd.n_thr);
+    const uint2* s_dn = s_tab2 + kc;
+    const uint2* s_up = s_tab2 + 3 * kc + 1;
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t sub = lane / G, kq = lane % G;
@@ -117,8 +163,8 @@ k_sweep_march(const Geom g, const int colour, uint64_t sweep, const uint64_t* __
     const uint32_t y0 = (blockIdx.x * R + sub) * MARCH;
     int accepted = 0;
     const bool active = pl < n_planes && y0 < g.Y;
-    // lanes of one row group share y0, so whole groups are in or out together: the shuffles below
-    // only name lanes of this mask
+    // lanes of one row group share y0, so whole groups are in or out together: the shuffles only
+    // name lanes of this mask
     const unsigned int lanes = __ballot_sync(0xffffffffu, active);
     if (active) {
         const uint32_t tl = tl_first + pl;
@@ -135,56 +181,22 @@ k_sweep_march(const Geom g, const int colour, uint64_t sweep, const uint64_t* __
         const int4* p_first = (y0 == 0) ? p_oc + (g.Y - 1) * G : p_oc - G;
         const int4* p_last = (y0 + MARCH == g.Y) ? p_oc - y0 * G : p_oc + MARCH * G;
         const bool wil_plane = WILSON && tg < cd.wil_h;
-        RoundKeys rk_local;
-        if (!SINGLE) rk_local = make_round_keys_dev(cd.k0, cd.k1);
-        const RoundKeys& rk = SINGLE ? rk_param : rk_local;
-        int4 om = __ldg(p_first);
-        int4 oc = __ldg(p_oc);
-        uint32_t grp = (tg * g.Y + y0) * G + kq;     // Philox counter word 0 of this quad
+        const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
+        const uint32_t grp = (tg * g.Y + y0) * G + kq;     // Philox counter word 0 of the first quad
         const uint32_t src_up = (lane & ~(G - 1u)) | ((lane + 1u) & (G - 1u));
         const uint32_t src_dn = (lane & ~(G - 1u)) | ((lane - 1u) & (G - 1u));
-        const uint32_t p0 = (y0 + tg + (uint32_t)colour) & 1u;
-#pragma unroll
-        for (uint32_t s = 0; s < MARCH; ++s) {
-            const uint32_t p = p0 ^ (s & 1u);
-            const int4 v = p_own[s * G];
-            const int4 on = __ldg(s + 1 < MARCH ? p_oc + (s + 1) * G : p_last);
-            const int4 ta = __ldg(p_ta + s * G);
-            const int4 tb = __ldg(p_tb + s * G);
-            // x neighbour outside the quad: p == 1 -> element k0+4 (next lane's .x), else k0-1 (prev lane's .w)
-            const int e = __shfl_sync(lanes, p ? oc.x : oc.w, p ? src_up : src_dn);
-            int4 ns;
-            ns.x = oc.x + (p ? oc.y : e);
-            ns.y = oc.y + (p ? oc.z : oc.x);
-            ns.z = oc.z + (p ? oc.w : oc.y);
-            ns.w = oc.w + (p ? e : oc.z);
-            ns.x += om.x + on.x; ns.y += om.y + on.y; ns.z += om.z + on.z; ns.w += om.w + on.w;
-            ns.x += ta.x + tb.x; ns.y += ta.y + tb.y; ns.z += ta.z + tb.z; ns.w += ta.w + tb.w;
-            const u32x4 r = philox4x32_rk(grp + s * G, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);
-            int4 off = make_int4(0, 0, 0, 0);
-            if (WILSON) {
-                const uint32_t y = y0 + s;
-                if (wil_plane && (y == 0u || y == 1u % g.Y)) {
-                    const int sgn = (y == 0u ? 1 : 0) - (y == 1u % g.Y ? 1 : 0);
-                    const uint32_t x0 = 8u * kq + p;
-                    off.x = x0 < cd.wil_w ? sgn : 0;
-                    off.y = x0 + 2u < cd.wil_w ? sgn : 0;
-                    off.z = x0 + 4u < cd.wil_w ? sgn : 0;
-                    off.w = x0 + 6u < cd.wil_w ? sgn : 0;
-                }
-            }
-            int4 dl;
-            dl.x = metropolis_delta2(v.x, ns.x, off.x, r.x, s_dn, s_up, kc);
-            dl.y = metropolis_delta2(v.y, ns.y, off.y, r.y, s_dn, s_up, kc);
-            dl.z = metropolis_delta2(v.z, ns.z, off.z, r.z, s_dn, s_up, kc);
-            dl.w = metropolis_delta2(v.w, ns.w, off.w, r.w, s_dn, s_up, kc);
-            accepted += dl.x * dl.x + dl.y * dl.y + dl.z * dl.z + dl.w * dl.w;
-            p_own[s * G] = make_int4(v.x + dl.x, v.y + dl.y, v.z + dl.z, v.w + dl.w);
-            om = oc;
-            oc = on;
-        }
+        // y0 is a multiple of the (even) march length: the parity is uniform over the warp
+        if ((tg + (uint32_t)colour) & 1u)
+            march_rows<G, MARCH, WILSON, COUNT, 1u>(p_own, p_oc, p_ta, p_tb, p_first, p_last, lanes, src_up, src_dn, grp,
+                                                    (uint32_t)colour, sweep, rk, s_dn, s_up, kc, y0, g.Y, kq, wil_plane,
+                                                    cd.wil_w, accepted);
+        else
+            march_rows<G, MARCH, WILSON, COUNT, 0u>(p_own, p_oc, p_ta, p_tb, p_first, p_last, lanes, src_up, src_dn, grp,
+                                                    (uint32_t)colour, sweep, rk, s_dn, s_up, kc, y0, g.Y, kq, wil_plane,
+                                                    cd.wil_w, accepted);
     }
-    block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
+    if (COUNT)
+        block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
 }
 
 struct TiledPlan {
@@ -193,8 +205,8 @@ struct TiledPlan {
     int march = 0;   // rows per thread
 };
 
-// The marching kernel applies when X = 8 G with G a power of two <= 32, Y is a multiple of the
-// march length and all element offsets / Philox group indices fit 32 bits.
+// The marching kernel applies when X = 8 G with G a power of two <= 32 and all element offsets and
+// Philox group indices fit 32 bits.  (Y is even, so a march of 2 always divides it.)
 inline cudaError_t tiled_prepare(TiledPlan& p, const Geom& g, uint32_t, int, bool force_off) {
     p.enabled = false;
     if (force_off) return cudaSuccess;
@@ -202,60 +214,51 @@ inline cudaError_t tiled_prepare(TiledPlan& p, const Geom& g, uint32_t, int, boo
     if (g.X % 8 != 0 || G == 0 || G > 32 || (G & (G - 1)) != 0) return cudaSuccess;
     if ((uint64_t)g.X * g.Y * g.T >= (1ull << 35)) return cudaSuccess;
     if (g.chain_stride >= (1ull << 31)) return cudaSuccess;
-    int march = 0;
-    for (int m : {8, 4, 2})
-        if (g.Y % m == 0) { march = m; break; }
-    if (!march) return cudaSuccess;
     p.g = (int)G;
-    p.march = march;
+    p.march = (g.Y % 8 == 0) ? 8 : 2;
     p.enabled = true;
     return cudaSuccess;
 }
 inline void tiled_release(TiledPlan&) {}
 
+struct MarchArgs {
+    Geom g;
+    int colour;
+    uint64_t sweep;
+    const uint64_t* ctr;
+    uint32_t tl_first, n_planes, n_chains;
+    int32_t* own;
+    const int32_t* oth;
+    const ChainDev* chains;
+    const uint32_t* thr;
+    unsigned long long* acc;
+    uint32_t max_thr;
+    bool wilson, count;
+    cudaStream_t stream;
+};
+
 template <int G, int MARCH>
-inline cudaError_t march_launch(const Geom& g, int colour, uint64_t sweep, const uint64_t* ctr,
-                                uint32_t tl_first, uint32_t n_planes, uint32_t n_chains, int32_t* own,
-                                const int32_t* oth, const ChainDev* chains, const uint32_t* thr,
-                                unsigned long long* acc, uint32_t max_thr, bool wilson, const RoundKeys* single,
-                                cudaStream_t s) {
+inline cudaError_t march_launch(const MarchArgs& a) {
     constexpr uint32_t R = 32u / G;
-    dim3 grid((g.Y + R * MARCH - 1) / (R * MARCH), (n_planes + kMarchWarps - 1) / kMarchWarps, n_chains);
-    const uint32_t kc = max_thr > 4 ? max_thr - 1 : 3;
-    const size_t smem = sizeof(uint32_t) * 2 * (2 * kc + 1);
-    const RoundKeys rk = single ? *single : RoundKeys{};
-#define LQFT_GO(W, S) \
-    k_sweep_march<G, MARCH, W, S><<<grid, kMarchWarps * 32, smem, s>>>(g, colour, sweep, ctr, tl_first, n_planes, own, \
-                                                                       oth, chains, thr, acc, rk)
-    if (single) {
-        if (wilson) LQFT_GO(true, true); else LQFT_GO(false, true);
+    dim3 grid((a.g.Y + R * MARCH - 1) / (R * MARCH), (a.n_planes + kMarchWarps - 1) / kMarchWarps, a.n_chains);
+    const uint32_t kc = a.max_thr > 4 ? a.max_thr - 1 : 3;
+    const size_t smem = sizeof(uint2) * 2 * (2 * kc + 1);
+#define LQFT_GO(W, C)                                                                                          \
+    k_sweep_march<G, MARCH, W, C><<<grid, kMarchWarps * 32, smem, a.stream>>>(a.g, a.colour, a.sweep, a.ctr, a.tl_first, \
+                                                                             a.n_planes, a.own, a.oth, a.chains, a.thr, a.acc)
+    if (a.wilson) {
+        if (a.count) LQFT_GO(true, true); else LQFT_GO(true, false);
     } else {
-        if (wilson) LQFT_GO(true, false); else LQFT_GO(false, false);
+        if (a.count) LQFT_GO(false, true); else LQFT_GO(false, false);
     }
 #undef LQFT_GO
     return cudaGetLastError();
 }
 
-template <int G>
-inline cudaError_t march_dispatch_m(int march, const Geom& g, int colour, uint64_t sweep, const uint64_t* ctr,
-                                    uint32_t tl_first, uint32_t n_planes, uint32_t n_chains, int32_t* own,
-                                    const int32_t* oth, const ChainDev* chains, const uint32_t* thr,
-                                    unsigned long long* acc, uint32_t max_thr, bool wilson, const RoundKeys* single, cudaStream_t s) {
-    switch (march) {
-        case 8: return march_launch<G, 8>(g, colour, sweep, ctr, tl_first, n_planes, n_chains, own, oth, chains, thr, acc, max_thr, wilson, single, s);
-        case 4: return march_launch<G, 4>(g, colour, sweep, ctr, tl_first, n_planes, n_chains, own, oth, chains, thr, acc, max_thr, wilson, single, s);
-        default: return march_launch<G, 2>(g, colour, sweep, ctr, tl_first, n_planes, n_chains, own, oth, chains, thr, acc, max_thr, wilson, single, s);
-    }
-}
-
 // One half-sweep of `colour` over local planes [tl_first, tl_first + n_planes).
-inline cudaError_t tiled_half(const TiledPlan& p, const Geom& g, int colour, uint64_t sweep, const uint64_t* ctr,
-                              uint32_t tl_first, uint32_t n_planes, uint32_t n_chains, int32_t* own,
-                              const int32_t* oth, const ChainDev* chains, const uint32_t* thr,
-                              unsigned long long* acc, uint32_t max_thr, bool wilson, const RoundKeys* single,
-                              cudaStream_t s) {
+inline cudaError_t tiled_half(const TiledPlan& p, const MarchArgs& a) {
 #define LQFT_MARCH(GV) \
-    case GV: return march_dispatch_m<GV>(p.march, g, colour, sweep, ctr, tl_first, n_planes, n_chains, own, oth, chains, thr, acc, max_thr, wilson, single, s)
+    case GV: return p.march == 8 ? march_launch<GV, 8>(a) : march_launch<GV, 2>(a)
     switch (p.g) {
         LQFT_MARCH(1);
         LQFT_MARCH(2);

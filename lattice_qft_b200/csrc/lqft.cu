@@ -104,10 +104,12 @@ static lqft_status nccl_load() {
 // ---------------------------------------------------------------------------------------------
 struct GraphKey {
     uint32_t energy_every, normalize_every, cycle;
+    bool count;
     bool operator<(const GraphKey& o) const {
         if (energy_every != o.energy_every) return energy_every < o.energy_every;
         if (normalize_every != o.normalize_every) return normalize_every < o.normalize_every;
-        return cycle < o.cycle;
+        if (cycle != o.cycle) return cycle < o.cycle;
+        return count < o.count;
     }
 };
 struct GraphVal {
@@ -148,6 +150,7 @@ struct lqft_handle {
     std::vector<double*> diff_sum, diff_comp;
     std::vector<uint64_t> diff_count;
     bool ghosts_valid = false;
+    bool count_accepts = false;  // current call wants acceptance counts
     uint64_t launches = 0;
     ncclComm_t comm = nullptr;
     int sm_count = 148;
@@ -501,11 +504,9 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
     int32_t* own = h->field[colour];
     const int32_t* oth = h->field[colour ^ 1];
     if (h->tiled.enabled) {
-        RoundKeys rk;
-        const bool single = h->cfg.n_chains == 1;
-        if (single) rk = make_round_keys(h->chains_h[0].k0, h->chains_h[0].k1);
-        CU(tiled_half(h->tiled, g, colour, sweep, ctr, tl_first, n_planes, h->cfg.n_chains, own, oth, h->chains_d,
-                      h->thr_d, h->acc_d, h->max_thr, h->any_wilson, single ? &rk : nullptr, s));
+        MarchArgs a{g, colour, sweep, ctr, tl_first, n_planes, h->cfg.n_chains, own, oth, h->chains_d, h->thr_d,
+                    h->acc_d, h->max_thr, h->any_wilson, h->count_accepts, s};
+        CU(tiled_half(h->tiled, a));
         h->launches += 1;
         return LQFT_OK;
     }
@@ -667,6 +668,7 @@ static lqft_status read_accepted(lqft_handle* h, uint64_t* accepted) {
 
 extern "C" lqft_status lqft_sweep(lqft_handle* h, uint64_t first_sweep, uint32_t n_sweeps, uint64_t* accepted) {
     ST(ready(h));
+    h->count_accepts = accepted != nullptr;
     if (accepted) CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * (size_t)h->cfg.n_chains * kAccSlots, h->stream));
     CU(cudaEventRecord(h->ev_start, h->stream));
     for (uint32_t s = 0; s < n_sweeps; ++s) ST(launch_sweep(h, first_sweep + s, nullptr));
@@ -889,6 +891,7 @@ extern "C" lqft_status lqft_run(lqft_handle* h, const lqft_schedule* s, double* 
                                 uint64_t* accepted) {
     if (!s) return fail(LQFT_ERR_INVALID, "null schedule");
     ST(ready(h));
+    h->count_accepts = accepted != nullptr;
     const uint32_t nc = h->cfg.n_chains;
     const uint64_t n_meas = lqft_run_measurements(s->first_step, s->n_steps, s->energy_every);
     if (n_meas > 0xffffffffull) return fail(LQFT_ERR_INVALID, "too many measurements in one run");
@@ -923,7 +926,7 @@ extern "C" lqft_status lqft_run(lqft_handle* h, const lqft_schedule* s, double* 
         }
         const uint64_t n_cycles = (end - step) / cycle;
         if (n_cycles) {
-            GraphKey key{s->energy_every, s->normalize_every, (uint32_t)cycle};
+            GraphKey key{s->energy_every, s->normalize_every, (uint32_t)cycle, h->count_accepts};
             auto it = h->graphs.find(key);
             if (it == h->graphs.end()) {
                 // capture one cycle; every kernel reads the sweep counter from device memory
