@@ -32,7 +32,7 @@ T_PER_GPU = 256
 BETA = 0.25
 SEED = 0xC0FFEE
 THERMALISE = 200
-SWEEPS_PER_STEP = 100
+SWEEPS_PER_STEP = 1000
 BYTES_PER_UPDATE = 8  # one i32 read + one i32 write per site update
 METRIC = "site updates/sec"
 UNIT = "site-updates/s"
@@ -152,12 +152,16 @@ def workload_config(n_gpus: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="LQFT_FLAG_* for experiments")
+    ap.add_argument("--lattice", default=None, help="X,Y,Tpergpu override for experiments (not the headline config)")
     args = ap.parse_args()
+    if args.lattice:
+        global X, Y, T_PER_GPU
+        X, Y, T_PER_GPU = (int(v) for v in args.lattice.split(","))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,7 +247,7 @@ def main():
     host_out = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
     np_in, np_out = host_in.numpy(), host_out.numpy()
     eng.download(0, np_in)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 5))
 
     def e2e_step(base):
         eng.upload(0, np_in)                                   # H2D from pinned memory
@@ -279,7 +283,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
-                    "what": "lqft_upload(pinned host field) + lqft_run(100 steps: sweep, energy every 10th, "
+                    "what": "lqft_upload(pinned host field) + lqft_run(SWEEPS_PER_STEP steps: sweep, energy every 10th, "
                             "normalize every 10th) + lqft_download(field) per step, wall clock"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

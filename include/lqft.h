@@ -78,6 +78,8 @@ typedef struct lqft_config {
 #define LQFT_FLAG_HALO_NCCL 4u    /* world_size>1: ncclSend/Recv halos (default: peer stores
                                      fused into the boundary kernel when P2P is available)  */
 #define LQFT_FLAG_FORCE_V1 8u     /* use the two-pass L1-cached kernels, not the tiled ones */
+#define LQFT_FLAG_NO_STREAM 16u   /* wide rows: marching kernel instead of the streaming one */
+#define LQFT_FLAG_NO_PDL 32u      /* no programmatic dependent launch between half-sweeps     */
 
 typedef struct lqft_handle lqft_handle;
 

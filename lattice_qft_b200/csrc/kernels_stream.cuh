@@ -1,0 +1,357 @@
+// kernels_stream.cuh — the streaming half-sweep for wide rows (X = 256 * SEGS).
+//
+// The marching kernel (kernels_tiled.cuh) cut the instruction count 3x and left the sweep latency
+// bound: at 256^3 the two colour arrays (64 MiB) do not stay in the two-die L2, one launch still
+// reads ~34 MB from HBM, and a warp sits on LDG round trips (profiles/r1_march_*: long scoreboard
+// 7-8 of every issue slot, issue 36-50 % busy, 2 waves of 8-step blocks).  This kernel keeps the
+// register window and the shuffle trick and adds
+//   * a per-thread asynchronous prefetch ring in shared memory: the four row loads of step s + D
+//     (own row, other colour row y+1, planes t-1 / t+1) are issued with cp.async (LDGSTS) D steps
+//     ahead and read back with LDS.128 — depth without registers, no block barriers;
+//   * one balanced wave: the y range of every plane group is cut into chunks so that the grid just
+//     fills the resident-block slots of the 148 SMs, and each thread streams its whole chunk with a
+//     runtime loop (prologue paid once per chunk, no tail wave);
+//   * rows wider than one warp (X = 512, 1024): a row is SEGS warp-wide segments; the neighbour
+//     across a segment edge is prefetched by the edge lanes into the same ring.
+// Same sites, same Philox counters, same decisions as every other path: bit-identical results.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels_tiled.cuh"
+
+namespace lqft {
+
+#ifndef LQFT_STREAM_WARPS
+#define LQFT_STREAM_WARPS 4
+#endif
+#ifndef LQFT_STREAM_DEPTH
+#define LQFT_STREAM_DEPTH 2
+#endif
+#ifndef LQFT_STREAM_MINBLOCKS
+#define LQFT_STREAM_MINBLOCKS 7
+#endif
+constexpr int kStreamWarps = LQFT_STREAM_WARPS;
+constexpr int kStreamDepth = LQFT_STREAM_DEPTH;   // prefetch distance in rows (even)
+constexpr int kStreamThreads = kStreamWarps * 32;
+static_assert(kStreamDepth % 2 == 0 && kStreamDepth >= 2, "the ring depth must be even");
+
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4_ca(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// Everything a thread needs to issue the loads of one row.
+struct StreamPtrs {
+    const int4* own;   // own colour, this plane, row 0 of the chunk's plane (quad column kq)
+    const int4* oc;    // other colour, this plane
+    const int4* ta;    // other colour, plane t+1
+    const int4* tb;    // other colour, plane t-1
+    const int32_t* edge;  // other colour, this plane, element across the segment edge (row 0)
+};
+
+template <int SEGS, bool P>
+__device__ __forceinline__ void stream_issue(const StreamPtrs& q, uint32_t y, uint32_t Y, uint32_t ring, uint32_t edge_ring,
+                                             uint32_t stage, bool edge_lane) {
+    constexpr uint32_t G = 32u * SEGS;
+    constexpr uint32_t STAGE_BYTES = 4u * kStreamThreads * 16u;
+    const uint32_t dst = ring + stage * STAGE_BYTES;
+    const uint32_t yn = (y + 1 == Y) ? 0u : y + 1;
+    cp_async16_cg(dst, q.own + y * G);
+    cp_async16_ca(dst + kStreamThreads * 16u, q.oc + yn * G);
+    cp_async16_ca(dst + 2u * kStreamThreads * 16u, q.ta + y * G);
+    cp_async16_ca(dst + 3u * kStreamThreads * 16u, q.tb + y * G);
+    if (SEGS > 1) {
+        if (edge_lane) cp_async4_ca(edge_ring + stage * (kStreamThreads * 4u), q.edge + y * (4u * G));
+    }
+}
+
+template <int SEGS, bool WILSON, bool COUNT, bool P>
+__device__ __forceinline__ void stream_step(int4* __restrict__ own_row, uint32_t ring, uint32_t edge_ring, uint32_t stage,
+                                            int4& om, int4& oc, const uint32_t src_lane, const bool edge_lane,
+                                            const uint32_t grp, const uint32_t colour, const uint64_t sweep,
+                                            const RoundKeys& rk, const uint2* __restrict__ s_dn,
+                                            const uint2* __restrict__ s_up, const int kc, const uint32_t y,
+                                            const uint32_t Y, const uint32_t kq, const bool wil_plane,
+                                            const uint32_t wil_w, int& accepted) {
+    constexpr uint32_t STAGE_BYTES = 4u * kStreamThreads * 16u;
+    const uint32_t src = ring + stage * STAGE_BYTES;
+    const int4 v = lds128(src);
+    const int4 on = lds128(src + kStreamThreads * 16u);
+    const int4 ta = lds128(src + 2u * kStreamThreads * 16u);
+    const int4 tb = lds128(src + 3u * kStreamThreads * 16u);
+    // x neighbour outside the quad: P -> element k0+4 (next lane's .x), else k0-1 (previous lane's .w)
+    int e = __shfl_sync(0xffffffffu, P ? oc.x : oc.w, src_lane);
+    if (SEGS > 1) {
+        if (edge_lane) e = lds32(edge_ring + stage * (kStreamThreads * 4u));
+    }
+    int4 ns;
+    ns.x = oc.x + (P ? oc.y : e);
+    ns.y = oc.y + (P ? oc.z : oc.x);
+    ns.z = oc.z + (P ? oc.w : oc.y);
+    ns.w = oc.w + (P ? e : oc.z);
+    ns.x += om.x + on.x; ns.y += om.y + on.y; ns.z += om.z + on.z; ns.w += om.w + on.w;
+    ns.x += ta.x + tb.x; ns.y += ta.y + tb.y; ns.z += ta.z + tb.z; ns.w += ta.w + tb.w;
+    const u32x4 r = philox4x32_rk(grp, colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);
+    int4 off = make_int4(0, 0, 0, 0);
+    if (WILSON) {
+        if (wil_plane && (y == 0u || y == 1u % Y)) {
+            const int sgn = (y == 0u ? 1 : 0) - (y == 1u % Y ? 1 : 0);
+            const uint32_t x0 = 8u * kq + (P ? 1u : 0u);
+            off.x = x0 < wil_w ? sgn : 0;
+            off.y = x0 + 2u < wil_w ? sgn : 0;
+            off.z = x0 + 4u < wil_w ? sgn : 0;
+            off.w = x0 + 6u < wil_w ? sgn : 0;
+        }
+    }
+    int4 w;
+    w.x = metropolis_update2<COUNT>(v.x, ns.x, off.x, r.x, s_dn, s_up, kc, accepted);
+    w.y = metropolis_update2<COUNT>(v.y, ns.y, off.y, r.y, s_dn, s_up, kc, accepted);
+    w.z = metropolis_update2<COUNT>(v.z, ns.z, off.z, r.z, s_dn, s_up, kc, accepted);
+    w.w = metropolis_update2<COUNT>(v.w, ns.w, off.w, r.w, s_dn, s_up, kc, accepted);
+    *own_row = w;
+    om = oc;
+    oc = on;
+}
+
+// The chunk [y_begin, y_end) of one plane, parity P0 at y_begin.
+template <int SEGS, bool WILSON, bool COUNT, bool P0>
+__device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, const StreamPtrs& q, const uint32_t y_begin,
+                                             const uint32_t y_end, const uint32_t Y, const uint32_t ring,
+                                             const uint32_t edge_ring, const uint32_t lane, const uint32_t kq,
+                                             const uint32_t grp_row0, const uint32_t colour, const uint64_t sweep,
+                                             const RoundKeys& rk, const uint2* __restrict__ s_dn,
+                                             const uint2* __restrict__ s_up, const int kc, const bool wil_plane,
+                                             const uint32_t wil_w, int& accepted) {
+    constexpr uint32_t G = 32u * SEGS;
+    constexpr int D = kStreamDepth;
+    const uint32_t n_steps = y_end - y_begin;  // even
+    const uint32_t src_up = (lane + 1u) & 31u, src_dn = (lane - 1u) & 31u;
+    // edge lanes of a multi-segment row fetch their neighbour from the adjacent segment
+    const bool edge_p = SEGS > 1 && lane == 31u, edge_n = SEGS > 1 && lane == 0u;
+    StreamPtrs qp = q, qn = q;  // parity-true rows look right (+4), parity-false rows look left (-1)
+    if (SEGS > 1) {
+        const uint32_t k_right = (kq + 1u == G) ? 0u : 4u * (kq + 1u);
+        const uint32_t k_left = (kq == 0u) ? 4u * G - 1u : 4u * kq - 1u;
+        qp.edge = q.edge + k_right;
+        qn.edge = q.edge + k_left;
+    }
+#pragma unroll
+    for (int s = 0; s < D; ++s) {
+        if ((uint32_t)s < n_steps) {
+            if ((s & 1) ? !P0 : P0) stream_issue<SEGS, true>(qp, y_begin + s, Y, ring, edge_ring, (uint32_t)s, edge_p);
+            else stream_issue<SEGS, false>(qn, y_begin + s, Y, ring, edge_ring, (uint32_t)s, edge_n);
+        }
+        cp_async_commit();
+    }
+    const uint32_t ym = (y_begin == 0u) ? Y - 1u : y_begin - 1u;
+    int4 om = __ldg(q.oc + ym * G);
+    int4 oc = __ldg(q.oc + y_begin * G);
+    for (uint32_t s = 0; s < n_steps; s += 2) {
+        const uint32_t y = y_begin + s;
+        const uint32_t st0 = s & (uint32_t)(D - 1), st1 = (s + 1u) & (uint32_t)(D - 1);
+        cp_async_wait<D - 1>();
+        stream_step<SEGS, WILSON, COUNT, P0>(own_w + y * G, ring, edge_ring, st0, om, oc, P0 ? src_up : src_dn,
+                                             P0 ? edge_p : edge_n, grp_row0 + y * G, colour, sweep, rk, s_dn, s_up, kc,
+                                             y, Y, kq, wil_plane, wil_w, accepted);
+        if (s + D < n_steps) {
+            if (P0) stream_issue<SEGS, true>(qp, y + D, Y, ring, edge_ring, st0, edge_p);
+            else stream_issue<SEGS, false>(qn, y + D, Y, ring, edge_ring, st0, edge_n);
+        }
+        cp_async_commit();
+        cp_async_wait<D - 1>();
+        stream_step<SEGS, WILSON, COUNT, !P0>(own_w + (y + 1u) * G, ring, edge_ring, st1, om, oc, P0 ? src_dn : src_up,
+                                              P0 ? edge_n : edge_p, grp_row0 + (y + 1u) * G, colour, sweep, rk, s_dn,
+                                              s_up, kc, y + 1u, Y, kq, wil_plane, wil_w, accepted);
+        if (s + 1u + D < n_steps) {
+            if (!P0) stream_issue<SEGS, true>(qp, y + 1u + D, Y, ring, edge_ring, st1, edge_p);
+            else stream_issue<SEGS, false>(qn, y + 1u + D, Y, ring, edge_ring, st1, edge_n);
+        }
+        cp_async_commit();
+    }
+    cp_async_wait<0>();
+}
+
+// grid = (n_chunks * SEGS, ceil(n_planes / kStreamWarps), n_chains), block = kStreamThreads.
+template <int SEGS, bool WILSON, bool COUNT>
+__global__ void __launch_bounds__(kStreamThreads, LQFT_STREAM_MINBLOCKS)
+k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr,
+               const uint32_t tl_first, const uint32_t n_planes, const uint32_t n_chunks,
+               int32_t* __restrict__ own_base, const int32_t* __restrict__ oth_base,
+               const ChainDev* __restrict__ chains, const uint32_t* __restrict__ thr_all,
+               unsigned long long* __restrict__ acc) {
+    constexpr uint32_t G = 32u * SEGS;
+    constexpr uint32_t RING_BYTES = (uint32_t)kStreamDepth * 4u * kStreamThreads * 16u;
+    constexpr uint32_t EDGE_BYTES = SEGS > 1 ? (uint32_t)kStreamDepth * kStreamThreads * 4u : 0u;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ unsigned int s_cnt;
+    pdl_launch_dependents();
+    const uint32_t chain = blockIdx.z;
+    const ChainDev cd = chains[chain];
+    if (COUNT && threadIdx.x == 0) s_cnt = 0;
+    uint2* s_tab2 = reinterpret_cast<uint2*>(s_raw + RING_BYTES + EDGE_BYTES);
+    const int kc = build_two_sided(s_tab2, thr_all + (size_t)chain * kThrStride, cd.n_thr);
+    const uint2* s_dn = s_tab2 + kc;
+    const uint2* s_up = s_tab2 + 3 * kc + 1;
+    pdl_wait();
+    if (ctr) sweep += *ctr;
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x / SEGS, seg = blockIdx.x % SEGS;
+    const uint32_t pl = blockIdx.y * kStreamWarps + warp;
+    const uint32_t half = g.Y >> 1;
+    const uint32_t y_begin = 2u * (uint32_t)(((uint64_t)chunk * half) / n_chunks);
+    const uint32_t y_end = 2u * (uint32_t)(((uint64_t)(chunk + 1u) * half) / n_chunks);
+    int accepted = 0;
+    if (pl < n_planes && y_begin < y_end) {  // warp uniform
+        const uint32_t tl = tl_first + pl;
+        const uint32_t tg = g.t0 + tl;
+        const size_t cbase = (size_t)chain * g.chain_stride;
+        const uint32_t kq = seg * 32u + lane;
+        const uint32_t planeq = g.plane / 4;
+        const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_raw) + threadIdx.x * 16u;
+        const uint32_t edge_ring = (uint32_t)__cvta_generic_to_shared(s_raw) + RING_BYTES + threadIdx.x * 4u;
+        int4* own_w = reinterpret_cast<int4*>(own_base + cbase) + (plane_self(g, tl) * planeq + kq);
+        const int4* othq = reinterpret_cast<const int4*>(oth_base + cbase);
+        StreamPtrs q;
+        q.own = own_w;
+        q.oc = othq + (plane_self(g, tl) * planeq + kq);
+        q.ta = othq + (plane_above(g, tl) * planeq + kq);
+        q.tb = othq + (plane_below(g, tl) * planeq + kq);
+        q.edge = oth_base + cbase + (size_t)plane_self(g, tl) * g.plane;
+        const bool wil_plane = WILSON && tg < cd.wil_h;
+        const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
+        const uint32_t grp_row0 = tg * g.Y * G + kq;  // Philox counter word 0 of this quad column at y = 0
+        if ((y_begin + tg + (uint32_t)colour) & 1u)
+            stream_chunk<SEGS, WILSON, COUNT, true>(own_w, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
+                                                    (uint32_t)colour, sweep, rk, s_dn, s_up, kc, wil_plane, cd.wil_w,
+                                                    accepted);
+        else
+            stream_chunk<SEGS, WILSON, COUNT, false>(own_w, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
+                                                     (uint32_t)colour, sweep, rk, s_dn, s_up, kc, wil_plane, cd.wil_w,
+                                                     accepted);
+    }
+    if (COUNT)
+        block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
+}
+
+struct StreamPlan {
+    bool enabled = false;
+    int segs = 0;
+    int blocks_per_sm = 0;
+    int sm_count = 0;
+};
+
+inline size_t stream_smem_bytes(int segs, uint32_t max_thr) {
+    const uint32_t kc = max_thr > 4 ? max_thr - 1 : 3;
+    return (size_t)kStreamDepth * 4 * kStreamThreads * 16 + (segs > 1 ? (size_t)kStreamDepth * kStreamThreads * 4 : 0) +
+           sizeof(uint2) * 2 * (2 * kc + 1);
+}
+
+template <int SEGS>
+inline cudaError_t stream_occupancy(int* blocks, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_stream<SEGS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k_sweep_stream<SEGS, false, false>, kStreamThreads, smem);
+}
+
+// Applies to X in {256, 512, 1024}.
+inline cudaError_t stream_prepare(StreamPlan& p, const Geom& g, int sm_count, uint32_t max_thr, bool force_off) {
+    p.enabled = false;
+    if (force_off) return cudaSuccess;
+    if (g.X != 256 && g.X != 512 && g.X != 1024) return cudaSuccess;
+    if ((uint64_t)g.X * g.Y * g.T >= (1ull << 35) || g.chain_stride >= (1ull << 31)) return cudaSuccess;
+    p.segs = (int)(g.X / 256);
+    p.sm_count = sm_count;
+    const size_t smem = stream_smem_bytes(p.segs, max_thr);
+    if (smem > 200 * 1024) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    switch (p.segs) {
+        case 1: e = stream_occupancy<1>(&p.blocks_per_sm, smem); break;
+        case 2: e = stream_occupancy<2>(&p.blocks_per_sm, smem); break;
+        default: e = stream_occupancy<4>(&p.blocks_per_sm, smem); break;
+    }
+    if (e != cudaSuccess) return e;
+    p.enabled = p.blocks_per_sm > 0;
+    return cudaSuccess;
+}
+
+// Number of y chunks per plane group: the grid should fill whole waves of resident blocks.
+inline uint32_t stream_chunks(const StreamPlan& p, const Geom& g, uint32_t n_planes, uint32_t n_chains) {
+    const uint64_t slots = (uint64_t)p.sm_count * p.blocks_per_sm;
+    const uint64_t base = (uint64_t)p.segs * ((n_planes + kStreamWarps - 1) / kStreamWarps) * n_chains;
+    const uint32_t max_chunks = g.Y / 4 ? g.Y / 4 : 1;  // at least 4 rows per chunk
+    uint32_t best = 1;
+    double best_eff = -1.0;
+    for (uint32_t nc = 1; nc <= max_chunks; ++nc) {
+        const double blocks = (double)(base * nc);
+        const double waves = blocks / (double)slots;
+        const double eff = waves / (double)(uint64_t)(waves + 0.999999);
+        // prefer the fewest chunks among (nearly) equally efficient choices: fewer prologues
+        if (eff > best_eff + 0.02) {
+            best_eff = eff;
+            best = nc;
+        }
+    }
+    return best;
+}
+
+template <int SEGS>
+inline cudaError_t stream_launch(const StreamPlan& p, const MarchArgs& a) {
+    const uint32_t n_chunks = stream_chunks(p, a.g, a.n_planes, a.n_chains);
+    dim3 grid(n_chunks * SEGS, (a.n_planes + kStreamWarps - 1) / kStreamWarps, a.n_chains);
+    const size_t smem = stream_smem_bytes(SEGS, a.max_thr);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kStreamThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = a.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = a.pdl ? 1 : 0;
+#define LQFT_GO(W, C)                                                                                                  \
+    return cudaLaunchKernelEx(&cfg, k_sweep_stream<SEGS, W, C>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_planes, \
+                              n_chunks, a.own, a.oth, a.chains, a.thr, a.acc)
+    if (a.wilson) {
+        if (a.count) LQFT_GO(true, true); else LQFT_GO(true, false);
+    } else {
+        if (a.count) LQFT_GO(false, true); else LQFT_GO(false, false);
+    }
+#undef LQFT_GO
+    return cudaGetLastError();
+}
+
+inline cudaError_t stream_half(const StreamPlan& p, const MarchArgs& a) {
+    switch (p.segs) {
+        case 1: return stream_launch<1>(p, a);
+        case 2: return stream_launch<2>(p, a);
+        default: return stream_launch<4>(p, a);
+    }
+}
+
+}  // namespace lqft

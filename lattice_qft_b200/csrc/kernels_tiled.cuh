@@ -23,7 +23,23 @@
 
 namespace lqft {
 
-constexpr int kMarchWarps = 4;  // warps (= t-planes) per block
+// Tunables (overridable at build time for experiments; defaults are the measured best on B200).
+#ifndef LQFT_MARCH_WARPS
+#define LQFT_MARCH_WARPS 4
+#endif
+#ifndef LQFT_MARCH_LONG
+#define LQFT_MARCH_LONG 8
+#endif
+#ifndef LQFT_MARCH_MINBLOCKS
+#define LQFT_MARCH_MINBLOCKS 7
+#endif
+constexpr int kMarchWarps = LQFT_MARCH_WARPS;  // warps (= t-planes) per block
+constexpr int kMarchLong = LQFT_MARCH_LONG;    // rows per thread when Y allows
+
+// Programmatic dependent launch: a sweep kernel lets its successor start (and run its prologue) at
+// once, and touches field data / the device sweep counter only after its predecessor has completed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Round keys of Philox4x32-10 (key + r * W), computed once per thread and kept in registers.
 struct RoundKeys {
@@ -141,7 +157,7 @@ __device__ __forceinline__ void march_rows(int4* __restrict__ p_own, const int4*
 }
 
 template <int G, int MARCH, bool WILSON, bool COUNT>
-__global__ void __launch_bounds__(kMarchWarps * 32)
+__global__ void __launch_bounds__(kMarchWarps * 32, LQFT_MARCH_MINBLOCKS)
 k_sweep_march(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr,
               const uint32_t tl_first, const uint32_t n_planes, int32_t* __restrict__ own_base,
               const int32_t* __restrict__ oth_base, const ChainDev* __restrict__ chains,
@@ -149,13 +165,15 @@ k_sweep_march(const Geom g, const int colour, uint64_t sweep, const uint64_t* __
     constexpr uint32_t R = 32u / G;      // rows handled side by side by one warp
     extern __shared__ uint2 s_tab2[];
     __shared__ unsigned int s_cnt;
+    pdl_launch_dependents();
     const uint32_t chain = blockIdx.z;
     const ChainDev cd = chains[chain];
-    if (ctr) sweep += *ctr;
     if (COUNT && threadIdx.x == 0) s_cnt = 0;
     const int kc = build_two_sided(s_tab2, thr_all + (size_t)chain * kThrStride, cd.n_thr);
     const uint2* s_dn = s_tab2 + kc;
     const uint2* s_up = s_tab2 + 3 * kc + 1;
+    pdl_wait();
+    if (ctr) sweep += *ctr;
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t sub = lane / G, kq = lane % G;
@@ -215,7 +233,7 @@ inline cudaError_t tiled_prepare(TiledPlan& p, const Geom& g, uint32_t, int, boo
     if ((uint64_t)g.X * g.Y * g.T >= (1ull << 35)) return cudaSuccess;
     if (g.chain_stride >= (1ull << 31)) return cudaSuccess;
     p.g = (int)G;
-    p.march = (g.Y % 8 == 0) ? 8 : 2;
+    p.march = (g.Y % kMarchLong == 0) ? kMarchLong : 2;
     p.enabled = true;
     return cudaSuccess;
 }
@@ -235,6 +253,7 @@ struct MarchArgs {
     uint32_t max_thr;
     bool wilson, count;
     cudaStream_t stream;
+    bool pdl;  // launch with programmatic stream serialization
 };
 
 template <int G, int MARCH>
@@ -243,9 +262,19 @@ inline cudaError_t march_launch(const MarchArgs& a) {
     dim3 grid((a.g.Y + R * MARCH - 1) / (R * MARCH), (a.n_planes + kMarchWarps - 1) / kMarchWarps, a.n_chains);
     const uint32_t kc = a.max_thr > 4 ? a.max_thr - 1 : 3;
     const size_t smem = sizeof(uint2) * 2 * (2 * kc + 1);
-#define LQFT_GO(W, C)                                                                                          \
-    k_sweep_march<G, MARCH, W, C><<<grid, kMarchWarps * 32, smem, a.stream>>>(a.g, a.colour, a.sweep, a.ctr, a.tl_first, \
-                                                                             a.n_planes, a.own, a.oth, a.chains, a.thr, a.acc)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kMarchWarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = a.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = a.pdl ? 1 : 0;
+#define LQFT_GO(W, C)                                                                                              \
+    return cudaLaunchKernelEx(&cfg, k_sweep_march<G, MARCH, W, C>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_planes, \
+                              a.own, a.oth, a.chains, a.thr, a.acc)
     if (a.wilson) {
         if (a.count) LQFT_GO(true, true); else LQFT_GO(true, false);
     } else {
@@ -258,13 +287,15 @@ inline cudaError_t march_launch(const MarchArgs& a) {
 // One half-sweep of `colour` over local planes [tl_first, tl_first + n_planes).
 inline cudaError_t tiled_half(const TiledPlan& p, const MarchArgs& a) {
 #define LQFT_MARCH(GV) \
-    case GV: return p.march == 8 ? march_launch<GV, 8>(a) : march_launch<GV, 2>(a)
+    case GV: return p.march == kMarchLong ? march_launch<GV, kMarchLong>(a) : march_launch<GV, 2>(a)
     switch (p.g) {
+#ifndef LQFT_G32_ONLY
         LQFT_MARCH(1);
         LQFT_MARCH(2);
         LQFT_MARCH(4);
         LQFT_MARCH(8);
         LQFT_MARCH(16);
+#endif
         LQFT_MARCH(32);
         default: return cudaErrorInvalidValue;
     }

@@ -8,6 +8,7 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "../../include/lqft.h"
+#include "kernels_stream.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_v1.cuh"
 #include "spec.cuh"
@@ -156,6 +158,7 @@ struct lqft_handle {
     int sm_count = 148;
     std::map<GraphKey, GraphVal> graphs;
     TiledPlan tiled{};
+    StreamPlan streamp{};
 };
 
 static lqft_status use_device(lqft_handle* h) {
@@ -182,8 +185,15 @@ static lqft_status upload_params(lqft_handle* h) {
         h->max_thr = std::max(h->max_thr, h->chains_h[c].n_thr);
     }
     h->params_dirty = false;
+    CU(stream_prepare(h->streamp, h->g, h->sm_count, h->max_thr,
+                      (h->cfg.flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_STREAM)) != 0));
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
+    if (getenv("LQFT_DEBUG"))
+        fprintf(stderr, "[lqft] %ux%ux%u chains=%u path=%s (stream: segs=%d blocks/SM=%d chunks=%u; march: g=%d rows=%d)\n",
+                h->g.X, h->g.Y, h->g.T, nc, h->streamp.enabled ? "stream" : (h->tiled.enabled ? "march" : "v1"),
+                h->streamp.segs, h->streamp.blocks_per_sm,
+                h->streamp.enabled ? stream_chunks(h->streamp, h->g, h->g.Tl, nc) : 0u, h->tiled.g, h->tiled.march);
     return LQFT_OK;
 }
 
@@ -503,10 +513,12 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
     const Geom& g = h->g;
     int32_t* own = h->field[colour];
     const int32_t* oth = h->field[colour ^ 1];
-    if (h->tiled.enabled) {
+    if (h->streamp.enabled || h->tiled.enabled) {
         MarchArgs a{g, colour, sweep, ctr, tl_first, n_planes, h->cfg.n_chains, own, oth, h->chains_d, h->thr_d,
-                    h->acc_d, h->max_thr, h->any_wilson, h->count_accepts, s};
-        CU(tiled_half(h->tiled, a));
+                    h->acc_d, h->max_thr, h->any_wilson, h->count_accepts, s,
+                    !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
+        if (h->streamp.enabled) CU(stream_half(h->streamp, a));
+        else CU(tiled_half(h->tiled, a));
         h->launches += 1;
         return LQFT_OK;
     }
@@ -666,16 +678,16 @@ static lqft_status read_accepted(lqft_handle* h, uint64_t* accepted) {
     return LQFT_OK;
 }
 
+static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_obs, int64_t* e_int, uint64_t* accepted);
+
 extern "C" lqft_status lqft_sweep(lqft_handle* h, uint64_t first_sweep, uint32_t n_sweeps, uint64_t* accepted) {
-    ST(ready(h));
-    h->count_accepts = accepted != nullptr;
-    if (accepted) CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * (size_t)h->cfg.n_chains * kAccSlots, h->stream));
-    CU(cudaEventRecord(h->ev_start, h->stream));
-    for (uint32_t s = 0; s < n_sweeps; ++s) ST(launch_sweep(h, first_sweep + s, nullptr));
-    CU(cudaEventRecord(h->ev_stop, h->stream));
-    h->timed = true;
-    if (accepted) ST(read_accepted(h, accepted));
-    return LQFT_OK;
+    lqft_schedule s{};
+    s.sweep_base = first_sweep;
+    s.first_step = 0;
+    s.n_steps = n_sweeps;
+    s.energy_every = 0;
+    s.normalize_every = 0;
+    return run_impl(h, &s, nullptr, nullptr, accepted);
 }
 
 extern "C" lqft_status lqft_normalize(lqft_handle* h, uint64_t sweep_index) {
@@ -889,6 +901,10 @@ static uint64_t gcd64(uint64_t a, uint64_t b) { return b ? gcd64(b, a % b) : a; 
 
 extern "C" lqft_status lqft_run(lqft_handle* h, const lqft_schedule* s, double* e_obs, int64_t* e_int,
                                 uint64_t* accepted) {
+    return run_impl(h, s, e_obs, e_int, accepted);
+}
+
+static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_obs, int64_t* e_int, uint64_t* accepted) {
     if (!s) return fail(LQFT_ERR_INVALID, "null schedule");
     ST(ready(h));
     h->count_accepts = accepted != nullptr;
@@ -913,8 +929,10 @@ extern "C" lqft_status lqft_run(lqft_handle* h, const lqft_schedule* s, double* 
 
     const uint64_t ee = s->energy_every ? s->energy_every : 1, ne = s->normalize_every ? s->normalize_every : 1;
     const uint64_t cycle = ee / gcd64(ee, ne) * ne;
+    // one captured graph = `reps` cycles (about kGraphSteps sweeps); it is replayed while whole periods remain
+    constexpr uint64_t kGraphSteps = 32;
     const bool use_graph = !(h->cfg.flags & LQFT_FLAG_NO_GRAPH) && h->cfg.world_size <= 1 && cycle <= 64 &&
-                           s->n_steps >= 2 * cycle;
+                           s->n_steps >= 2 * cycle && s->n_steps >= 8;
 
     CU(cudaEventRecord(h->ev_start, h->stream));
     uint64_t step = s->first_step;
@@ -924,21 +942,24 @@ extern "C" lqft_status lqft_run(lqft_handle* h, const lqft_schedule* s, double* 
             ST(launch_step(h, s, step, step, nullptr));
             ++step;
         }
-        const uint64_t n_cycles = (end - step) / cycle;
-        if (n_cycles) {
-            GraphKey key{s->energy_every, s->normalize_every, (uint32_t)cycle, h->count_accepts};
+        const uint64_t avail = (end - step) / cycle;
+        const uint64_t reps = std::max<uint64_t>(1, std::min<uint64_t>(avail, std::max<uint64_t>(1, kGraphSteps / cycle)));
+        const uint64_t period = reps * cycle;
+        const uint64_t n_periods = (end - step) / period;
+        if (n_periods) {
+            GraphKey key{s->energy_every, s->normalize_every, (uint32_t)period, h->count_accepts};
             auto it = h->graphs.find(key);
             if (it == h->graphs.end()) {
-                // capture one cycle; every kernel reads the sweep counter from device memory
+                // capture one period; every kernel reads the sweep counter from device memory
                 const uint64_t before = h->launches;
                 lqft_schedule rel = *s;
                 rel.sweep_base = 0;
                 cudaGraph_t graph = nullptr;
                 CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                 lqft_status st = LQFT_OK;
-                for (uint64_t i = 0; i < cycle && st == LQFT_OK; ++i) st = launch_step(h, &rel, i, i, h->sweep_ctr_d);
+                for (uint64_t i = 0; i < period && st == LQFT_OK; ++i) st = launch_step(h, &rel, i, i, h->sweep_ctr_d);
                 if (st == LQFT_OK) {
-                    k_tick<<<1, 1, 0, h->stream>>>(h->sweep_ctr_d, cycle);
+                    k_tick<<<1, 1, 0, h->stream>>>(h->sweep_ctr_d, period);
                     h->launches += 1;
                 }
                 cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
@@ -957,9 +978,9 @@ extern "C" lqft_status lqft_run(lqft_handle* h, const lqft_schedule* s, double* 
             }
             const uint64_t base = s->sweep_base + step;
             CU(cudaMemcpyAsync(h->sweep_ctr_d, &base, sizeof base, cudaMemcpyHostToDevice, h->stream));
-            for (uint64_t c = 0; c < n_cycles; ++c) CU(cudaGraphLaunch(it->second.exec, h->stream));
-            h->launches += it->second.kernels * n_cycles;
-            step += n_cycles * cycle;
+            for (uint64_t c = 0; c < n_periods; ++c) CU(cudaGraphLaunch(it->second.exec, h->stream));
+            h->launches += it->second.kernels * n_periods;
+            step += n_periods * period;
         }
     }
     while (step < end) {

@@ -71,6 +71,31 @@ def test_sweep_bit_exact_vs_oracle(size, beta, wilson):
         assert got_acc == want_acc
 
 
+@pytest.mark.parametrize("size,beta,wilson", [
+    ((256, 8, 4), 0.25, (0, 0)), ((256, 4, 2), 0.2, (100, 2)), ((256, 10, 6), 0.3, (0, 0)),
+    ((512, 4, 4), 0.25, (0, 0)), ((512, 6, 2), 0.22, (300, 1)), ((1024, 4, 2), 0.25, (0, 0)),
+    ((1024, 2, 4), 0.28, (1000, 3)), ((256, 36, 2), 0.25, (0, 0)),
+])
+def test_wide_row_kernels_bit_exact_vs_oracle(size, beta, wilson):
+    """Streaming (cp.async ring, X = 256/512/1024), marching, vector and scalar kernels all equal the oracle."""
+    X, Y, T = size
+    seed = 0xBEEF + X + Y
+    v0 = seeded_field(X * Y * T, seed=X + 7 * Y)
+    want = v0.copy()
+    want_acc = oracle_sweeps(size, want, beta, seed, 10, 3, wilson)
+    for flags in (0, _lib.FLAG_NO_STREAM, _lib.FLAG_FORCE_V1, _lib.FLAG_FORCE_GENERIC):
+        with Engine(X, Y, T, flags=flags) as eng:
+            eng.set_chain(0, beta, seed, *wilson)
+            eng.upload(0, v0)
+            got_acc = eng.sweep(10, 3, want_accepted=True)[0]
+            eng.sweep(13, 2)              # the non-counting instantiation
+            got2 = eng.download(0)
+        want2 = want.copy()
+        oracle_sweeps(size, want2, beta, seed, 13, 2, wilson)
+        assert got_acc == want_acc, flags
+        assert (got2 == want2).all(), f"{int((got2 != want2).sum())} sites differ (flags={flags})"
+
+
 def test_hot_start_matches_oracle():
     with Engine(16, 8, 4) as eng:
         eng.set_chain(0, 0.2, 99)
