@@ -548,3 +548,55 @@ double orc_bench_chains(const orc_lattice* l, double temp, uint64_t seed, uint64
     free(th);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---------------------------------------------------------------------------------------- */
+/* slab form (multi-GPU decomposition check): the same per-site rule on one rank's t-slab      */
+/* ---------------------------------------------------------------------------------------- */
+/* `values` holds (tl + 2) planes of X*Y sites in lexicographic order: plane 0 = ghost (global
+ * plane t0-1), planes 1..tl = owned (global t0 .. t0+tl-1), plane tl+1 = ghost.  One half-sweep of
+ * `colour` over the owned planes, RNG keyed by the GLOBAL site index, Wilson sheet by global
+ * coordinates (fields.rs:556-561).  Returns #accepted. */
+uint64_t orc_half_sweep_slab(uint32_t X, uint32_t Y, uint32_t T, uint32_t t0, uint32_t tl, int32_t* values,
+                             int colour, double temp, uint64_t seed, uint64_t sweep, uint32_t wil_w,
+                             uint32_t wil_h) {
+    (void)T;
+    uint64_t acc = 0;
+    const uint64_t plane = (uint64_t)X * Y;
+    for (uint32_t p = 1; p <= tl; ++p) {
+        const uint32_t t = t0 + p - 1;
+        for (uint32_t y = 0; y < Y; ++y)
+            for (uint32_t x = 0; x < X; ++x) {
+                if (((x + y + t) & 1u) != (uint32_t)colour) continue;
+                const uint64_t here = p * plane + (uint64_t)y * X + x;
+                const uint64_t nb[6] = {
+                    p * plane + (uint64_t)y * X + (x + 1) % X,       p * plane + (uint64_t)((y + 1) % Y) * X + x,
+                    (p + 1) * plane + (uint64_t)y * X + x,           p * plane + (uint64_t)y * X + (x + X - 1) % X,
+                    p * plane + (uint64_t)((y + Y - 1) % Y) * X + x, (p - 1) * plane + (uint64_t)y * X + x};
+                /* Wilson: +1 seen from (x,0,t) along +y, -1 seen from (x,1,t) along -y */
+                int32_t mod[6] = {0, 0, 0, 0, 0, 0};
+                if (wil_w && wil_h && x < wil_w && t < wil_h) {
+                    if (y == 0) mod[1] = 1;
+                    if (y == 1 % Y) mod[4] = -1;
+                }
+                const uint64_t gidx = (uint64_t)t * plane + (uint64_t)y * X + x;
+                const uint32_t word = orc_site_word(seed, gidx, (uint32_t)colour, sweep);
+                const int coin = (int)(word >> 31);
+                const double draw = (double)(word & 0x7fffffffu) * (1.0 / 2147483648.0);
+                const int32_t old_value = values[here];
+                const int32_t new_value = coin ? old_value + 1 : old_value - 1;
+                uint32_t old_action = 0, new_action = 0;
+                for (int d = 0; d < 6; ++d) {
+                    const uint32_t d0 = (uint32_t)old_value - (uint32_t)values[nb[d]] + (uint32_t)mod[d];
+                    const uint32_t d1 = (uint32_t)new_value - (uint32_t)values[nb[d]] + (uint32_t)mod[d];
+                    old_action += d0 * d0;
+                    new_action += d1 * d1;
+                }
+                const double prob = exp((double)(int32_t)(old_action - new_action) * temp);
+                if (draw <= prob) {
+                    values[here] = new_value;
+                    ++acc;
+                }
+            }
+    }
+    return acc;
+}

@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
             "orc_sizeof_welford": (u64, []),
             "orc_run": (u64, [vp, vp, vp, f64, u64, u64, u64, u64, u32, u32, C.c_int, vp, P(u64)]),
             "orc_bench_chains": (f64, [vp, f64, u64, u64, u32, u32, P(f64)]),
+            "orc_half_sweep_slab": (u64, [u32, u32, u32, u32, u32, vp, C.c_int, f64, u64, u64, u32, u32]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -243,3 +244,10 @@ def bench_chains(lat, temp, seed, sweeps, energy_every, threads):
     e = C.c_double()
     secs = lib().orc_bench_chains(lat._h, temp, seed, sweeps, energy_every, threads, C.byref(e))
     return float(secs), float(e.value)
+
+
+def half_sweep_slab(X, Y, T, t0, tl, values_with_ghosts, colour, temp, seed, sweep_index, wilson=(0, 0)) -> int:
+    """One colour of one sweep on a t-slab stored with one ghost plane on each side (in place)."""
+    v = values_with_ghosts
+    assert v.dtype == np.int32 and v.flags.c_contiguous and v.size == X * Y * (tl + 2)
+    return int(lib().orc_half_sweep_slab(X, Y, T, t0, tl, _ptr(v), colour, temp, seed, sweep_index, wilson[0], wilson[1]))

@@ -1,0 +1,80 @@
+"""Worker of tests/test_gpu_multi.py: run under torchrun with one rank per GPU.
+
+Checks that ONE lattice decomposed into t-slabs over the ranks gives, bit for bit, the result of the same
+lattice on a single GPU (and of the CPU oracle at the small size): sweeps, run schedule, energy / action,
+slice moments, correlator, normalize."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lattice_qft_b200 import Engine  # noqa: E402
+from lattice_qft_b200 import distributed as D  # noqa: E402
+from lattice_qft_b200 import engine as E  # noqa: E402
+
+
+def gather_field(eng, local):
+    rank, ws = D.world()
+    mine = torch.from_numpy(local).cuda()
+    parts = [torch.empty_like(mine) for _ in range(ws)]
+    dist.all_gather(parts, mine)
+    return torch.cat(parts).cpu().numpy()
+
+
+def check(size, beta, seed, wilson, n_sweeps, flags=0):
+    rank, ws = D.world()
+    X, Y, T = size
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    full = np.random.default_rng(1234).integers(-128, 128, size=X * Y * T, dtype=np.int32)
+    eng = D.slab_engine(X, Y, T, device=dev, flags=flags)
+    eng.set_chain(0, beta, seed, *wilson)
+    eng.upload(0, D.scatter_slab(full, X, Y, T, rank, ws))
+    acc = eng.sweep(0, n_sweeps, want_accepted=True)[0]
+    e_obs, e_int, _ = eng.run(12, first_step=0, sweep_base=n_sweeps, energy_every=4, normalize_every=10)
+    e_now = eng.energy()
+    s_now = eng.action()
+    s1, s2 = eng.slice_moments(0)
+    corr = eng.correlator(0, reps=10, sweep_index=5)
+    got = gather_field(eng, eng.download(0))
+    acc_t = torch.tensor([acc], dtype=torch.int64, device="cuda")
+    dist.all_reduce(acc_t)
+    eng.close()
+    if rank == 0:
+        ref = Engine(X, Y, T, device=dev, flags=flags)
+        ref.set_chain(0, beta, seed, *wilson)
+        ref.upload(0, full)
+        racc = ref.sweep(0, n_sweeps, want_accepted=True)[0]
+        r_obs, r_int, _ = ref.run(12, first_step=0, sweep_base=n_sweeps, energy_every=4, normalize_every=10)
+        assert int(acc_t.item()) == racc, (int(acc_t.item()), racc)
+        assert (r_int == e_int).all() and (r_obs == e_obs).all()
+        assert (ref.energy()[0] == e_now[0]).all() and (ref.action()[0] == s_now[0]).all()
+        r1, r2 = ref.slice_moments(0)
+        assert (r1 == s1).all() and (r2 == s2).all()
+        assert (ref.correlator(0, reps=10, sweep_index=5) == corr).all()
+        want = ref.download(0)
+        assert (want == got).all(), f"{int((want != got).sum())} sites differ for {size} ws={ws}"
+        ref.close()
+        print(f"ok {size} ws={ws} flags={flags} accepted={racc}", flush=True)
+    dist.barrier()
+
+
+def main():
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    ws = dist.get_world_size()
+    check((16, 16, 8 * ws), 0.25, 77, (0, 0), 4)
+    check((8, 6, 4 * ws), 0.3, 5, (5, 3), 5)
+    check((64, 32, 4 * ws), 0.22, 9, (21, 6), 3)
+    check((256, 16, 4 * ws), 0.25, 11, (0, 0), 3)           # streaming kernel on slabs
+    check((256, 16, 4 * ws), 0.25, 11, (0, 0), 3, flags=2)  # scalar kernels on slabs
+    check((512, 8, 2 * ws), 0.25, 12, (100, 3), 2)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
