@@ -26,7 +26,7 @@ def _sources():
 
 
 def stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(os.path.join(PKG, "lqft_sim")):
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(s) > t for s in _sources())
@@ -45,7 +45,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.replace(LIB + ".tmp", LIB)
     if verbose:
         print(res.stderr)
+    build_host_driver()
     return LIB
+
+
+SIM = os.path.join(PKG, "lqft_sim")
+
+
+def build_host_driver() -> str:
+    """g++ -> lattice_qft_b200/lqft_sim: src/bin/sim.rs written against the C++ host mirror."""
+    cmd = ["g++", "-O2", "-std=c++17", "-o", SIM + ".tmp", os.path.join(CSRC, "host", "sim.cpp"), "-L", PKG, "-llqft",
+           "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    os.replace(SIM + ".tmp", SIM)
+    return SIM
 
 
 if __name__ == "__main__":

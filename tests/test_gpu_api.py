@@ -120,3 +120,26 @@ def test_wilson_sim_quirks():
 def test_cluster_algorithms_are_out_of_scope():
     with pytest.raises(NotImplementedError):
         AlgorithmType.new_cluster()
+
+
+def test_cpp_host_driver_matches_oracle(tmp_path):
+    """lqft_sim = src/bin/sim.rs against the C++ host mirror (lattice_qft.hpp): same schedule, same CSVs."""
+    import os
+    import subprocess
+    from lattice_qft_b200 import _build
+    root = str(tmp_path)
+    res = subprocess.run([_build.SIM, "8", "10", "30", "--temps", "0.2,0.26", "--energy", "10", "--corr", "4", "15",
+                          "--root", root], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    rows = open(os.path.join(root, "data", "results.csv")).read().splitlines()
+    assert rows[1].startswith("0,3,512,8,8,8,0.2,Metropolis Simulation,10,30,") and rows[1].endswith(",,false,true,false,true")
+    assert rows[2].startswith("1,3,512,8,8,8,0.26,Metropolis Simulation,10,30,")
+    olat = O.Lattice([8, 8, 8])
+    for index, (temp, seed) in enumerate([(0.2, 0xC0FFEE), (0.26, 0xC0FFEE + 1)]):
+        want = O.init_hot(olat, seed)
+        O.run(olat, want, temp, seed, 0, 0, 10, 0, 10, order=1)
+        we, _ = O.run(olat, want, temp, seed, 10, 0, 30, 10, 10, order=1)
+        got = [float(v) for v in open(os.path.join(root, "data", "energy_data", f"energy_{index}.csv")).read().split()]
+        assert got == we.tolist()
+        corr = open(os.path.join(root, "data", "correlation_data", f"correlation_{index}.csv")).read().splitlines()
+        assert len(corr) == 2 and len(corr[0].split(",")) == 8
