@@ -86,10 +86,33 @@ def make_reference_energies():
     return out
 
 
+def make_reference_corr_lengths():
+    """Second-moment correlation lengths (corr12 +- corr12_err, largest bin size) keyed by (L, temp)."""
+    runs = {}
+    with open(os.path.join(REF, "results_comp.csv")) as fh:
+        for row in csv.DictReader(fh):
+            runs[int(row["index"])] = row
+    out = []
+    for idx, row in sorted(runs.items()):
+        path = os.path.join(REF, "comp_correlation_stats", f"correlation_{idx}_len.csv")
+        if not os.path.exists(path):
+            continue
+        with open(path) as fh:
+            stats = {int(r["bin_size"]): r for r in csv.DictReader(fh)}
+        s = stats[max(stats)]
+        if not s["corr12"] or not s["corr12_err"]:
+            continue
+        out.append({"index": idx, "x": int(row["x"]), "y": int(row["y"]), "t": int(row["t"]), "temp": float(row["temp"]),
+                    "bin_size": max(stats), "corr12": float(s["corr12"]), "corr12_err": float(s["corr12_err"])})
+    return out
+
+
 if __name__ == "__main__":
     with open(os.path.join(HERE, "sweep_golden.json"), "w") as fh:
         json.dump(make_sweeps(), fh, indent=1)
     if os.path.isdir(REF):
         with open(os.path.join(HERE, "reference_energies.json"), "w") as fh:
             json.dump(make_reference_energies(), fh, indent=1)
+        with open(os.path.join(HERE, "reference_corr_lengths.json"), "w") as fh:
+            json.dump(make_reference_corr_lengths(), fh, indent=1)
     print("ok")

@@ -1,0 +1,134 @@
+"""Ensemble parity with the reference's published data (tests/golden/reference_*.json, copied out of
+data/comp_energy_stats and data/comp_correlation_stats by tests/golden/make_golden.py): mean energy,
+Wilson-inserted energies and the second-moment correlation length must agree within 2 sigma, the errors
+on our side taken over independent chains (no autocorrelation).  Seeds are fixed, so the outcome is
+deterministic."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from lattice_qft_b200 import Engine, analysis
+from lattice_qft_b200.computation import NORMALIZE_EVERY
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+BURNIN = 1000  # sim.rs:18
+
+
+def ref_energy(L, temp, wilson=(0, 0)):
+    with open(os.path.join(GOLDEN, "reference_energies.json")) as fh:
+        rows = json.load(fh)
+    for r in rows:
+        if r["x"] == L and abs(r["temp"] - temp) < 1e-9 and tuple(r["wilson"]) == tuple(wilson):
+            return r["energy"], r["energy_err"]
+    raise KeyError((L, temp, wilson))
+
+
+def ref_xi(L, temp):
+    with open(os.path.join(GOLDEN, "reference_corr_lengths.json")) as fh:
+        rows = json.load(fh)
+    best = [r for r in rows if r["x"] == L and abs(r["temp"] - temp) < 1e-9]
+    return best[0]["corr12"], best[0]["corr12_err"]
+
+
+def test_symmetrize_kat():  # correlation_data_analysis.rs:550-556
+    assert analysis.symmetrize_single_correlation_function([1, 2, 3, 4, 5, 6]).tolist() == [1, 4, 4, 4, 4, 4]
+
+
+def test_xi_estimator_on_pure_cosh():
+    """lib.rs:106-120 recovers m exactly for C(t) = cosh(m (t - T/2)) on a periodic lattice."""
+    T, m = 32, 0.2
+    c = [np.cosh(m * (t - T / 2)) for t in range(T)]
+    assert analysis.second_moment_xi(c) == pytest.approx(1 / m, rel=1e-9)
+
+
+def run_chains(L, betas, chains_per_beta, iterations, every, wilson=None, seed0=0x5EED):
+    n = len(betas) * chains_per_beta
+    eng = Engine(L, L, L, n_chains=n)
+    for c in range(n):
+        b = c // chains_per_beta
+        w = wilson[b] if wilson else (0, 0)
+        eng.set_chain(c, betas[b], seed0 + c, *w)
+    eng.init_hot()
+    eng.run(BURNIN, energy_every=0, normalize_every=NORMALIZE_EVERY)
+    e_obs, _, _ = eng.run(iterations, sweep_base=BURNIN, energy_every=every, normalize_every=NORMALIZE_EVERY)
+    return eng, e_obs.reshape(len(betas), chains_per_beta, -1)
+
+
+@pytest.mark.gpu
+def test_free_energy_16_within_2_sigma():
+    """Config 1 (16^3, energy every 10th sweep) for beta = 0.20, 0.25, 0.29 — 48 independent chains each."""
+    betas = [0.20, 0.25, 0.29]
+    eng, e = run_chains(16, betas, 48, 40000, 10)
+    eng.close()
+    for b, beta in enumerate(betas):
+        mean, err = analysis.chain_mean_and_error(e[b].mean(axis=1))
+        ref, ref_err = ref_energy(16, beta)
+        z = (mean - ref) / np.hypot(err, ref_err)
+        print(f"16^3 beta={beta}: ours {mean:.3f} +- {err:.3f}  reference {ref:.3f} +- {ref_err:.3f}  z = {z:+.2f}")
+        assert abs(z) < 2.0
+    # analytic anchor E -> N/6 at small beta
+    assert abs(e[0].mean() - 4096 / 6) < 0.5
+
+
+@pytest.mark.gpu
+def test_free_energy_24_and_36_within_2_sigma():
+    for L, beta, chains, iters in ((24, 0.25, 32, 20000), (36, 0.22, 16, 10000)):
+        eng, e = run_chains(L, [beta], chains, iters, 10)
+        eng.close()
+        mean, err = analysis.chain_mean_and_error(e[0].mean(axis=1))
+        ref, ref_err = ref_energy(L, beta)
+        z = (mean - ref) / np.hypot(err, ref_err)
+        print(f"{L}^3 beta={beta}: ours {mean:.3f} +- {err:.3f}  reference {ref:.3f} +- {ref_err:.3f}  z = {z:+.2f}")
+        assert abs(z) < 2.0
+
+
+@pytest.mark.gpu
+def test_wilson_energies_16_within_2_sigma():
+    """Wilson-inserted chains: sampling with the shifted sheet, energy of the PLAIN field every sweep (Q3, Q4)."""
+    widths = [2, 8, 13]
+    eng, e = run_chains(16, [0.2] * len(widths), 32, 20000, 1, wilson=[(w, 16) for w in widths])
+    eng.close()
+    for b, w in enumerate(widths):
+        mean, err = analysis.chain_mean_and_error(e[b].mean(axis=1))
+        ref, ref_err = ref_energy(16, 0.2, (w, 16))
+        z = (mean - ref) / np.hypot(err, ref_err)
+        print(f"16^3 Wilson {w}x16: ours {mean:.3f} +- {err:.3f}  reference {ref:.3f} +- {ref_err:.3f}  z = {z:+.2f}")
+        assert abs(z) < 2.0
+
+
+@pytest.mark.gpu
+def test_string_tension_slope_16():
+    """E(R) - E_free grows linearly in R; slope (string tension * L) vs data/string_tension_results.csv: 3.005 at beta=0.2."""
+    widths = [2, 5, 8, 10, 13]
+    eng, e = run_chains(16, [0.2] * (len(widths) + 1), 24, 20000, 1, wilson=[(w, 16) for w in widths] + [(0, 0)])
+    eng.close()
+    means = e.mean(axis=(1, 2))
+    slope = np.polyfit(widths, means[:-1], 1)[0]
+    print(f"string tension slope 16^3 beta=0.2: {slope:.4f} (reference 3.0050)")
+    assert slope == pytest.approx(3.005, abs=0.06)
+
+
+@pytest.mark.gpu
+def test_correlation_length_16_within_2_sigma():
+    """Config 3 shape at 16^3: correlator with 100 reference sites every 10th sweep, xi_12 via lib.rs:106-120."""
+    L, beta, chains, meas = 16, 0.28, 24, 400
+    eng = Engine(L, L, L, n_chains=chains)
+    for c in range(chains):
+        eng.set_chain(c, beta, 0xABCD + c)
+    eng.init_hot()
+    eng.run(BURNIN, energy_every=0, normalize_every=NORMALIZE_EVERY)
+    acc = np.zeros((chains, L))
+    sweep = BURNIN
+    for m in range(meas):
+        eng.run(10, first_step=m * 10, sweep_base=BURNIN, energy_every=0, normalize_every=NORMALIZE_EVERY)
+        sweep += 10
+        for c in range(chains):
+            acc[c] += eng.correlator(c, reps=100, sweep_index=sweep)
+    eng.close()
+    xi, err = analysis.jackknife(acc / meas, analysis.second_moment_xi)
+    ref, ref_err = ref_xi(L, beta)
+    z = (xi - ref) / np.hypot(err, ref_err)
+    print(f"16^3 beta={beta}: xi_12 = {xi:.3f} +- {err:.3f}  reference {ref:.3f} +- {ref_err:.3f}  z = {z:+.2f}")
+    assert abs(z) < 2.0
