@@ -61,6 +61,57 @@ __device__ __forceinline__ int lds32(uint32_t addr) {
     return v;
 }
 
+// ---- peer-memory halo (world_size > 1): the sweep kernel pushes its boundary rows straight into the
+// neighbours' ghost planes over NVLink and publishes a phase flag when its boundary blocks are done;
+// the warps that read a ghost plane wait for the neighbour's flag of the previous phase.  No separate
+// pack / send / receive launches and no collective on the critical path.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag >= need.  Bounded: after 4 s the error word is set and the caller proceeds, so a lost
+// neighbour surfaces as LQFT_ERR_STATE on the host instead of a hung device.
+__device__ __forceinline__ void halo_wait(const unsigned long long* flag, unsigned long long need, unsigned int* error) {
+    if (ld_acquire_sys(flag) >= need) return;
+    if (*reinterpret_cast<volatile unsigned int*>(error)) return;  // already broken: do not stack timeouts
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) < need) {
+        __nanosleep(64);
+        if (global_timer_ns() - t0 > 4000000000ull) {
+            atomicExch(error, 1u);
+            break;
+        }
+    }
+}
+
+// One thread: wait for both neighbours' flags (before an operation that reads or rewrites ghost planes).
+__global__ void k_halo_wait(HaloSync* mine, unsigned long long need) {
+    halo_wait(&mine->from_lo, need, &mine->error);
+    halo_wait(&mine->from_hi, need, &mine->error);
+}
+// One thread: publish `phase` to both neighbours (after such an operation).
+__global__ void k_halo_signal(HaloSync* lo_sync, HaloSync* hi_sync, unsigned long long phase) {
+    st_release_sys(&lo_sync->from_hi, phase);
+    st_release_sys(&hi_sync->from_lo, phase);
+}
+
 // Everything a thread needs to issue the loads of one row.
 struct StreamPtrs {
     const int4* own;   // own colour, this plane, row 0 of the chunk's plane (quad column kq)
@@ -86,8 +137,8 @@ __device__ __forceinline__ void stream_issue(const StreamPtrs& q, uint32_t y, ui
     }
 }
 
-template <int SEGS, bool WILSON, bool COUNT, bool P>
-__device__ __forceinline__ void stream_step(int4* __restrict__ own_row, uint32_t ring, uint32_t edge_ring, uint32_t stage,
+template <int SEGS, bool WILSON, bool COUNT, bool HALO, bool P>
+__device__ __forceinline__ void stream_step(int4* __restrict__ own_row, int4* __restrict__ peer_row, uint32_t ring, uint32_t edge_ring, uint32_t stage,
                                             int4& om, int4& oc, const uint32_t src_lane, const bool edge_lane,
                                             const uint32_t grp, const uint32_t colour, const uint64_t sweep,
                                             const RoundKeys& rk, const uint2* __restrict__ s_dn,
@@ -130,13 +181,17 @@ __device__ __forceinline__ void stream_step(int4* __restrict__ own_row, uint32_t
     w.z = metropolis_update2<COUNT>(v.z, ns.z, off.z, r.z, s_dn, s_up, kc, accepted);
     w.w = metropolis_update2<COUNT>(v.w, ns.w, off.w, r.w, s_dn, s_up, kc, accepted);
     *own_row = w;
+    if (HALO) {
+        if (peer_row) *peer_row = w;  // boundary plane: the neighbour's ghost copy, over NVLink
+    }
     om = oc;
     oc = on;
 }
 
 // The chunk [y_begin, y_end) of one plane, parity P0 at y_begin.
-template <int SEGS, bool WILSON, bool COUNT, bool P0>
-__device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, const StreamPtrs& q, const uint32_t y_begin,
+template <int SEGS, bool WILSON, bool COUNT, bool HALO, bool P0>
+__device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, int4* __restrict__ peer_w, const StreamPtrs& q,
+                                             const uint32_t y_begin,
                                              const uint32_t y_end, const uint32_t Y, const uint32_t ring,
                                              const uint32_t edge_ring, const uint32_t lane, const uint32_t kq,
                                              const uint32_t grp_row0, const uint32_t colour, const uint64_t sweep,
@@ -171,7 +226,7 @@ __device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, const Str
         const uint32_t y = y_begin + s;
         const uint32_t st0 = s & (uint32_t)(D - 1), st1 = (s + 1u) & (uint32_t)(D - 1);
         cp_async_wait<D - 1>();
-        stream_step<SEGS, WILSON, COUNT, P0>(own_w + y * G, ring, edge_ring, st0, om, oc, P0 ? src_up : src_dn,
+        stream_step<SEGS, WILSON, COUNT, HALO, P0>(own_w + y * G, (HALO && peer_w) ? peer_w + y * G : nullptr, ring, edge_ring, st0, om, oc, P0 ? src_up : src_dn,
                                              P0 ? edge_p : edge_n, grp_row0 + y * G, colour, sweep, rk, s_dn, s_up, kc,
                                              y, Y, kq, wil_plane, wil_w, accepted);
         if (s + D < n_steps) {
@@ -180,7 +235,8 @@ __device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, const Str
         }
         cp_async_commit();
         cp_async_wait<D - 1>();
-        stream_step<SEGS, WILSON, COUNT, !P0>(own_w + (y + 1u) * G, ring, edge_ring, st1, om, oc, P0 ? src_dn : src_up,
+        stream_step<SEGS, WILSON, COUNT, HALO, !P0>(own_w + (y + 1u) * G, (HALO && peer_w) ? peer_w + (y + 1u) * G : nullptr, ring, edge_ring,
+                                              st1, om, oc, P0 ? src_dn : src_up,
                                               P0 ? edge_n : edge_p, grp_row0 + (y + 1u) * G, colour, sweep, rk, s_dn,
                                               s_up, kc, y + 1u, Y, kq, wil_plane, wil_w, accepted);
         if (s + 1u + D < n_steps) {
@@ -193,13 +249,13 @@ __device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, const Str
 }
 
 // grid = (n_chunks * SEGS, ceil(n_planes / kStreamWarps), n_chains), block = kStreamThreads.
-template <int SEGS, bool WILSON, bool COUNT>
-__global__ void __launch_bounds__(kStreamThreads, LQFT_STREAM_MINBLOCKS)
+template <int SEGS, bool WILSON, bool COUNT, bool HALO>
+__global__ void __launch_bounds__(kStreamThreads, HALO ? LQFT_STREAM_MINBLOCKS - 1 : LQFT_STREAM_MINBLOCKS)
 k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr,
                const uint32_t tl_first, const uint32_t n_planes, const uint32_t n_chunks,
                int32_t* __restrict__ own_base, const int32_t* __restrict__ oth_base,
                const ChainDev* __restrict__ chains, const uint32_t* __restrict__ thr_all,
-               unsigned long long* __restrict__ acc) {
+               unsigned long long* __restrict__ acc, const HaloP2P halo) {
     constexpr uint32_t G = 32u * SEGS;
     constexpr uint32_t RING_BYTES = (uint32_t)kStreamDepth * 4u * kStreamThreads * 16u;
     constexpr uint32_t EDGE_BYTES = SEGS > 1 ? (uint32_t)kStreamDepth * kStreamThreads * 4u : 0u;
@@ -242,17 +298,44 @@ k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* _
         const bool wil_plane = WILSON && tg < cd.wil_h;
         const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
         const uint32_t grp_row0 = tg * g.Y * G + kq;  // Philox counter word 0 of this quad column at y = 0
+        int4* peer_w = nullptr;
+        if (HALO && halo.enabled) {  // warp uniform
+            if (tl == 0u) {
+                if (lane == 0u) halo_wait(&halo.mine->from_lo, halo.wait_for, &halo.mine->error);
+                if (halo.enabled == 1u) peer_w = reinterpret_cast<int4*>(halo.lo_ghost + cbase) + kq;
+            } else if (tl + 1u == g.Tl) {
+                if (lane == 0u) halo_wait(&halo.mine->from_hi, halo.wait_for, &halo.mine->error);
+                if (halo.enabled == 1u) peer_w = reinterpret_cast<int4*>(halo.hi_ghost + cbase) + kq;
+            }
+            __syncwarp();
+        }
         if ((y_begin + tg + (uint32_t)colour) & 1u)
-            stream_chunk<SEGS, WILSON, COUNT, true>(own_w, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
+            stream_chunk<SEGS, WILSON, COUNT, HALO, true>(own_w, peer_w, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
                                                     (uint32_t)colour, sweep, rk, s_dn, s_up, kc, wil_plane, cd.wil_w,
                                                     accepted);
         else
-            stream_chunk<SEGS, WILSON, COUNT, false>(own_w, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
+            stream_chunk<SEGS, WILSON, COUNT, HALO, false>(own_w, peer_w, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
                                                      (uint32_t)colour, sweep, rk, s_dn, s_up, kc, wil_plane, cd.wil_w,
                                                      accepted);
     }
     if (COUNT)
         block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
+    if (HALO && halo.enabled) {
+        // the last boundary block to finish publishes this launch's phase to both neighbours
+        __syncthreads();
+        const bool boundary_block = blockIdx.y == 0u || blockIdx.y + 1u == gridDim.y;
+        if (boundary_block && threadIdx.x == 0) {
+            // release chain instead of sequentially-consistent fences (a MEMBAR.SC.SYS here costs ~10 us):
+            // the block's stores happen-before the bar.sync above, thread 0 releases them with the ticket
+            // increment, the last block acquires every ticket and releases the flag at system scope.
+            const unsigned int done = atom_add_acq_rel_gpu(&halo.mine->ticket, 1u);
+            if (done + 1u == halo.n_boundary_blocks) {
+                st_relaxed_gpu(&halo.mine->ticket, 0u);
+                st_release_sys(&halo.lo_sync->from_hi, halo.phase);
+                st_release_sys(&halo.hi_sync->from_lo, halo.phase);
+            }
+        }
+    }
 }
 
 struct StreamPlan {
@@ -269,17 +352,22 @@ inline size_t stream_smem_bytes(int segs, uint32_t max_thr) {
 }
 
 template <int SEGS>
-inline cudaError_t stream_occupancy(int* blocks, size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_sweep_stream<SEGS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+inline cudaError_t stream_occupancy(int* blocks, size_t smem, bool halo) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_stream<SEGS, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(k_sweep_stream<SEGS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_sweep_stream<SEGS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_sweep_stream<SEGS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k_sweep_stream<SEGS, false, false>, kStreamThreads, smem);
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sweep_stream<SEGS, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (halo) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k_sweep_stream<SEGS, false, false, true>, kStreamThreads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k_sweep_stream<SEGS, false, false, false>, kStreamThreads, smem);
 }
 
 // Applies to X in {256, 512, 1024}.
-inline cudaError_t stream_prepare(StreamPlan& p, const Geom& g, int sm_count, uint32_t max_thr, bool force_off) {
+inline cudaError_t stream_prepare(StreamPlan& p, const Geom& g, int sm_count, uint32_t max_thr, bool force_off, bool halo) {
     p.enabled = false;
     if (force_off) return cudaSuccess;
     if (g.X != 256 && g.X != 512 && g.X != 1024) return cudaSuccess;
@@ -290,9 +378,9 @@ inline cudaError_t stream_prepare(StreamPlan& p, const Geom& g, int sm_count, ui
     if (smem > 200 * 1024) return cudaSuccess;
     cudaError_t e = cudaSuccess;
     switch (p.segs) {
-        case 1: e = stream_occupancy<1>(&p.blocks_per_sm, smem); break;
-        case 2: e = stream_occupancy<2>(&p.blocks_per_sm, smem); break;
-        default: e = stream_occupancy<4>(&p.blocks_per_sm, smem); break;
+        case 1: e = stream_occupancy<1>(&p.blocks_per_sm, smem, halo); break;
+        case 2: e = stream_occupancy<2>(&p.blocks_per_sm, smem, halo); break;
+        default: e = stream_occupancy<4>(&p.blocks_per_sm, smem, halo); break;
     }
     if (e != cudaSuccess) return e;
     p.enabled = p.blocks_per_sm > 0;
@@ -311,7 +399,7 @@ inline uint32_t stream_chunks(const StreamPlan& p, const Geom& g, uint32_t n_pla
         const double waves = blocks / (double)slots;
         const double eff = waves / (double)(uint64_t)(waves + 0.999999);
         // prefer the fewest chunks among (nearly) equally efficient choices: fewer prologues
-        if (eff > best_eff + 0.02) {
+        if (eff > best_eff + 0.05) {
             best_eff = eff;
             best = nc;
         }
@@ -324,6 +412,8 @@ inline cudaError_t stream_launch(const StreamPlan& p, const MarchArgs& a) {
     const uint32_t n_chunks = stream_chunks(p, a.g, a.n_planes, a.n_chains);
     dim3 grid(n_chunks * SEGS, (a.n_planes + kStreamWarps - 1) / kStreamWarps, a.n_chains);
     const size_t smem = stream_smem_bytes(SEGS, a.max_thr);
+    HaloP2P halo = a.halo;
+    halo.n_boundary_blocks = grid.x * grid.z * (grid.y == 1 ? 1u : 2u);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kStreamThreads);
@@ -334,13 +424,20 @@ inline cudaError_t stream_launch(const StreamPlan& p, const MarchArgs& a) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = a.pdl ? 1 : 0;
-#define LQFT_GO(W, C)                                                                                                  \
-    return cudaLaunchKernelEx(&cfg, k_sweep_stream<SEGS, W, C>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_planes, \
-                              n_chunks, a.own, a.oth, a.chains, a.thr, a.acc)
+#define LQFT_GO(W, C, H)                                                                                                 \
+    return cudaLaunchKernelEx(&cfg, k_sweep_stream<SEGS, W, C, H>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_planes, \
+                              n_chunks, a.own, a.oth, a.chains, a.thr, a.acc, halo)
+    if (halo.enabled) {
+        if (a.wilson) {
+            if (a.count) LQFT_GO(true, true, true); else LQFT_GO(true, false, true);
+        } else {
+            if (a.count) LQFT_GO(false, true, true); else LQFT_GO(false, false, true);
+        }
+    }
     if (a.wilson) {
-        if (a.count) LQFT_GO(true, true); else LQFT_GO(true, false);
+        if (a.count) LQFT_GO(true, true, false); else LQFT_GO(true, false, false);
     } else {
-        if (a.count) LQFT_GO(false, true); else LQFT_GO(false, false);
+        if (a.count) LQFT_GO(false, true, false); else LQFT_GO(false, false, false);
     }
 #undef LQFT_GO
     return cudaGetLastError();

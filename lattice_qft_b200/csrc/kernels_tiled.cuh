@@ -239,6 +239,26 @@ inline cudaError_t tiled_prepare(TiledPlan& p, const Geom& g, uint32_t, int, boo
 }
 inline void tiled_release(TiledPlan&) {}
 
+// peer-memory halo descriptors (used by the streaming kernel, kernels_stream.cuh)
+struct HaloSync {  // lives in each rank's device memory, mapped into both neighbours
+    unsigned long long from_lo;   // last phase published by the lower neighbour (rank - 1)
+    unsigned long long from_hi;   // last phase published by the upper neighbour (rank + 1)
+    unsigned int ticket;          // boundary blocks of the running launch that have finished
+    unsigned int error;           // set when a flag wait timed out
+};
+
+struct HaloP2P {
+    int32_t* lo_ghost = nullptr;  // lower neighbour's UPPER ghost plane of the colour being updated (chain 0)
+    int32_t* hi_ghost = nullptr;  // upper neighbour's LOWER ghost plane
+    HaloSync* lo_sync = nullptr;  // lower neighbour's HaloSync (we write its from_hi)
+    HaloSync* hi_sync = nullptr;  // upper neighbour's HaloSync (we write its from_lo)
+    HaloSync* mine = nullptr;
+    unsigned long long phase = 0;     // published when this launch's boundary blocks are done
+    unsigned long long wait_for = 0;  // ghost readers wait until the neighbour has published >= this
+    uint32_t n_boundary_blocks = 0;
+    uint32_t enabled = 0;
+};
+
 struct MarchArgs {
     Geom g;
     int colour;
@@ -254,6 +274,7 @@ struct MarchArgs {
     bool wilson, count;
     cudaStream_t stream;
     bool pdl;  // launch with programmatic stream serialization
+    HaloP2P halo;  // peer-memory halo push (streaming kernel, world_size > 1)
 };
 
 template <int G, int MARCH>

@@ -67,6 +67,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -87,6 +88,7 @@ static lqft_status nccl_load() {
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     g_nccl.lib = lib;
@@ -159,6 +161,13 @@ struct lqft_handle {
     std::map<GraphKey, GraphVal> graphs;
     TiledPlan tiled{};
     StreamPlan streamp{};
+    // peer-memory halo (world_size > 1)
+    bool p2p = false;
+    HaloSync* halo_d = nullptr;                 // mine
+    void* peer_base[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [lo/hi][field0, field1, sync]
+    bool peer_same = false;                     // lo and hi are the same rank (world_size == 2)
+    bool self_halo = false;                     // LQFT_FLAG_SELF_HALO: this rank is its own neighbour
+    unsigned long long phase = 0;               // operations that touch ghost planes so far (same on every rank)
 };
 
 static lqft_status use_device(lqft_handle* h) {
@@ -186,7 +195,7 @@ static lqft_status upload_params(lqft_handle* h) {
     }
     h->params_dirty = false;
     CU(stream_prepare(h->streamp, h->g, h->sm_count, h->max_thr,
-                      (h->cfg.flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_STREAM)) != 0));
+                      (h->cfg.flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_STREAM)) != 0, h->p2p));
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
     if (getenv("LQFT_DEBUG"))
@@ -302,6 +311,93 @@ extern "C" lqft_status lqft_comm_unique_id(uint8_t id[128]) {
     return LQFT_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// peer-memory halo: map the neighbours' fields and HaloSync words through CUDA IPC
+// ---------------------------------------------------------------------------------------------
+static lqft_status setup_p2p(lqft_handle* h) {
+    h->p2p = false;
+    const int ws = (int)h->cfg.world_size, r = (int)h->cfg.rank;
+    struct Handles { cudaIpcMemHandle_t f0, f1, sync; };
+    Handles mine{};
+    bool ok = cudaIpcGetMemHandle(&mine.f0, h->field[0]) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.f1, h->field[1]) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.sync, h->halo_d) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    // every rank takes part in the exchange (and in the vote below) even if its own export failed
+    Handles* all_d = nullptr;
+    CU(cudaMalloc(&all_d, sizeof(Handles) * ws));
+    CU(cudaMemcpyAsync(all_d + r, &mine, sizeof(Handles), cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllGather(all_d + r, all_d, sizeof(Handles), ncclInt8, h->comm, h->stream));
+    std::vector<Handles> all(ws);
+    CU(cudaMemcpyAsync(all.data(), all_d, sizeof(Handles) * ws, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(all_d);
+    const int lo = (r + ws - 1) % ws, hi = (r + 1) % ws;
+    h->peer_same = lo == hi;
+    if (ok && !(h->cfg.flags & LQFT_FLAG_HALO_NCCL)) {
+        for (int side = 0; side < 2 && ok; ++side) {
+            if (side == 1 && h->peer_same) {
+                for (int k = 0; k < 3; ++k) h->peer_base[1][k] = h->peer_base[0][k];
+                break;
+            }
+            const Handles& ph = all[side == 0 ? lo : hi];
+            const cudaIpcMemHandle_t* hs[3] = {&ph.f0, &ph.f1, &ph.sync};
+            for (int k = 0; k < 3 && ok; ++k)
+                if (cudaIpcOpenMemHandle(&h->peer_base[side][k], *hs[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    h->peer_base[side][k] = nullptr;
+                    ok = false;
+                }
+        }
+    } else {
+        ok = false;
+    }
+    // all ranks must agree, or one side would wait for flags the other never writes
+    int* vote_d = nullptr;
+    CU(cudaMalloc(&vote_d, sizeof(int)));
+    const int v = ok ? 0 : 1;
+    CU(cudaMemcpyAsync(vote_d, &v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllReduce(vote_d, vote_d, 1, ncclInt32, ncclSum, h->comm, h->stream));
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, vote_d, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(vote_d);
+    h->p2p = bad == 0;
+    if (getenv("LQFT_DEBUG")) fprintf(stderr, "[lqft] rank %d/%d halo: %s\n", r, ws, h->p2p ? "peer memory (IPC)" : "NCCL send/recv");
+    return LQFT_OK;
+}
+
+// The streaming kernel carries the peer-memory halo; every other kernel uses the NCCL exchange.
+static bool halo_fused(const lqft_handle* h) { return h->p2p && h->streamp.enabled; }
+
+// Operations other than sweeps that read or rewrite ghost planes are phases too: wait until both
+// neighbours have finished the previous phase, run, then publish.
+static lqft_status ghost_op_begin(lqft_handle* h) {
+    if (!halo_fused(h)) return LQFT_OK;
+    k_halo_wait<<<1, 1, 0, h->stream>>>(h->halo_d, h->phase);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return LQFT_OK;
+}
+static lqft_status ghost_op_end(lqft_handle* h) {
+    if (!halo_fused(h)) return LQFT_OK;
+    h->phase += 1;
+    k_halo_signal<<<1, 1, 0, h->stream>>>((HaloSync*)h->peer_base[0][2], (HaloSync*)h->peer_base[1][2], h->phase);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return LQFT_OK;
+}
+
+static lqft_status check_halo_error(lqft_handle* h) {
+    if (!h->halo_d) return LQFT_OK;
+    HaloSync s{};
+    CU(cudaMemcpyAsync(&s, h->halo_d, sizeof s, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (s.error) return fail(LQFT_ERR_STATE, "halo exchange timed out waiting for a neighbour rank (phase %llu)", h->phase);
+    return LQFT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // lifetime
 // ---------------------------------------------------------------------------------------------
@@ -312,6 +408,12 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int side = 0; side < 2 && !h->self_halo; ++side) {
+        if (side == 1 && h->peer_same) break;
+        for (int k = 0; k < 3; ++k)
+            if (h->peer_base[side][k]) cudaIpcCloseMemHandle(h->peer_base[side][k]);
+    }
+    cudaFree(h->halo_d);
     tiled_release(h->tiled);
     cudaFree(h->field[0]); cudaFree(h->field[1]);
     cudaFree(h->chains_d); cudaFree(h->thr_d); cudaFree(h->acc_d); cudaFree(h->obs_d);
@@ -365,7 +467,8 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     Geom& g = h->g;
     g.X = X; g.Y = Y; g.T = T; g.Xh = X / 2;
     g.Tl = nt; g.t0 = t0;
-    g.ghost = ws > 1 ? 1 : 0;
+    const bool self_halo = ws == 1 && (cfg->flags & LQFT_FLAG_SELF_HALO);
+    g.ghost = (ws > 1 || self_halo) ? 1 : 0;
     g.plane = g.Xh * Y;
     g.chain_stride = (uint64_t)g.plane * (g.Tl + 2 * g.ghost);
     h->n_slab = (uint64_t)X * Y * nt;
@@ -411,6 +514,21 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         ncclUniqueId id;
         memcpy(&id, cfg->nccl_id, 128);
         NC(g_nccl.CommInitRank(&h->comm, (int)ws, id, (int)cfg->rank));
+        CU(cudaMalloc(&h->halo_d, sizeof(HaloSync)));
+        CU(cudaMemsetAsync(h->halo_d, 0, sizeof(HaloSync), h->stream));
+        ST(setup_p2p(h));
+    } else if (self_halo) {
+        // one rank that is its own lower and upper neighbour: the whole peer-memory halo path (pushes,
+        // flags, phases) on a single device
+        CU(cudaMalloc(&h->halo_d, sizeof(HaloSync)));
+        CU(cudaMemsetAsync(h->halo_d, 0, sizeof(HaloSync), h->stream));
+        for (int side = 0; side < 2; ++side) {
+            h->peer_base[side][0] = h->field[0];
+            h->peer_base[side][1] = h->field[1];
+            h->peer_base[side][2] = h->halo_d;
+        }
+        h->self_halo = true;
+        h->p2p = true;
     }
     CU(tiled_prepare(h->tiled, g, nc, h->sm_count, (cfg->flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1)) != 0));
     CU(cudaStreamSynchronize(h->stream));
@@ -463,6 +581,14 @@ extern "C" lqft_status lqft_set_chain(lqft_handle* h, uint32_t chain, double bet
 // ---------------------------------------------------------------------------------------------
 static lqft_status exchange_halo_nccl(lqft_handle* h, int colour, cudaStream_t s) {
     const Geom& g = h->g;
+    if (h->cfg.world_size <= 1) {  // self halo: periodic wrap by copy
+        for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
+            int32_t* f = h->field[colour] + (size_t)c * g.chain_stride;
+            CU(cudaMemcpyAsync(f + (size_t)(g.Tl + 1) * g.plane, f + (size_t)1 * g.plane, sizeof(int32_t) * g.plane, cudaMemcpyDeviceToDevice, s));
+            CU(cudaMemcpyAsync(f, f + (size_t)g.Tl * g.plane, sizeof(int32_t) * g.plane, cudaMemcpyDeviceToDevice, s));
+        }
+        return LQFT_OK;
+    }
     const int ws = (int)h->cfg.world_size, r = (int)h->cfg.rank;
     const int lo = (r + ws - 1) % ws, hi = (r + 1) % ws;
     NC(g_nccl.GroupStart());
@@ -480,9 +606,11 @@ static lqft_status exchange_halo_nccl(lqft_handle* h, int colour, cudaStream_t s
 }
 
 static lqft_status refresh_ghosts(lqft_handle* h) {
-    if (h->cfg.world_size <= 1 || h->ghosts_valid) return LQFT_OK;
+    if (h->g.ghost == 0 || h->ghosts_valid) return LQFT_OK;
+    ST(ghost_op_begin(h));
     ST(exchange_halo_nccl(h, 0, h->stream));
     ST(exchange_halo_nccl(h, 1, h->stream));
+    ST(ghost_op_end(h));
     h->ghosts_valid = true;
     return LQFT_OK;
 }
@@ -508,7 +636,7 @@ static inline uint32_t block_for(uint32_t units) {
 
 // One half-sweep of colour `colour` over local planes tl_first .. tl_first + n_planes - 1.
 static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr,
-                               uint32_t tl_first, uint32_t n_planes, cudaStream_t s) {
+                               uint32_t tl_first, uint32_t n_planes, cudaStream_t s, bool halo_now = false) {
     if (n_planes == 0) return LQFT_OK;
     const Geom& g = h->g;
     int32_t* own = h->field[colour];
@@ -516,7 +644,23 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
     if (h->streamp.enabled || h->tiled.enabled) {
         MarchArgs a{g, colour, sweep, ctr, tl_first, n_planes, h->cfg.n_chains, own, oth, h->chains_d, h->thr_d,
                     h->acc_d, h->max_thr, h->any_wilson, h->count_accepts, s,
-                    !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
+                    !(h->cfg.flags & LQFT_FLAG_NO_PDL), HaloP2P{}};
+        if (halo_now) {
+            // colour-c boundary rows go to the neighbours' colour-c ghost planes: my first owned plane is the
+            // lower neighbour's upper ghost (storage plane Tl+1), my last owned plane the upper neighbour's
+            // lower ghost (storage plane 0)
+            a.halo.lo_ghost = (int32_t*)h->peer_base[0][colour] + (size_t)(g.Tl + 1) * g.plane;
+            a.halo.hi_ghost = (int32_t*)h->peer_base[1][colour];
+            a.halo.lo_sync = (HaloSync*)h->peer_base[0][2];
+            a.halo.hi_sync = (HaloSync*)h->peer_base[1][2];
+            a.halo.mine = h->halo_d;
+            a.halo.wait_for = h->phase;
+            a.halo.phase = ++h->phase;
+            a.halo.enabled = 1;
+            static const int dbg = getenv("LQFT_HALO_DEBUG") ? atoi(getenv("LQFT_HALO_DEBUG")) : 0;  // timing experiments only
+            if (dbg & 1) a.halo.wait_for = 0;
+            if (dbg & 2) a.halo.enabled = 2;  // no push
+        }
         if (h->streamp.enabled) CU(stream_half(h->streamp, a));
         else CU(tiled_half(h->tiled, a));
         h->launches += 1;
@@ -543,12 +687,19 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
 // One full red-black sweep.  `sweep` + (*ctr if ctr) is the RNG sweep counter.
 static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* ctr) {
     const Geom& g = h->g;
-    if (h->cfg.world_size <= 1) {
+    if (g.ghost == 0) {
         ST(launch_half(h, 0, sweep, ctr, 0, g.Tl, h->stream));
         ST(launch_half(h, 1, sweep, ctr, 0, g.Tl, h->stream));
         return LQFT_OK;
     }
-    // slab: boundary planes first, exchange on the comm stream while the interior updates
+    if (halo_fused(h)) {
+        // slab, peer memory: one launch per colour; its boundary rows are pushed into the neighbours' ghost
+        // planes by the kernel itself, flags order the phases (kernels_stream.cuh)
+        ST(launch_half(h, 0, sweep, ctr, 0, g.Tl, h->stream, true));
+        ST(launch_half(h, 1, sweep, ctr, 0, g.Tl, h->stream, true));
+        return LQFT_OK;
+    }
+    // slab, NCCL: boundary planes first, exchange on the comm stream while the interior updates
     for (int colour = 0; colour < 2; ++colour) {
         ST(launch_half(h, colour, sweep, ctr, 0, 1, h->stream));
         ST(launch_half(h, colour, sweep, ctr, g.Tl - 1, 1, h->stream));
@@ -564,11 +715,13 @@ static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* 
 
 static lqft_status launch_observe(lqft_handle* h, bool moments) {
     const Geom& g = h->g;
+    ST(ghost_op_begin(h));
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
     k_observe<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->obs_d, moments ? h->mom_d : nullptr);
     CU(cudaGetLastError());
     h->launches += 1;
+    ST(ghost_op_end(h));
     return LQFT_OK;
 }
 
@@ -576,6 +729,7 @@ static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint
                                     int64_t explicit_site, int32_t only_chain) {
     const Geom& g = h->g;
     const uint32_t nc = h->cfg.n_chains;
+    ST(ghost_op_begin(h));
     k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d, nc,
                                                          counter, ctr, explicit_site, only_chain, h->shift_d);
     CU(cudaGetLastError());
@@ -586,6 +740,7 @@ static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint
     k_shift<<<grid, 256, 0, h->stream>>>(g.chain_stride, h->field[0], h->field[1], h->shift_d);
     CU(cudaGetLastError());
     h->launches += 2;
+    ST(ghost_op_end(h));
     return LQFT_OK;
 }
 
@@ -715,9 +870,11 @@ extern "C" lqft_status lqft_shift_values(lqft_handle* h, uint32_t chain, double 
     const uint64_t n4 = g.chain_stride / 4 + 1;
     const uint32_t blocks = (uint32_t)std::min<uint64_t>((n4 + 255) / 256, (uint64_t)h->sm_count * 8);
     dim3 grid(blocks, 1, h->cfg.n_chains);
+    ST(ghost_op_begin(h));
     k_shift<<<grid, 256, 0, h->stream>>>(g.chain_stride, h->field[0], h->field[1], h->shift_d);
     CU(cudaGetLastError());
     h->launches += 1;
+    ST(ghost_op_end(h));
     return LQFT_OK;
 }
 
@@ -848,11 +1005,13 @@ extern "C" lqft_status lqft_difference_update(lqft_handle* h, uint32_t chain) {
     }
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
+    ST(ghost_op_begin(h));
     k_difference_update<<<grid, bd, 0, h->stream>>>(g, h->field[0] + (size_t)chain * g.chain_stride,
                                                     h->field[1] + (size_t)chain * g.chain_stride,
                                                     h->diff_sum[chain], h->diff_comp[chain]);
     CU(cudaGetLastError());
     h->launches += 1;
+    ST(ghost_op_end(h));
     h->diff_count[chain] += 1;
     return LQFT_OK;
 }
@@ -931,7 +1090,7 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
     const uint64_t cycle = ee / gcd64(ee, ne) * ne;
     // one captured graph = `reps` cycles (about kGraphSteps sweeps); it is replayed while whole periods remain
     constexpr uint64_t kGraphSteps = 32;
-    const bool use_graph = !(h->cfg.flags & LQFT_FLAG_NO_GRAPH) && h->cfg.world_size <= 1 && cycle <= 64 &&
+    const bool use_graph = !(h->cfg.flags & LQFT_FLAG_NO_GRAPH) && h->g.ghost == 0 && cycle <= 64 &&
                            s->n_steps >= 2 * cycle && s->n_steps >= 8;
 
     CU(cudaEventRecord(h->ev_start, h->stream));
@@ -1010,7 +1169,7 @@ extern "C" lqft_status lqft_synchronize(lqft_handle* h) {
     ST(use_device(h));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaStreamSynchronize(h->comm_stream));
-    return LQFT_OK;
+    return check_halo_error(h);
 }
 
 extern "C" lqft_status lqft_last_device_ms(lqft_handle* h, float* ms) {

@@ -96,6 +96,38 @@ def test_wide_row_kernels_bit_exact_vs_oracle(size, beta, wilson):
         assert (got2 == want2).all(), f"{int((got2 != want2).sum())} sites differ (flags={flags})"
 
 
+@pytest.mark.parametrize("size,wilson", [((256, 8, 8), (0, 0)), ((256, 6, 4), (77, 3)), ((512, 4, 6), (0, 0)),
+                                         ((16, 16, 8), (5, 8)), ((10, 6, 4), (0, 0))])
+def test_self_halo_slab_path_on_one_gpu(size, wilson):
+    """LQFT_FLAG_SELF_HALO: ghost planes + the multi-GPU code path (peer-memory pushes and phase flags fused in
+    the streaming kernel for wide rows, boundary-first + exchange otherwise) with this rank as its own
+    neighbour.  Must equal the oracle bit for bit: sweeps, fused schedule, observables, normalize."""
+    X, Y, T = size
+    beta, seed = 0.24, 4321
+    lat = O.Lattice([X, Y, T])
+    wil = O.Wilson(lat, *wilson) if wilson[0] else None
+    v0 = seeded_field(X * Y * T, seed=3 * X + T)
+    want = v0.copy()
+    wacc = sum(O.sweep(lat, want, beta, seed, s, order=1, wilson=wil) for s in range(4))
+    we, _ = O.run(lat, want, beta, seed, 4, 0, 12, 4, 10, order=1, wilson=wil)
+    with Engine(X, Y, T, flags=_lib.FLAG_SELF_HALO) as eng:
+        eng.set_chain(0, beta, seed, *wilson)
+        eng.upload(0, v0)
+        acc = eng.sweep(0, 4, want_accepted=True)[0]
+        e_obs, _, _ = eng.run(12, sweep_base=4, energy_every=4, normalize_every=10)
+        got = eng.download(0)
+        s1, s2 = eng.slice_moments(0)
+        e_int = int(eng.energy()[0][0])
+        s_int = int(eng.action()[0][0])
+        eng.synchronize()
+    assert acc == wacc
+    assert (e_obs[0] == we).all()
+    assert (got == want).all(), f"{int((got != want).sum())} sites differ"
+    f = want.reshape(T, Y * X).astype(np.int64)
+    assert (s1 == f.sum(axis=1)).all() and (s2 == (f * f).sum(axis=1)).all()
+    assert e_int == O.integer_energy(lat, want)[0] and float(s_int) == O.float_action(lat, want)
+
+
 def test_hot_start_matches_oracle():
     with Engine(16, 8, 4) as eng:
         eng.set_chain(0, 0.2, 99)
