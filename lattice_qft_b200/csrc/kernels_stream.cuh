@@ -252,7 +252,7 @@ __device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, int4* __r
 template <int SEGS, bool WILSON, bool COUNT, bool HALO>
 __global__ void __launch_bounds__(kStreamThreads, HALO ? LQFT_STREAM_MINBLOCKS - 1 : LQFT_STREAM_MINBLOCKS)
 k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr,
-               const uint32_t tl_first, const uint32_t n_planes, const uint32_t n_chunks,
+               const uint32_t tl_first, const uint32_t n_planes, const uint32_t n_chunks, const uint32_t n_bchunks,
                int32_t* __restrict__ own_base, const int32_t* __restrict__ oth_base,
                const ChainDev* __restrict__ chains, const uint32_t* __restrict__ thr_all,
                unsigned long long* __restrict__ acc, const HaloP2P halo) {
@@ -273,13 +273,31 @@ k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* _
     if (ctr) sweep += *ctr;
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.x / SEGS, seg = blockIdx.x % SEGS;
-    const uint32_t pl = blockIdx.y * kStreamWarps + warp;
+    const uint32_t seg = blockIdx.x % SEGS;
+    uint32_t chunk = blockIdx.x / SEGS, group = blockIdx.y, chunks_here = n_chunks;
+    bool boundary_block = false;
+    if (HALO) {
+        // peer-memory halo launch, grid.y == 1: the first n_bchunks blocks take plane group 0 — rotated so
+        // that it holds the slab's two boundary planes {Tl-2, Tl-1, 0, 1} — in short chunks: they are
+        // scheduled first and finish early, so pushes and flag are out long before the phase ends.
+        if (chunk < n_bchunks) {
+            group = 0;
+            chunks_here = n_bchunks;
+            boundary_block = true;
+        } else {
+            chunk -= n_bchunks;
+            group = 1u + chunk / n_chunks;
+            chunk %= n_chunks;
+        }
+    }
+    uint32_t pl = group * kStreamWarps + warp;
+    const bool plane_ok = pl < n_planes;
+    if (HALO) pl = (pl + n_planes - (uint32_t)(kStreamWarps / 2) % n_planes) % n_planes;
     const uint32_t half = g.Y >> 1;
-    const uint32_t y_begin = 2u * (uint32_t)(((uint64_t)chunk * half) / n_chunks);
-    const uint32_t y_end = 2u * (uint32_t)(((uint64_t)(chunk + 1u) * half) / n_chunks);
+    const uint32_t y_begin = 2u * (uint32_t)(((uint64_t)chunk * half) / chunks_here);
+    const uint32_t y_end = 2u * (uint32_t)(((uint64_t)(chunk + 1u) * half) / chunks_here);
     int accepted = 0;
-    if (pl < n_planes && y_begin < y_end) {  // warp uniform
+    if (plane_ok && y_begin < y_end) {  // warp uniform
         const uint32_t tl = tl_first + pl;
         const uint32_t tg = g.t0 + tl;
         const size_t cbase = (size_t)chain * g.chain_stride;
@@ -323,7 +341,6 @@ k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* _
     if (HALO && halo.enabled) {
         // the last boundary block to finish publishes this launch's phase to both neighbours
         __syncthreads();
-        const bool boundary_block = blockIdx.y == 0u || blockIdx.y + 1u == gridDim.y;
         if (boundary_block && threadIdx.x == 0) {
             // release chain instead of sequentially-consistent fences (a MEMBAR.SC.SYS here costs ~10 us):
             // the block's stores happen-before the bar.sync above, thread 0 releases them with the ticket
@@ -387,20 +404,21 @@ inline cudaError_t stream_prepare(StreamPlan& p, const Geom& g, int sm_count, ui
     return cudaSuccess;
 }
 
-// Number of y chunks per plane group: the grid should fill whole waves of resident blocks.
+// Number of y chunks per plane group.  Blocks are resident for their whole chunk, so a launch lasts about
+// ceil(waves) * (rows per chunk + a per-chunk prologue worth ~3 rows): pick the count that minimises it.
 inline uint32_t stream_chunks(const StreamPlan& p, const Geom& g, uint32_t n_planes, uint32_t n_chains) {
     const uint64_t slots = (uint64_t)p.sm_count * p.blocks_per_sm;
     const uint64_t base = (uint64_t)p.segs * ((n_planes + kStreamWarps - 1) / kStreamWarps) * n_chains;
     const uint32_t max_chunks = g.Y / 4 ? g.Y / 4 : 1;  // at least 4 rows per chunk
     uint32_t best = 1;
-    double best_eff = -1.0;
+    double best_cost = 1e300;
     for (uint32_t nc = 1; nc <= max_chunks; ++nc) {
-        const double blocks = (double)(base * nc);
-        const double waves = blocks / (double)slots;
-        const double eff = waves / (double)(uint64_t)(waves + 0.999999);
-        // prefer the fewest chunks among (nearly) equally efficient choices: fewer prologues
-        if (eff > best_eff + 0.05) {
-            best_eff = eff;
+        const uint64_t blocks = base * nc;
+        const uint64_t waves = (blocks + slots - 1) / slots;
+        const double rows = (double)((g.Y / 2 + nc - 1) / nc) * 2.0;  // longest chunk
+        const double cost = (double)waves * (rows + 3.0);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
             best = nc;
         }
     }
@@ -410,10 +428,18 @@ inline uint32_t stream_chunks(const StreamPlan& p, const Geom& g, uint32_t n_pla
 template <int SEGS>
 inline cudaError_t stream_launch(const StreamPlan& p, const MarchArgs& a) {
     const uint32_t n_chunks = stream_chunks(p, a.g, a.n_planes, a.n_chains);
-    dim3 grid(n_chunks * SEGS, (a.n_planes + kStreamWarps - 1) / kStreamWarps, a.n_chains);
+    const uint32_t n_groups = (a.n_planes + kStreamWarps - 1) / kStreamWarps;
+    dim3 grid(n_chunks * SEGS, n_groups, a.n_chains);
     const size_t smem = stream_smem_bytes(SEGS, a.max_thr);
     HaloP2P halo = a.halo;
-    halo.n_boundary_blocks = grid.x * grid.z * (grid.y == 1 ? 1u : 2u);
+    uint32_t n_bchunks = 0;
+    if (halo.enabled) {
+        // boundary plane group in chunks half as long as the interior ones (at least 4 rows each)
+        const uint32_t max_chunks = a.g.Y / 4 ? a.g.Y / 4 : 1;
+        n_bchunks = 2 * n_chunks < max_chunks ? 2 * n_chunks : max_chunks;
+        grid = dim3(SEGS * (n_bchunks + (n_groups - 1) * n_chunks), 1, a.n_chains);
+        halo.n_boundary_blocks = SEGS * n_bchunks * a.n_chains;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kStreamThreads);
@@ -426,7 +452,7 @@ inline cudaError_t stream_launch(const StreamPlan& p, const MarchArgs& a) {
     cfg.numAttrs = a.pdl ? 1 : 0;
 #define LQFT_GO(W, C, H)                                                                                                 \
     return cudaLaunchKernelEx(&cfg, k_sweep_stream<SEGS, W, C, H>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_planes, \
-                              n_chunks, a.own, a.oth, a.chains, a.thr, a.acc, halo)
+                              n_chunks, n_bchunks, a.own, a.oth, a.chains, a.thr, a.acc, halo)
     if (halo.enabled) {
         if (a.wilson) {
             if (a.count) LQFT_GO(true, true, true); else LQFT_GO(true, false, true);
