@@ -33,6 +33,8 @@ BETA = 0.25
 SEED = 0xC0FFEE
 THERMALISE = 200
 SWEEPS_PER_STEP = 1000
+CPU_SAMPLE_T = 32        # the CPU legs sweep a 256 x 256 x 32 slice per core (same row / plane strides as 256^3)
+CPU_SAMPLE_SWEEPS = 8    # ~1.2 s per core per sweep of that slice: about 10-20 s of CPU work in total
 BYTES_PER_UPDATE = 8  # one i32 read + one i32 write per site update
 METRIC = "site updates/sec"
 UNIT = "site-updates/s"
@@ -48,52 +50,49 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled (NVML, every 10 ms) while the timed region runs."""
 
     def __init__(self, index: int):
         self.index = index
-        self.lines = []
-        self.proc = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[0].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.01)
+        except Exception as exc:  # NVML missing: report it, never fake a clock
+            self.reasons.add(f"nvml unavailable: {exc}")
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [c.strip() for c in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def cpu_baseline_sample(threads: int, sweeps: int, x: int, y: int, t: int):
@@ -110,10 +109,10 @@ def run_reference(args, rank: int, world: int):
         return
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    # bounded sample of the 256^3 workload: each step = one lexicographic sweep of a 256 x 256 x 16
+    # bounded sample of the 256^3 workload: each step = one lexicographic sweep of a 256 x 256 x 32
     # slab-sized lattice per core (same row/plane strides as 256^3; the full 805 MB neighbour table of
     # 256^3 would only add build time), all cores busy, like sim.rs's rayon pool.
-    t_sample = 16
+    t_sample = CPU_SAMPLE_T
     lat = O.Lattice([X, Y, t_sample])
     for _ in range(args.warmup):
         O.bench_chains(lat, BETA, SEED, 1, 10, cores)
@@ -294,11 +293,12 @@ def main():
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, secs = cpu_baseline_sample(cores, 2, X, Y, 16)
+            v, secs = cpu_baseline_sample(cores, CPU_SAMPLE_SWEEPS, X, Y, CPU_SAMPLE_T)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{cores} independent chains x 2 lexicographic sweeps of {X}x{Y}x16 ({secs:.1f}s); "
-                          "C restatement of the reference's neighbour-table i32 path (oracle/lqft_oracle.c)"}
+                "sample": f"{cores} independent chains x {CPU_SAMPLE_SWEEPS} lexicographic sweeps of {X}x{Y}x{CPU_SAMPLE_T} "
+                          f"({secs:.1f}s wall, {cores * secs:.0f} core-seconds); C restatement of the reference's "
+                          "neighbour-table i32 path (oracle/lqft_oracle.c), hot start, energy every 10th sweep"}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
