@@ -156,11 +156,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="LQFT_FLAG_* for experiments")
+    ap.add_argument("--sweeps", type=int, default=None, help="sweeps per step override (experiments)")
     ap.add_argument("--lattice", default=None, help="X,Y,Tpergpu override for experiments (not the headline config)")
     args = ap.parse_args()
+    global X, Y, T_PER_GPU, SWEEPS_PER_STEP
     if args.lattice:
-        global X, Y, T_PER_GPU
         X, Y, T_PER_GPU = (int(v) for v in args.lattice.split(","))
+    if args.sweeps:
+        SWEEPS_PER_STEP = args.sweeps
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

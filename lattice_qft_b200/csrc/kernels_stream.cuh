@@ -31,6 +31,9 @@ namespace lqft {
 #ifndef LQFT_STREAM_MINBLOCKS
 #define LQFT_STREAM_MINBLOCKS 7
 #endif
+#ifndef LQFT_STREAM_HALO_MINBLOCKS
+#define LQFT_STREAM_HALO_MINBLOCKS 6
+#endif
 constexpr int kStreamWarps = LQFT_STREAM_WARPS;
 constexpr int kStreamDepth = LQFT_STREAM_DEPTH;   // prefetch distance in rows (even)
 constexpr int kStreamThreads = kStreamWarps * 32;
@@ -138,7 +141,7 @@ __device__ __forceinline__ void stream_issue(const StreamPtrs& q, uint32_t y, ui
 }
 
 template <int SEGS, bool WILSON, bool COUNT, bool HALO, bool P>
-__device__ __forceinline__ void stream_step(int4* __restrict__ own_row, int4* __restrict__ peer_row, uint32_t ring, uint32_t edge_ring, uint32_t stage,
+__device__ __forceinline__ void stream_step(int4* __restrict__ own_row, const bool push, const long long* s_delta, uint32_t ring, uint32_t edge_ring, uint32_t stage,
                                             int4& om, int4& oc, const uint32_t src_lane, const bool edge_lane,
                                             const uint32_t grp, const uint32_t colour, const uint64_t sweep,
                                             const RoundKeys& rk, const uint2* __restrict__ s_dn,
@@ -182,7 +185,9 @@ __device__ __forceinline__ void stream_step(int4* __restrict__ own_row, int4* __
     w.w = metropolis_update2<COUNT>(v.w, ns.w, off.w, r.w, s_dn, s_up, kc, accepted);
     *own_row = w;
     if (HALO) {
-        if (peer_row) *peer_row = w;  // boundary plane: the neighbour's ghost copy, over NVLink
+        // boundary plane: the same row goes to the neighbour's ghost plane over NVLink.  The byte offset from
+        // the own row to the peer row sits in shared memory so that it costs no register in the hot loop.
+        if (push) *reinterpret_cast<int4*>(reinterpret_cast<char*>(own_row) + *s_delta) = w;
     }
     om = oc;
     oc = on;
@@ -190,7 +195,7 @@ __device__ __forceinline__ void stream_step(int4* __restrict__ own_row, int4* __
 
 // The chunk [y_begin, y_end) of one plane, parity P0 at y_begin.
 template <int SEGS, bool WILSON, bool COUNT, bool HALO, bool P0>
-__device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, int4* __restrict__ peer_w, const StreamPtrs& q,
+__device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, const bool push, const long long* s_delta, const StreamPtrs& q,
                                              const uint32_t y_begin,
                                              const uint32_t y_end, const uint32_t Y, const uint32_t ring,
                                              const uint32_t edge_ring, const uint32_t lane, const uint32_t kq,
@@ -226,7 +231,7 @@ __device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, int4* __r
         const uint32_t y = y_begin + s;
         const uint32_t st0 = s & (uint32_t)(D - 1), st1 = (s + 1u) & (uint32_t)(D - 1);
         cp_async_wait<D - 1>();
-        stream_step<SEGS, WILSON, COUNT, HALO, P0>(own_w + y * G, (HALO && peer_w) ? peer_w + y * G : nullptr, ring, edge_ring, st0, om, oc, P0 ? src_up : src_dn,
+        stream_step<SEGS, WILSON, COUNT, HALO, P0>(own_w + y * G, push, s_delta, ring, edge_ring, st0, om, oc, P0 ? src_up : src_dn,
                                              P0 ? edge_p : edge_n, grp_row0 + y * G, colour, sweep, rk, s_dn, s_up, kc,
                                              y, Y, kq, wil_plane, wil_w, accepted);
         if (s + D < n_steps) {
@@ -235,8 +240,7 @@ __device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, int4* __r
         }
         cp_async_commit();
         cp_async_wait<D - 1>();
-        stream_step<SEGS, WILSON, COUNT, HALO, !P0>(own_w + (y + 1u) * G, (HALO && peer_w) ? peer_w + (y + 1u) * G : nullptr, ring, edge_ring,
-                                              st1, om, oc, P0 ? src_dn : src_up,
+        stream_step<SEGS, WILSON, COUNT, HALO, !P0>(own_w + (y + 1u) * G, push, s_delta, ring, edge_ring, st1, om, oc, P0 ? src_dn : src_up,
                                               P0 ? edge_n : edge_p, grp_row0 + (y + 1u) * G, colour, sweep, rk, s_dn,
                                               s_up, kc, y + 1u, Y, kq, wil_plane, wil_w, accepted);
         if (s + 1u + D < n_steps) {
@@ -250,7 +254,7 @@ __device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, int4* __r
 
 // grid = (n_chunks * SEGS, ceil(n_planes / kStreamWarps), n_chains), block = kStreamThreads.
 template <int SEGS, bool WILSON, bool COUNT, bool HALO>
-__global__ void __launch_bounds__(kStreamThreads, HALO ? LQFT_STREAM_MINBLOCKS - 1 : LQFT_STREAM_MINBLOCKS)
+__global__ void __launch_bounds__(kStreamThreads, HALO ? LQFT_STREAM_HALO_MINBLOCKS : LQFT_STREAM_MINBLOCKS)
 k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr,
                const uint32_t tl_first, const uint32_t n_planes, const uint32_t n_chunks, const uint32_t n_bchunks,
                int32_t* __restrict__ own_base, const int32_t* __restrict__ oth_base,
@@ -261,6 +265,7 @@ k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* _
     constexpr uint32_t EDGE_BYTES = SEGS > 1 ? (uint32_t)kStreamDepth * kStreamThreads * 4u : 0u;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ unsigned int s_cnt;
+    __shared__ long long s_delta[kStreamWarps];
     pdl_launch_dependents();
     const uint32_t chain = blockIdx.z;
     const ChainDev cd = chains[chain];
@@ -316,23 +321,28 @@ k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* _
         const bool wil_plane = WILSON && tg < cd.wil_h;
         const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
         const uint32_t grp_row0 = tg * g.Y * G + kq;  // Philox counter word 0 of this quad column at y = 0
-        int4* peer_w = nullptr;
+        bool push = false;
         if (HALO && halo.enabled) {  // warp uniform
+            const int4* peer_w = nullptr;
             if (tl == 0u) {
                 if (lane == 0u) halo_wait(&halo.mine->from_lo, halo.wait_for, &halo.mine->error);
-                if (halo.enabled == 1u) peer_w = reinterpret_cast<int4*>(halo.lo_ghost + cbase) + kq;
+                peer_w = reinterpret_cast<const int4*>(halo.lo_ghost + cbase) + kq;
             } else if (tl + 1u == g.Tl) {
                 if (lane == 0u) halo_wait(&halo.mine->from_hi, halo.wait_for, &halo.mine->error);
-                if (halo.enabled == 1u) peer_w = reinterpret_cast<int4*>(halo.hi_ghost + cbase) + kq;
+                peer_w = reinterpret_cast<const int4*>(halo.hi_ghost + cbase) + kq;
             }
+            push = peer_w != nullptr && halo.enabled == 1u;
+            // lanes differ only by kq on both sides, so one offset per warp serves all of them
+            if (push && lane == 0u)
+                s_delta[warp] = reinterpret_cast<const char*>(peer_w) - reinterpret_cast<const char*>(own_w);
             __syncwarp();
         }
         if ((y_begin + tg + (uint32_t)colour) & 1u)
-            stream_chunk<SEGS, WILSON, COUNT, HALO, true>(own_w, peer_w, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
+            stream_chunk<SEGS, WILSON, COUNT, HALO, true>(own_w, push, s_delta + warp, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
                                                     (uint32_t)colour, sweep, rk, s_dn, s_up, kc, wil_plane, cd.wil_w,
                                                     accepted);
         else
-            stream_chunk<SEGS, WILSON, COUNT, HALO, false>(own_w, peer_w, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
+            stream_chunk<SEGS, WILSON, COUNT, HALO, false>(own_w, push, s_delta + warp, q, y_begin, y_end, g.Y, ring, edge_ring, lane, kq, grp_row0,
                                                      (uint32_t)colour, sweep, rk, s_dn, s_up, kc, wil_plane, cd.wil_w,
                                                      accepted);
     }
