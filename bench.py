@@ -34,10 +34,20 @@ SEED = 0xC0FFEE
 THERMALISE = 200
 SWEEPS_PER_STEP = 1000
 CPU_SAMPLE_T = 32        # the CPU legs sweep a 256 x 256 x 32 slice per core (same row / plane strides as 256^3)
-CPU_SAMPLE_SWEEPS = 8    # ~1.2 s per core per sweep of that slice: about 10-20 s of CPU work in total
+CPU_SAMPLE_SWEEPS = 24   # ~2 s wall on 16 cores: 20-40 core-seconds of CPU work
 BYTES_PER_UPDATE = 8  # one i32 read + one i32 write per site update
 METRIC = "site updates/sec"
 UNIT = "site-updates/s"
+
+
+def measured_traffic(lattice):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh).get("x".join(str(v) for v in lattice))
+        return (t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]) if t else (None, None)
+    except Exception:
+        return None, None
 
 
 def measured_peak_gbs():
@@ -114,16 +124,17 @@ def run_reference(args, rank: int, world: int):
     # 256^3 would only add build time), all cores busy, like sim.rs's rayon pool.
     t_sample = CPU_SAMPLE_T
     lat = O.Lattice([X, Y, t_sample])
+    per_step = 4  # sweeps per step and core: amortises thread start-up and the hot start of each call
     for _ in range(args.warmup):
-        O.bench_chains(lat, BETA, SEED, 1, 10, cores)
+        O.bench_chains(lat, BETA, SEED, per_step, 10, cores)
     t0 = time.time()
     secs = 0.0
     for _ in range(args.steps):
-        s, _ = O.bench_chains(lat, BETA, SEED, 1, 10, cores)
+        s, _ = O.bench_chains(lat, BETA, SEED, per_step, 10, cores)
         secs += s
-    updates = float(cores) * args.steps * lat.n_sites
+    updates = float(cores) * args.steps * per_step * lat.n_sites
     value = updates / secs
-    sample = (f"{cores} independent chains x {args.steps} lexicographic sweeps of {X}x{Y}x{t_sample} "
+    sample = (f"{cores} independent chains x {args.steps} steps of {per_step} lexicographic sweeps of {X}x{Y}x{t_sample} "
               f"(neighbour-table i32 path of algorithm.rs:117-157), wall {time.time() - t0:.1f}s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -278,6 +289,7 @@ def main():
         per_launch_s = (ms * 1e-3) / n_sweep_launches
         alg_bytes_per_launch = BYTES_PER_UPDATE * (n_local / 2)
         achieved = alg_bytes_per_launch / per_launch_s / 1e9
+        traffic, traffic_src = measured_traffic([X, Y, T_PER_GPU]) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -289,7 +301,7 @@ def main():
                             "normalize every 10th) + lqft_download(field) per step, wall clock"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "half-sweep (one colour) of the red-black Metropolis sweep",
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                          "avg_launch_us": per_launch_s * 1e6},
