@@ -148,6 +148,75 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(device: int):
+    """The other BASELINE.json configs on one GPU, each timed briefly with CUDA events through the C ABI
+    (device-resident, synthetic hot starts): updates/s and measurements/s.  Parity for these shapes is in
+    tests/; these are throughput notes beside the headline line, not the headline."""
+    import torch
+    from lattice_qft_b200 import Engine
+
+    def timed(eng, fn, reps):
+        stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", device))
+        fn()
+        eng.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        eng.synchronize()
+        return a.elapsed_time(b) * 1e-3 / reps
+
+    out = {}
+    # config 2: 64^3 coupling scan, 64 independent chains batched in one handle, energy every 10th sweep
+    eng = Engine(64, 64, 64, n_chains=64, device=device)
+    for c in range(64):
+        eng.set_chain(c, 0.20 + 0.005 * c, 0xC0FFEE + c)
+    eng.init_hot()
+    eng.run(200, energy_every=0)
+    sec = timed(eng, lambda: eng.run(200, sweep_base=200, energy_every=10), 3)
+    out["coupling_scan_64x64^3"] = {"site_updates_per_s": 64 * 64**3 * 200 / sec,
+                                    "energy_measurements_per_s": 64 * 20 / sec, "sweeps_per_call": 200}
+    eng.close()
+    # config 4: 64^3 Wilson sweep, widths {10,21,32,42,53} x heights {16,32,64} + one free chain, energy every sweep
+    shapes = [(w, h) for h in (16, 32, 64) for w in (10, 21, 32, 42, 53)] + [(0, 0)]
+    eng = Engine(64, 64, 64, n_chains=len(shapes), device=device)
+    for c, (w, h) in enumerate(shapes):
+        eng.set_chain(c, 0.26, 0xBEEF + c, w, h)
+    eng.init_hot()
+    eng.run(100, energy_every=0)
+    sec = timed(eng, lambda: eng.run(100, sweep_base=100, energy_every=1), 3)
+    out["wilson_scan_16x64^3"] = {"site_updates_per_s": len(shapes) * 64**3 * 100 / sec,
+                                  "energy_measurements_per_s": len(shapes) * 100 / sec}
+    eng.close()
+    # config 3: 128^3 correlator, 100 reference sites per measurement (reference work: 100 * N site visits each)
+    eng = Engine(128, 128, 128, device=device)
+    eng.set_chain(0, 0.25, 0xABCD)
+    eng.init_hot()
+    eng.run(100, energy_every=0)
+    sec = timed(eng, lambda: eng.correlator(0, reps=100, sweep_index=7), 20)
+    out["correlator_128^3_100_sites"] = {"measurements_per_s": 1.0 / sec,
+                                         "reference_equivalent_site_visits_per_s": 100 * 128**3 / sec}
+    sec = timed(eng, lambda: eng.run(100, sweep_base=100, energy_every=0), 3)
+    out["correlator_128^3_100_sites"]["site_updates_per_s"] = 128**3 * 100 / sec
+    eng.close()
+    # config 1: the reference's own 16^3 case (one chain: launch-latency bound on a GPU)
+    eng = Engine(16, 16, 16, device=device)
+    eng.set_chain(0, 0.2, 1)
+    eng.init_hot()
+    sec = timed(eng, lambda: eng.run(2000, energy_every=10), 2)
+    out["reference_case_16^3_1_chain"] = {"site_updates_per_s": 4096 * 2000 / sec, "energy_measurements_per_s": 200 / sec}
+    eng.close()
+    # energy / action measurement at the headline size
+    eng = Engine(256, 256, 256, device=device)
+    eng.set_chain(0, BETA, SEED)
+    eng.init_hot()
+    sec = timed(eng, lambda: eng.energy(), 20)
+    out["energy_256^3"] = {"measurements_per_s": 1.0 / sec, "GB_per_s_of_4B_per_site": 4 * 256**3 / sec / 1e9}
+    eng.close()
+    return out
+
+
 def workload_config(n_gpus: int):
     t = T_PER_GPU * n_gpus
     return {
@@ -166,6 +235,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE.json configs")
     ap.add_argument("--flags", type=int, default=0, help="LQFT_FLAG_* for experiments")
     ap.add_argument("--sweeps", type=int, default=None, help="sweeps per step override (experiments)")
     ap.add_argument("--lattice", default=None, help="X,Y,Tpergpu override for experiments (not the headline config)")
@@ -283,6 +353,9 @@ def main():
     h2d = n_local * 4
     d2h = n_local * 4 + int(e_obs.size) * 8
 
+    other = None
+    if world == 1 and not args.lattice and not args.no_configs:
+        other = other_configs(local_rank)
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         n_sweep_launches = 2 * SWEEPS_PER_STEP * args.steps  # per rank, dominant kernel: half-sweep
@@ -306,6 +379,8 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                          "avg_launch_us": per_launch_s * 1e6},
         }
+        if other:
+            line["configs"] = other
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, secs = cpu_baseline_sample(cores, CPU_SAMPLE_SWEEPS, X, Y, CPU_SAMPLE_T)
