@@ -211,16 +211,17 @@ __global__ void k_split(Geom g, const int32_t* __restrict__ lex, int32_t* __rest
 }
 
 __global__ void k_merge(Geom g, int32_t* __restrict__ lex, const int32_t* __restrict__ c0,
-                        const int32_t* __restrict__ c1) {
+                        const int32_t* __restrict__ c1, const int32_t* __restrict__ offset) {
     const uint32_t tl = blockIdx.y;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.plane) return;
     const uint32_t y = i / g.Xh;
     const uint32_t q = (y + g.t0 + tl) & 1u;
     const size_t src = (size_t)plane_self(g, tl) * g.plane + i;
+    const int32_t off = *offset;  // pending normalisation shift of this chain (see k_pick_shift)
     int2 v;
-    v.x = (q ? c1 : c0)[src];
-    v.y = (q ? c0 : c1)[src];
+    v.x = (q ? c1 : c0)[src] - off;
+    v.y = (q ? c0 : c1)[src] - off;
     reinterpret_cast<int2*>(lex)[(size_t)tl * g.plane + i] = v;
 }
 
@@ -245,7 +246,11 @@ __global__ void k_init_hot(Geom g, int32_t* __restrict__ c0_base, int32_t* __res
 }
 
 // ---- normalize (fields.rs:616-633) ----------------------------------------------------------
-// Step 1: one thread per chain reads the height of the picked site (0 if another rank owns it).
+// The action, every observable and every Metropolis decision depend on height differences only, so
+// shift_values never has to touch the field: each chain carries an offset, true height = stored - offset,
+// and normalize_random (subtract the TRUE height of the picked site) simply sets offset := stored[site].
+// The offset is applied where absolute heights leave the device (k_merge, lqft_slice_moments).
+// Step 1: one thread per chain reads the stored height of the picked site (0 if another rank owns it).
 __global__ void k_pick_shift(Geom g, const int32_t* __restrict__ c0_base,
                              const int32_t* __restrict__ c1_base,
                              const ChainDev* __restrict__ chains, uint32_t n_chains,
@@ -277,7 +282,19 @@ __global__ void k_pick_shift(Geom g, const int32_t* __restrict__ c0_base,
     shift[chain] = s;
 }
 
-// Step 2: subtract shift[chain] everywhere (ghost planes included).  grid = (blocks, 1, n_chains)
+// Step 2: offset[chain] := picked[chain] for the chains being normalised (after the all-reduce that hands the
+// owner's value to every rank).
+__global__ void k_set_offset(const int32_t* __restrict__ picked, int32_t* __restrict__ offset, uint32_t n_chains,
+                             int32_t only_chain) {
+    const uint32_t chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= n_chains) return;
+    if (only_chain >= 0 && (int32_t)chain != only_chain) return;
+    offset[chain] = picked[chain];
+}
+__global__ void k_add_offset(int32_t* __restrict__ offset, uint32_t chain, int32_t shift) { offset[chain] += shift; }
+
+// Explicit re-centring (not on the hot path): subtract shift[chain] everywhere (ghost planes included).
+// grid = (blocks, 1, n_chains)
 __global__ void k_shift(uint64_t n_per_chain, int32_t* __restrict__ c0_base,
                         int32_t* __restrict__ c1_base, const int32_t* __restrict__ shift) {
     const uint32_t chain = blockIdx.z;
@@ -362,6 +379,57 @@ k_observe(Geom g, const int32_t* __restrict__ c0_base, const int32_t* __restrict
         q[1] = dx + dy + dt;
         q[2] = a + b;
         q[3] = a * a + b * b;
+    }
+    unsigned long long* const dst[4] = {
+        obs + (size_t)chain * 2, obs + (size_t)chain * 2 + 1,
+        mom ? mom + ((size_t)chain * g.T + tg) * 2 : nullptr,
+        mom ? mom + ((size_t)chain * g.T + tg) * 2 + 1 : nullptr};
+    block_sum_flush<4>(q, dst);
+}
+
+// Vectorised form of k_observe for X % 8 == 0: one thread per quad position owns four colour-0 and four
+// colour-1 sites (6 LDG.128 + 1 LDG for 8 sites).  Same exact int64 sums.
+// grid = (ceil(plane/4/bd), Tl, n_chains)
+__global__ void __launch_bounds__(256)
+k_observe_vec4(Geom g, const int32_t* __restrict__ c0_base, const int32_t* __restrict__ c1_base,
+               unsigned long long* __restrict__ obs, unsigned long long* __restrict__ mom) {
+    const uint32_t chain = blockIdx.z, tl = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    long long q[4] = {0, 0, 0, 0};
+    const uint32_t tg = g.t0 + tl;
+    const uint32_t Qx = g.Xh >> 2;
+    if (i < (g.plane >> 2)) {
+        const int32_t* c0 = c0_base + (size_t)chain * g.chain_stride;
+        const int32_t* c1 = c1_base + (size_t)chain * g.chain_stride;
+        const uint32_t y = i / Qx, k0 = (i - y * Qx) << 2;
+        const uint32_t p0 = (y + tg) & 1u;  // x parity of the colour-0 sites of this row
+        const size_t ps = (size_t)plane_self(g, tl) * g.plane;
+        const size_t row = ps + (size_t)y * g.Xh;
+        const uint32_t yp = (y + 1 == g.Y) ? 0 : y + 1;
+        const uint32_t kn = (k0 + 4 == g.Xh) ? 0 : k0 + 4;
+        const size_t up = (size_t)plane_above(g, tl) * g.plane + (size_t)y * g.Xh + k0;
+        const size_t yr = ps + (size_t)yp * g.Xh + k0;
+        const int4 a = *reinterpret_cast<const int4*>(c0 + row + k0);
+        const int4 b = *reinterpret_cast<const int4*>(c1 + row + k0);
+        const int4 ay = *reinterpret_cast<const int4*>(c1 + yr), by = *reinterpret_cast<const int4*>(c0 + yr);
+        const int4 at = *reinterpret_cast<const int4*>(c1 + up), bt = *reinterpret_cast<const int4*>(c0 + up);
+        // +x neighbour: the odd-x colour looks one position to the right in the other colour's row
+        const int e = (p0 ? c1 : c0)[row + kn];
+        const int4 ax = p0 ? make_int4(b.y, b.z, b.w, e) : b;
+        const int4 bx = p0 ? a : make_int4(a.y, a.z, a.w, e);
+        auto sq = [](int u, int v) { const long long d = (long long)u - (long long)v; return d * d; };
+        const long long dx = sq(a.x, ax.x) + sq(a.y, ax.y) + sq(a.z, ax.z) + sq(a.w, ax.w) +
+                             sq(b.x, bx.x) + sq(b.y, bx.y) + sq(b.z, bx.z) + sq(b.w, bx.w);
+        const long long dy = sq(a.x, ay.x) + sq(a.y, ay.y) + sq(a.z, ay.z) + sq(a.w, ay.w) +
+                             sq(b.x, by.x) + sq(b.y, by.y) + sq(b.z, by.z) + sq(b.w, by.w);
+        const long long dt = sq(a.x, at.x) + sq(a.y, at.y) + sq(a.z, at.z) + sq(a.w, at.w) +
+                             sq(b.x, bt.x) + sq(b.y, bt.y) + sq(b.z, bt.z) + sq(b.w, bt.w);
+        q[0] = dx + dy - dt;
+        q[1] = dx + dy + dt;
+        if (mom) {
+            q[2] = (long long)a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+            q[3] = sq(a.x, 0) + sq(a.y, 0) + sq(a.z, 0) + sq(a.w, 0) + sq(b.x, 0) + sq(b.y, 0) + sq(b.z, 0) + sq(b.w, 0);
+        }
     }
     unsigned long long* const dst[4] = {
         obs + (size_t)chain * 2, obs + (size_t)chain * 2 + 1,

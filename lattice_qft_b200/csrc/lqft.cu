@@ -142,7 +142,8 @@ struct lqft_handle {
     unsigned long long* acc_d = nullptr;   // [n_chains][kAccSlots]
     unsigned long long* obs_d = nullptr;   // [n_chains][2]
     unsigned long long* mom_d = nullptr;   // [n_chains][T][2]
-    int32_t* shift_d = nullptr;            // [n_chains]
+    int32_t* shift_d = nullptr;            // [n_chains] scratch: picked heights
+    int32_t* offset_d = nullptr;           // [n_chains] true height = stored - offset (lazy normalisation)
     int32_t* staging_d = nullptr;          // [n_slab] lexicographic
     uint64_t* sweep_ctr_d = nullptr;       // device sweep counter for graph replays
     uint32_t* n_meas_d = nullptr;
@@ -417,7 +418,7 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
     tiled_release(h->tiled);
     cudaFree(h->field[0]); cudaFree(h->field[1]);
     cudaFree(h->chains_d); cudaFree(h->thr_d); cudaFree(h->acc_d); cudaFree(h->obs_d);
-    cudaFree(h->mom_d); cudaFree(h->shift_d); cudaFree(h->staging_d); cudaFree(h->sweep_ctr_d);
+    cudaFree(h->mom_d); cudaFree(h->shift_d); cudaFree(h->offset_d); cudaFree(h->staging_d); cudaFree(h->sweep_ctr_d);
     cudaFree(h->n_meas_d); cudaFree(h->elog_d); cudaFree(h->sites_d); cudaFree(h->gathered_d);
     for (auto p : h->diff_sum) cudaFree(p);
     for (auto p : h->diff_comp) cudaFree(p);
@@ -495,6 +496,8 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     CU(cudaMalloc(&h->obs_d, sizeof(unsigned long long) * (size_t)nc * 2));
     CU(cudaMalloc(&h->mom_d, sizeof(unsigned long long) * (size_t)nc * T * 2));
     CU(cudaMalloc(&h->shift_d, sizeof(int32_t) * nc));
+    CU(cudaMalloc(&h->offset_d, sizeof(int32_t) * nc));
+    CU(cudaMemsetAsync(h->offset_d, 0, sizeof(int32_t) * nc, h->stream));
     CU(cudaMalloc(&h->sweep_ctr_d, sizeof(uint64_t)));
     CU(cudaMalloc(&h->n_meas_d, sizeof(uint32_t)));
     CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * (size_t)nc * kAccSlots, h->stream));
@@ -716,9 +719,16 @@ static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* 
 static lqft_status launch_observe(lqft_handle* h, bool moments) {
     const Geom& g = h->g;
     ST(ghost_op_begin(h));
-    const uint32_t bd = block_for(g.plane);
-    dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
-    k_observe<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->obs_d, moments ? h->mom_d : nullptr);
+    if (g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) {
+        const uint32_t units = g.plane / 4;
+        const uint32_t bd = block_for(units);
+        dim3 grid((units + bd - 1) / bd, g.Tl, h->cfg.n_chains);
+        k_observe_vec4<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->obs_d, moments ? h->mom_d : nullptr);
+    } else {
+        const uint32_t bd = block_for(g.plane);
+        dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
+        k_observe<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->obs_d, moments ? h->mom_d : nullptr);
+    }
     CU(cudaGetLastError());
     h->launches += 1;
     ST(ghost_op_end(h));
@@ -727,20 +737,17 @@ static lqft_status launch_observe(lqft_handle* h, bool moments) {
 
 static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint64_t* ctr,
                                     int64_t explicit_site, int32_t only_chain) {
+    // normalize_random without a pass over the field: offset[chain] := stored height of the picked site
+    // (kernels_v1.cuh, k_pick_shift).  Reads owned planes only, so it is not a ghost operation.
     const Geom& g = h->g;
     const uint32_t nc = h->cfg.n_chains;
-    ST(ghost_op_begin(h));
     k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d, nc,
                                                          counter, ctr, explicit_site, only_chain, h->shift_d);
     CU(cudaGetLastError());
     ST(allreduce_i32(h, h->shift_d, nc));
-    const uint64_t n4 = g.chain_stride / 4 + 1;
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n4 + 255) / 256, (uint64_t)h->sm_count * 8);
-    dim3 grid(blocks, 1, nc);
-    k_shift<<<grid, 256, 0, h->stream>>>(g.chain_stride, h->field[0], h->field[1], h->shift_d);
+    k_set_offset<<<(nc + 127) / 128, 128, 0, h->stream>>>(h->shift_d, h->offset_d, nc, only_chain);
     CU(cudaGetLastError());
     h->launches += 2;
-    ST(ghost_op_end(h));
     return LQFT_OK;
 }
 
@@ -762,6 +769,7 @@ extern "C" lqft_status lqft_init_hot(lqft_handle* h) {
     const Geom& g = h->g;
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
+    CU(cudaMemsetAsync(h->offset_d, 0, sizeof(int32_t) * h->cfg.n_chains, h->stream));
     k_init_hot<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d);
     CU(cudaGetLastError());
     h->launches += 1;
@@ -787,6 +795,7 @@ extern "C" lqft_status lqft_upload(lqft_handle* h, uint32_t chain, const void* v
     ST(need_staging(h));
     const Geom& g = h->g;
     CU(cudaMemcpyAsync(h->staging_d, values, sizeof(int32_t) * h->n_slab, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->offset_d + chain, 0, sizeof(int32_t), h->stream));
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
     k_split<<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
@@ -807,7 +816,7 @@ extern "C" lqft_status lqft_download(lqft_handle* h, uint32_t chain, void* value
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
     k_merge<<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
-                                        h->field[1] + (size_t)chain * g.chain_stride);
+                                        h->field[1] + (size_t)chain * g.chain_stride, h->offset_d + chain);
     CU(cudaGetLastError());
     h->launches += 1;
     CU(cudaMemcpyAsync(values, h->staging_d, sizeof(int32_t) * h->n_slab, cudaMemcpyDeviceToHost, h->stream));
@@ -862,19 +871,9 @@ extern "C" lqft_status lqft_shift_values(lqft_handle* h, uint32_t chain, double 
     if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
     const int32_t s = (int32_t)shift;
     if ((double)s != shift) return fail(LQFT_ERR_INVALID, "shift %g is not an i32 value", shift);
-    std::vector<int32_t> sh(h->cfg.n_chains, 0);
-    sh[chain] = s;
-    CU(cudaMemcpyAsync(h->shift_d, sh.data(), sizeof(int32_t) * sh.size(), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    const Geom& g = h->g;
-    const uint64_t n4 = g.chain_stride / 4 + 1;
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n4 + 255) / 256, (uint64_t)h->sm_count * 8);
-    dim3 grid(blocks, 1, h->cfg.n_chains);
-    ST(ghost_op_begin(h));
-    k_shift<<<grid, 256, 0, h->stream>>>(g.chain_stride, h->field[0], h->field[1], h->shift_d);
+    k_add_offset<<<1, 1, 0, h->stream>>>(h->offset_d, chain, s);  // true = stored - offset
     CU(cudaGetLastError());
     h->launches += 1;
-    ST(ghost_op_end(h));
     return LQFT_OK;
 }
 
@@ -932,9 +931,15 @@ extern "C" lqft_status lqft_slice_moments(lqft_handle* h, uint32_t chain, int64_
     if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
     std::vector<long long> mom;
     ST(fetch_moments(h, chain, mom));
+    int32_t off = 0;
+    CU(cudaMemcpyAsync(&off, h->offset_d + chain, sizeof off, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    // moments of the TRUE heights h = stored - off:  sum h = S1 - A off,  sum h^2 = S2 - 2 off S1 + A off^2
+    const long long A = (long long)h->g.X * h->g.Y, o = off;
     for (uint32_t t = 0; t < h->g.T; ++t) {
-        if (s1) s1[t] = mom[(size_t)t * 2];
-        if (s2) s2[t] = mom[(size_t)t * 2 + 1];
+        const long long m1 = mom[(size_t)t * 2], m2 = mom[(size_t)t * 2 + 1];
+        if (s1) s1[t] = m1 - A * o;
+        if (s2) s2[t] = m2 - 2 * o * m1 + A * o * o;
     }
     return LQFT_OK;
 }
