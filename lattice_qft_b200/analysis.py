@@ -53,3 +53,65 @@ def jackknife(per_chain: np.ndarray, estimator) -> Tuple[float, float]:
     loo = np.array([estimator(np.delete(per_chain, i, axis=0).mean(axis=0)) for i in range(n)])
     err = math.sqrt((n - 1) / n * float(((loo - loo.mean()) ** 2).sum()))
     return float(full), err
+
+
+# ---- binned bootstrap of src/bin/energy_data_analysis.rs:238-315 ---------------------------------------
+BIN_SIZES = (1, 2, 4, 8, 16, 32)      # energy_data_analysis.rs:17
+BOOTSTRAPPING_ENSEMBLES = 100         # energy_data_analysis.rs:18
+
+
+def binned_bootstrap(runs: Sequence[Sequence[float]], bin_size: int, ensembles: int = BOOTSTRAPPING_ENSEMBLES,
+                     seed0: int = 0) -> Tuple[float, float]:
+    """(energy, energy_err) of one `EnergyData` row: every run is cut into bins of `bin_size` consecutive
+    measurements (chunks_exact), each bootstrap ensemble redraws runs with replacement and, inside a run,
+    bins with replacement; the ensemble value is the mean over all redrawn measurements; the row is the
+    mean and the unbiased standard deviation over the ensembles.  The reference seeds ensemble i with
+    StdRng::seed_from_u64(i); numpy's generator stands in (same recipe, different stream)."""
+    binned = []
+    for run in runs:
+        a = np.asarray(run, dtype=np.float64)
+        n = len(a) // bin_size
+        binned.append(a[: n * bin_size].reshape(n, bin_size))
+    means = np.empty(ensembles)
+    for e in range(ensembles):
+        rng = np.random.default_rng(seed0 + e)
+        total, count = 0.0, 0
+        for _ in binned:
+            b = binned[rng.integers(len(binned))]
+            pick = b[rng.integers(len(b), size=len(b))]
+            total += float(pick.sum())
+            count += pick.size
+        means[e] = total / count
+    return float(means.mean()), float(means.std(ddof=1))
+
+
+def integrated_autocorrelation_time(series: Sequence[float], c: float = 5.0) -> float:
+    """tau_int with Sokal's automatic window (smallest W with W >= c * tau_int(W)); 0.5 = uncorrelated."""
+    a = np.asarray(series, dtype=np.float64)
+    a = a - a.mean()
+    n = len(a)
+    var = float(a @ a) / n
+    if var == 0.0:
+        return 0.5
+    tau = 0.5
+    for w in range(1, n // 2):
+        tau += float(a[:-w] @ a[w:]) / ((n - w) * var)
+        if w >= c * tau:
+            break
+    return max(tau, 0.5)
+
+
+def autocorrelation_corrected_error(series: Sequence[float]) -> Tuple[float, float, float]:
+    """(mean, error, tau_int): naive standard error inflated by sqrt(2 tau_int)."""
+    a = np.asarray(series, dtype=np.float64)
+    tau = integrated_autocorrelation_time(a)
+    return float(a.mean()), float(a.std(ddof=1) / math.sqrt(len(a)) * math.sqrt(2.0 * tau)), tau
+
+
+def weighted_linear_fit(x: Sequence[float], y: Sequence[float], err: Sequence[float]) -> Tuple[float, float]:
+    """Slope and offset of `regression` in energy_data_analysis.rs:125-160, weights diag(err)^-1 as there
+    (sic: not err^-2): the slope of E(width) is the string tension times L."""
+    x, y, w = np.asarray(x, float), np.asarray(y, float), 1.0 / np.asarray(err, float)
+    a = np.stack([x, np.ones_like(x)], axis=1)
+    sol = np.linalg.solve(a.T @ (w[:, None] * a), a.T @ (w * y))
+    return float(sol[0]), float(sol[1])

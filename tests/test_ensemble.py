@@ -32,17 +32,6 @@ def ref_xi(L, temp):
     return best[0]["corr12"], best[0]["corr12_err"]
 
 
-def test_symmetrize_kat():  # correlation_data_analysis.rs:550-556
-    assert analysis.symmetrize_single_correlation_function([1, 2, 3, 4, 5, 6]).tolist() == [1, 4, 4, 4, 4, 4]
-
-
-def test_xi_estimator_on_pure_cosh():
-    """lib.rs:106-120 recovers m exactly for C(t) = cosh(m (t - T/2)) on a periodic lattice."""
-    T, m = 32, 0.2
-    c = [np.cosh(m * (t - T / 2)) for t in range(T)]
-    assert analysis.second_moment_xi(c) == pytest.approx(1 / m, rel=1e-9)
-
-
 def run_chains(L, betas, chains_per_beta, iterations, every, wilson=None, seed0=0x5EED):
     n = len(betas) * chains_per_beta
     eng = Engine(L, L, L, n_chains=n)

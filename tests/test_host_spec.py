@@ -144,3 +144,13 @@ def test_run_measurements():
         for n in (0, 1, 5, 10, 25, 100):
             for every in (0, 1, 3, 10):
                 assert E.run_measurements(first, n, every) == brute(first, n, every)
+
+
+def test_rust_shim_declares_every_symbol():
+    """bindings/rust/src/ffi.rs (the reference-side binding of INTEGRATION.md) names exactly the header's symbols."""
+    header = open(os.path.join(ROOT, "include", "lqft.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(lqft_[a-z0-9_]+)\s*\(", header))
+    rust = open(os.path.join(ROOT, "bindings", "rust", "src", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (lqft_[a-z0-9_]+)\s*\(", rust))
+    assert bound == declared, bound ^ declared
