@@ -331,7 +331,7 @@ k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* _
                 if (lane == 0u) halo_wait(&halo.mine->from_hi, halo.wait_for, &halo.mine->error);
                 peer_w = reinterpret_cast<const int4*>(halo.hi_ghost + cbase) + kq;
             }
-            push = peer_w != nullptr && halo.enabled == 1u;
+            push = peer_w != nullptr;
             // lanes differ only by kq on both sides, so one offset per warp serves all of them
             if (push && lane == 0u)
                 s_delta[warp] = reinterpret_cast<const char*>(peer_w) - reinterpret_cast<const char*>(own_w);

@@ -293,32 +293,6 @@ __global__ void k_set_offset(const int32_t* __restrict__ picked, int32_t* __rest
 }
 __global__ void k_add_offset(int32_t* __restrict__ offset, uint32_t chain, int32_t shift) { offset[chain] += shift; }
 
-// Explicit re-centring (not on the hot path): subtract shift[chain] everywhere (ghost planes included).
-// grid = (blocks, 1, n_chains)
-__global__ void k_shift(uint64_t n_per_chain, int32_t* __restrict__ c0_base,
-                        int32_t* __restrict__ c1_base, const int32_t* __restrict__ shift) {
-    const uint32_t chain = blockIdx.z;
-    const int32_t s = shift[chain];
-    if (s == 0) return;
-    int4* a = reinterpret_cast<int4*>(c0_base + (size_t)chain * n_per_chain);
-    int4* b = reinterpret_cast<int4*>(c1_base + (size_t)chain * n_per_chain);
-    const size_t n4 = n_per_chain >> 2;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-         i += (size_t)gridDim.x * blockDim.x) {
-        int4 u = a[i], w = b[i];
-        u.x -= s; u.y -= s; u.z -= s; u.w -= s;
-        w.x -= s; w.y -= s; w.z -= s; w.w -= s;
-        a[i] = u;
-        b[i] = w;
-    }
-    if (blockIdx.x == 0) {  // tail (n_per_chain % 4)
-        for (size_t i = (n4 << 2) + threadIdx.x; i < n_per_chain; i += blockDim.x) {
-            c0_base[(size_t)chain * n_per_chain + i] -= s;
-            c1_base[(size_t)chain * n_per_chain + i] -= s;
-        }
-    }
-}
-
 // ---- observables ---------------------------------------------------------------------------
 // Block-level exact int64 sums, one atomic per block per quantity.
 __device__ __forceinline__ long long warp_sum_ll(long long v) {

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/lqft.h"
+#include "kernels_f64.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_v1.cuh"
@@ -130,6 +131,16 @@ struct lqft_handle {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_bnd = nullptr, ev_comm = nullptr;
     bool timed = false;
     int32_t* field[2] = {nullptr, nullptr};
+    // LQFT_F64 handles (scalar path, one GPU)
+    bool is64 = false;
+    double* field64[2] = {nullptr, nullptr};
+    double* beta_d = nullptr;      // [n_chains]
+    double* offset64_d = nullptr;  // [n_chains]
+    double* obs64_d = nullptr;     // [n_chains][2]
+    double* mom64_d = nullptr;     // [n_chains][T][2]
+    double2* part_d = nullptr;     // per-block compensated partial sums
+    double* elog64_d = nullptr;    // energy log of lqft_run
+    double* gathered64_d = nullptr;
     std::vector<ChainDev> chains_h;
     std::vector<double> beta;
     std::vector<uint8_t> configured;
@@ -196,7 +207,12 @@ static lqft_status upload_params(lqft_handle* h) {
     }
     h->params_dirty = false;
     CU(stream_prepare(h->streamp, h->g, h->sm_count, h->max_thr,
-                      (h->cfg.flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_STREAM)) != 0, h->p2p));
+                      h->is64 || (h->cfg.flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_STREAM)) != 0,
+                      h->p2p));
+    if (h->is64) {
+        CU(cudaMemcpyAsync(h->beta_d, h->beta.data(), sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
     if (getenv("LQFT_DEBUG"))
@@ -417,6 +433,8 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
     cudaFree(h->halo_d);
     tiled_release(h->tiled);
     cudaFree(h->field[0]); cudaFree(h->field[1]);
+    cudaFree(h->field64[0]); cudaFree(h->field64[1]); cudaFree(h->beta_d); cudaFree(h->offset64_d);
+    cudaFree(h->obs64_d); cudaFree(h->mom64_d); cudaFree(h->part_d); cudaFree(h->elog64_d); cudaFree(h->gathered64_d);
     cudaFree(h->chains_d); cudaFree(h->thr_d); cudaFree(h->acc_d); cudaFree(h->obs_d);
     cudaFree(h->mom_d); cudaFree(h->shift_d); cudaFree(h->offset_d); cudaFree(h->staging_d); cudaFree(h->sweep_ctr_d);
     cudaFree(h->n_meas_d); cudaFree(h->elog_d); cudaFree(h->sites_d); cudaFree(h->gathered_d);
@@ -440,8 +458,10 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         return fail(LQFT_ERR_INVALID, "extents %ux%ux%u must be even and >= 2 (red-black order)", X, Y, T);
     if (cfg->n_chains == 0 || cfg->n_chains > 65535)
         return fail(LQFT_ERR_INVALID, "n_chains=%u outside [1,65535]", cfg->n_chains);
-    if (cfg->dtype != LQFT_I32)
-        return fail(LQFT_ERR_INVALID, "dtype %u: only LQFT_I32 fields are implemented", cfg->dtype);
+    if (cfg->dtype != LQFT_I32 && cfg->dtype != LQFT_F64) return fail(LQFT_ERR_INVALID, "unknown dtype %u", cfg->dtype);
+    if (cfg->dtype == LQFT_F64 && (ws > 1 || (cfg->flags & LQFT_FLAG_SELF_HALO)))
+        return fail(LQFT_ERR_INVALID, "LQFT_F64 fields run on one GPU (no slab decomposition)");
+    h->is64 = cfg->dtype == LQFT_F64;
     if ((uint64_t)X * Y / 2 >= (1ull << 31))
         return fail(LQFT_ERR_INVALID, "a t-plane of %ux%u exceeds 2^31 elements per colour", X, Y);
     if ((uint64_t)X * Y * T >= (1ull << 40))
@@ -482,13 +502,23 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     CU(cudaEventCreate(&h->ev_stop));
     CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
-    const size_t fbytes = sizeof(int32_t) * g.chain_stride * nc;
+    const size_t fbytes = (h->is64 ? sizeof(double) : sizeof(int32_t)) * g.chain_stride * nc;
     for (int c = 0; c < 2; ++c) {
-        if (cudaMalloc(&h->field[c], fbytes) != cudaSuccess) {
+        void** slot = h->is64 ? (void**)&h->field64[c] : (void**)&h->field[c];
+        if (cudaMalloc(slot, fbytes) != cudaSuccess) {
             cudaGetLastError();
             return fail(LQFT_ERR_NOMEM, "cannot allocate %zu bytes of device memory for the field", fbytes);
         }
-        CU(cudaMemsetAsync(h->field[c], 0, fbytes, h->stream));
+        CU(cudaMemsetAsync(*slot, 0, fbytes, h->stream));
+    }
+    if (h->is64) {
+        CU(cudaMalloc(&h->beta_d, sizeof(double) * nc));
+        CU(cudaMalloc(&h->offset64_d, sizeof(double) * nc));
+        CU(cudaMemsetAsync(h->offset64_d, 0, sizeof(double) * nc, h->stream));
+        CU(cudaMalloc(&h->obs64_d, sizeof(double) * nc * 2));
+        CU(cudaMalloc(&h->mom64_d, sizeof(double) * (size_t)nc * T * 2));
+        const uint32_t bd64 = 256, bx64 = (g.plane + bd64 - 1) / bd64;
+        CU(cudaMalloc(&h->part_d, sizeof(double2) * (size_t)nc * g.Tl * bx64 * 4));
     }
     CU(cudaMalloc(&h->chains_d, sizeof(ChainDev) * nc));
     CU(cudaMalloc(&h->thr_d, sizeof(uint32_t) * (size_t)nc * kThrStride));
@@ -533,7 +563,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         h->self_halo = true;
         h->p2p = true;
     }
-    CU(tiled_prepare(h->tiled, g, nc, h->sm_count, (cfg->flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1)) != 0));
+    CU(tiled_prepare(h->tiled, g, nc, h->sm_count, h->is64 || (cfg->flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1)) != 0));
     CU(cudaStreamSynchronize(h->stream));
     return LQFT_OK;
 }
@@ -642,6 +672,19 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
                                uint32_t tl_first, uint32_t n_planes, cudaStream_t s, bool halo_now = false) {
     if (n_planes == 0) return LQFT_OK;
     const Geom& g = h->g;
+    if (h->is64) {
+        const uint32_t bd = block_for(g.plane);
+        dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
+        if (h->any_wilson)
+            k_sweep_generic_f64<true><<<grid, bd, 0, s>>>(g, colour, sweep, ctr, h->field64[colour], h->field64[colour ^ 1],
+                                                          h->chains_d, h->beta_d, h->acc_d);
+        else
+            k_sweep_generic_f64<false><<<grid, bd, 0, s>>>(g, colour, sweep, ctr, h->field64[colour], h->field64[colour ^ 1],
+                                                           h->chains_d, h->beta_d, h->acc_d);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        return LQFT_OK;
+    }
     int32_t* own = h->field[colour];
     const int32_t* oth = h->field[colour ^ 1];
     if (h->streamp.enabled || h->tiled.enabled) {
@@ -660,9 +703,6 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
             a.halo.wait_for = h->phase;
             a.halo.phase = ++h->phase;
             a.halo.enabled = 1;
-            static const int dbg = getenv("LQFT_HALO_DEBUG") ? atoi(getenv("LQFT_HALO_DEBUG")) : 0;  // timing experiments only
-            if (dbg & 1) a.halo.wait_for = 0;
-            if (dbg & 2) a.halo.enabled = 2;  // no push
         }
         if (h->streamp.enabled) CU(stream_half(h->streamp, a));
         else CU(tiled_half(h->tiled, a));
@@ -718,6 +758,15 @@ static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* 
 
 static lqft_status launch_observe(lqft_handle* h, bool moments) {
     const Geom& g = h->g;
+    if (h->is64) {  // compensated two-pass reduction, deterministic order
+        const uint32_t bd = 256, bx = (g.plane + bd - 1) / bd;
+        dim3 grid(bx, g.Tl, h->cfg.n_chains);
+        k_observe_f64<<<grid, bd, 0, h->stream>>>(g, h->field64[0], h->field64[1], h->part_d);
+        k_observe_fold_f64<<<h->cfg.n_chains, 128, 0, h->stream>>>(g, h->part_d, bx, h->obs64_d, moments ? h->mom64_d : nullptr);
+        CU(cudaGetLastError());
+        h->launches += 2;
+        return LQFT_OK;
+    }
     ST(ghost_op_begin(h));
     if (g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) {
         const uint32_t units = g.plane / 4;
@@ -741,6 +790,13 @@ static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint
     // (kernels_v1.cuh, k_pick_shift).  Reads owned planes only, so it is not a ghost operation.
     const Geom& g = h->g;
     const uint32_t nc = h->cfg.n_chains;
+    if (h->is64) {
+        k_pick_offset_f64<<<(nc + 127) / 128, 128, 0, h->stream>>>(g, h->field64[0], h->field64[1], h->chains_d, nc, counter,
+                                                                  ctr, explicit_site, only_chain, h->offset64_d);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        return LQFT_OK;
+    }
     k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d, nc,
                                                          counter, ctr, explicit_site, only_chain, h->shift_d);
     CU(cudaGetLastError());
@@ -770,6 +826,10 @@ extern "C" lqft_status lqft_init_hot(lqft_handle* h) {
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
     CU(cudaMemsetAsync(h->offset_d, 0, sizeof(int32_t) * h->cfg.n_chains, h->stream));
+    if (h->is64) {
+        CU(cudaMemsetAsync(h->offset64_d, 0, sizeof(double) * h->cfg.n_chains, h->stream));
+        k_init_hot_f64<<<grid, bd, 0, h->stream>>>(g, h->field64[0], h->field64[1], h->chains_d);
+    } else
     k_init_hot<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d);
     CU(cudaGetLastError());
     h->launches += 1;
@@ -779,7 +839,7 @@ extern "C" lqft_status lqft_init_hot(lqft_handle* h) {
 
 static lqft_status need_staging(lqft_handle* h) {
     if (!h->staging_d) {
-        if (cudaMalloc(&h->staging_d, sizeof(int32_t) * h->n_slab) != cudaSuccess) {
+        if (cudaMalloc(&h->staging_d, (h->is64 ? sizeof(double) : sizeof(int32_t)) * h->n_slab) != cudaSuccess) {
             cudaGetLastError();
             return fail(LQFT_ERR_NOMEM, "cannot allocate the %llu-byte staging buffer",
                         (unsigned long long)(sizeof(int32_t) * h->n_slab));
@@ -794,10 +854,16 @@ extern "C" lqft_status lqft_upload(lqft_handle* h, uint32_t chain, const void* v
     ST(use_device(h));
     ST(need_staging(h));
     const Geom& g = h->g;
-    CU(cudaMemcpyAsync(h->staging_d, values, sizeof(int32_t) * h->n_slab, cudaMemcpyHostToDevice, h->stream));
+    const size_t esz = h->is64 ? sizeof(double) : sizeof(int32_t);
+    CU(cudaMemcpyAsync(h->staging_d, values, esz * h->n_slab, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->offset_d + chain, 0, sizeof(int32_t), h->stream));
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
+    if (h->is64) {
+        CU(cudaMemsetAsync(h->offset64_d + chain, 0, sizeof(double), h->stream));
+        k_split_f64<<<grid, bd, 0, h->stream>>>(g, (const double*)h->staging_d, h->field64[0] + (size_t)chain * g.chain_stride,
+                                                h->field64[1] + (size_t)chain * g.chain_stride);
+    } else
     k_split<<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
                                         h->field[1] + (size_t)chain * g.chain_stride);
     CU(cudaGetLastError());
@@ -815,11 +881,15 @@ extern "C" lqft_status lqft_download(lqft_handle* h, uint32_t chain, void* value
     const Geom& g = h->g;
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
+    if (h->is64)
+        k_merge_f64<<<grid, bd, 0, h->stream>>>(g, (double*)h->staging_d, h->field64[0] + (size_t)chain * g.chain_stride,
+                                                h->field64[1] + (size_t)chain * g.chain_stride, h->offset64_d + chain);
+    else
     k_merge<<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
                                         h->field[1] + (size_t)chain * g.chain_stride, h->offset_d + chain);
     CU(cudaGetLastError());
     h->launches += 1;
-    CU(cudaMemcpyAsync(values, h->staging_d, sizeof(int32_t) * h->n_slab, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(values, h->staging_d, (h->is64 ? sizeof(double) : sizeof(int32_t)) * h->n_slab, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return LQFT_OK;
 }
@@ -869,6 +939,12 @@ extern "C" lqft_status lqft_normalize_site(lqft_handle* h, uint32_t chain, uint6
 extern "C" lqft_status lqft_shift_values(lqft_handle* h, uint32_t chain, double shift) {
     ST(ready(h));
     if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
+    if (h->is64) {
+        k_add_offset_f64<<<1, 1, 0, h->stream>>>(h->offset64_d, chain, shift);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        return LQFT_OK;
+    }
     const int32_t s = (int32_t)shift;
     if ((double)s != shift) return fail(LQFT_ERR_INVALID, "shift %g is not an i32 value", shift);
     k_add_offset<<<1, 1, 0, h->stream>>>(h->offset_d, chain, s);  // true = stored - offset
@@ -893,8 +969,27 @@ static lqft_status measure(lqft_handle* h, bool moments, std::vector<long long>&
     return LQFT_OK;
 }
 
+// f64 handles: energy / action (and moments) as doubles
+static lqft_status measure64(lqft_handle* h, bool moments, std::vector<double>& obs) {
+    const uint32_t nc = h->cfg.n_chains;
+    ST(launch_observe(h, moments));
+    obs.resize((size_t)nc * 2);
+    CU(cudaMemcpyAsync(obs.data(), h->obs64_d, sizeof(double) * obs.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LQFT_OK;
+}
+
 extern "C" lqft_status lqft_energy(lqft_handle* h, int64_t* e_int, double* e_obs) {
     ST(ready(h));
+    if (h->is64) {  // float_energy of a Field<f64>; e_int is its truncation
+        std::vector<double> o;
+        ST(measure64(h, false, o));
+        for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
+            if (e_int) e_int[c] = (int64_t)o[(size_t)c * 2];
+            if (e_obs) e_obs[c] = h->beta[c] * o[(size_t)c * 2];
+        }
+        return LQFT_OK;
+    }
     std::vector<long long> obs;
     ST(measure(h, false, obs));
     for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
@@ -906,6 +1001,15 @@ extern "C" lqft_status lqft_energy(lqft_handle* h, int64_t* e_int, double* e_obs
 
 extern "C" lqft_status lqft_action(lqft_handle* h, int64_t* s_int, double* s_obs) {
     ST(ready(h));
+    if (h->is64) {
+        std::vector<double> o;
+        ST(measure64(h, false, o));
+        for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
+            if (s_int) s_int[c] = (int64_t)o[(size_t)c * 2 + 1];
+            if (s_obs) s_obs[c] = h->beta[c] * o[(size_t)c * 2 + 1];
+        }
+        return LQFT_OK;
+    }
     std::vector<long long> obs;
     ST(measure(h, false, obs));
     for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
@@ -928,6 +1032,7 @@ static lqft_status fetch_moments(lqft_handle* h, uint32_t chain, std::vector<lon
 
 extern "C" lqft_status lqft_slice_moments(lqft_handle* h, uint32_t chain, int64_t* s1, int64_t* s2) {
     ST(ready(h));
+    if (h->is64) return fail(LQFT_ERR_INVALID, "integer slice moments are defined for LQFT_I32 fields");
     if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
     std::vector<long long> mom;
     ST(fetch_moments(h, chain, mom));
@@ -958,6 +1063,43 @@ extern "C" lqft_status lqft_correlator(lqft_handle* h, uint32_t chain, const uin
                              : pick_site(cd.k0, cd.k1, LQFT_STREAM_CORRELATOR, sweep_index, r, h->n_global);
         if (sites[r] >= h->n_global)
             return fail(LQFT_ERR_INVALID, "reference site %llu outside the lattice", (unsigned long long)sites[r]);
+    }
+    if (h->is64) {
+        std::vector<double> o;
+        ST(measure64(h, true, o));
+        std::vector<double> m((size_t)T * 2), hv(reps, 0.0);
+        CU(cudaMemcpyAsync(m.data(), h->mom64_d + (size_t)chain * T * 2, sizeof(double) * T * 2, cudaMemcpyDeviceToHost, h->stream));
+        if (reps) {
+            if (reps > h->sites_cap) {
+                cudaFree(h->sites_d); cudaFree(h->gathered_d); cudaFree(h->gathered64_d);
+                h->sites_d = nullptr; h->gathered_d = nullptr; h->gathered64_d = nullptr; h->sites_cap = 0;
+                CU(cudaMalloc(&h->sites_d, sizeof(uint64_t) * reps));
+                CU(cudaMalloc(&h->gathered_d, sizeof(long long) * reps));
+                CU(cudaMalloc(&h->gathered64_d, sizeof(double) * reps));
+                h->sites_cap = reps;
+            }
+            if (!h->gathered64_d) CU(cudaMalloc(&h->gathered64_d, sizeof(double) * h->sites_cap));
+            CU(cudaMemcpyAsync(h->sites_d, sites.data(), sizeof(uint64_t) * reps, cudaMemcpyHostToDevice, h->stream));
+            k_gather_sites_f64<<<(reps + 127) / 128, 128, 0, h->stream>>>(g, h->field64[0] + (size_t)chain * g.chain_stride,
+                                                                         h->field64[1] + (size_t)chain * g.chain_stride,
+                                                                         h->sites_d, reps, h->gathered64_d);
+            CU(cudaGetLastError());
+            h->launches += 1;
+            CU(cudaMemcpyAsync(hv.data(), h->gathered64_d, sizeof(double) * reps, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        const long double A = (long double)g.X * g.Y;
+        std::vector<long double> c(T, 0.0L);
+        for (uint32_t r = 0; r < reps; ++r) {
+            const uint32_t tx = (uint32_t)(sites[r] / ((uint64_t)g.X * g.Y));
+            const long double v = hv[r];
+            for (uint32_t tau = 0; tau < T; ++tau) {
+                const uint32_t t = (tx + tau) % T;
+                c[tau] += A * v * v - 2.0L * v * (long double)m[(size_t)t * 2] + (long double)m[(size_t)t * 2 + 1];
+            }
+        }
+        for (uint32_t tau = 0; tau < T; ++tau) c_of_tau[tau] = (double)c[tau];
+        return LQFT_OK;
     }
     std::vector<long long> mom;
     ST(fetch_moments(h, chain, mom));
@@ -1011,6 +1153,11 @@ extern "C" lqft_status lqft_difference_update(lqft_handle* h, uint32_t chain) {
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
     ST(ghost_op_begin(h));
+    if (h->is64)
+        k_difference_update_f64<<<grid, bd, 0, h->stream>>>(g, h->field64[0] + (size_t)chain * g.chain_stride,
+                                                            h->field64[1] + (size_t)chain * g.chain_stride,
+                                                            h->diff_sum[chain], h->diff_comp[chain]);
+    else
     k_difference_update<<<grid, bd, 0, h->stream>>>(g, h->field[0] + (size_t)chain * g.chain_stride,
                                                     h->field[1] + (size_t)chain * g.chain_stride,
                                                     h->diff_sum[chain], h->diff_comp[chain]);
@@ -1044,6 +1191,12 @@ extern "C" lqft_status lqft_difference_read(lqft_handle* h, uint32_t chain, doub
 // ---------------------------------------------------------------------------------------------
 static lqft_status launch_energy_log(lqft_handle* h) {
     ST(launch_observe(h, false));
+    if (h->is64) {
+        k_energy_log_f64<<<1, 128, 0, h->stream>>>(h->obs64_d, h->elog64_d, h->elog_cap, h->cfg.n_chains, h->n_meas_d);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        return LQFT_OK;
+    }
     ST(allreduce_i64(h, h->obs_d, (size_t)h->cfg.n_chains * 2));
     k_energy_log<<<1, 128, 0, h->stream>>>(h->obs_d, h->elog_d, h->elog_cap, h->cfg.n_chains, h->n_meas_d);
     CU(cudaGetLastError());
@@ -1082,6 +1235,11 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
         if (cudaMalloc(&h->elog_d, sizeof(long long) * (size_t)nc * n_meas) != cudaSuccess) {
             cudaGetLastError();
             return fail(LQFT_ERR_NOMEM, "cannot allocate the energy log");
+        }
+        if (h->is64) {
+            cudaFree(h->elog64_d);
+            h->elog64_d = nullptr;
+            CU(cudaMalloc(&h->elog64_d, sizeof(double) * (size_t)nc * n_meas));
         }
         h->elog_cap = (uint32_t)n_meas;
         for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
@@ -1154,7 +1312,17 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
     CU(cudaEventRecord(h->ev_stop, h->stream));
     h->timed = true;
 
-    if (n_meas && (e_obs || e_int)) {
+    if (n_meas && (e_obs || e_int) && h->is64) {
+        std::vector<double> log((size_t)nc * h->elog_cap);
+        CU(cudaMemcpyAsync(log.data(), h->elog64_d, sizeof(double) * log.size(), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (uint32_t c = 0; c < nc; ++c)
+            for (uint64_t m = 0; m < n_meas; ++m) {
+                const double e = log[(size_t)c * h->elog_cap + m];
+                if (e_int) e_int[(size_t)c * n_meas + m] = (int64_t)e;
+                if (e_obs) e_obs[(size_t)c * n_meas + m] = h->beta[c] * e;
+            }
+    } else if (n_meas && (e_obs || e_int)) {
         std::vector<long long> log((size_t)nc * h->elog_cap);
         CU(cudaMemcpyAsync(log.data(), h->elog_d, sizeof(long long) * log.size(), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));

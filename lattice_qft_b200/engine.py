@@ -54,10 +54,13 @@ class Engine:
     (or one t-slab of it when world_size > 1)."""
 
     def __init__(self, x: int, y: int, t: int, n_chains: int = 1, device: int = 0, world_size: int = 1,
-                 rank: int = 0, nccl_id: Optional[bytes] = None, flags: int = 0):
+                 rank: int = 0, nccl_id: Optional[bytes] = None, flags: int = 0, dtype: str = "i32"):
         cfg = Config()
         cfg.x, cfg.y, cfg.t = x, y, t
-        cfg.dtype = _lib.LQFT_I32
+        if dtype not in ("i32", "f64"):
+            raise ValueError("dtype must be 'i32' or 'f64'")
+        self.dtype = np.int32 if dtype == "i32" else np.float64
+        cfg.dtype = _lib.LQFT_I32 if dtype == "i32" else _lib.LQFT_F64
         cfg.n_chains = n_chains
         cfg.device = device
         cfg.world_size, cfg.rank = world_size, rank
@@ -102,15 +105,15 @@ class Engine:
         check(lib().lqft_init_hot(self._h))
 
     def upload(self, chain: int, values: np.ndarray):
-        v = np.ascontiguousarray(values, dtype=np.int32).reshape(-1)
+        v = np.ascontiguousarray(values, dtype=self.dtype).reshape(-1)
         if v.size != self.n_slab:
             raise ValueError(f"expected {self.n_slab} values, got {v.size}")
         check(lib().lqft_upload(self._h, chain, v.ctypes.data_as(C.c_void_p)))
 
     def download(self, chain: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:
-            out = np.empty(self.n_slab, dtype=np.int32)
-        assert out.dtype == np.int32 and out.size == self.n_slab and out.flags.c_contiguous
+            out = np.empty(self.n_slab, dtype=self.dtype)
+        assert out.dtype == self.dtype and out.size == self.n_slab and out.flags.c_contiguous
         check(lib().lqft_download(self._h, chain, out.ctypes.data_as(C.c_void_p)))
         return out
 

@@ -600,3 +600,90 @@ uint64_t orc_half_sweep_slab(uint32_t X, uint32_t Y, uint32_t T, uint32_t t0, ui
     }
     return acc;
 }
+
+/* ---------------------------------------------------------------------------------------- */
+/* Field<f64,...>: the same generic code paths instantiated with T = f64 (fields.rs:573-599)   */
+/* ---------------------------------------------------------------------------------------- */
+static double assumed_local_action_f64(const orc_lattice* l, const double* values, const orc_wilson* w,
+                                       uint64_t index, double value) {
+    double sum = 0.0;
+    const uint64_t* nb = orc_neighbours(l, index);
+    for (uint32_t direction = 0; direction < 2 * l->d; ++direction) {
+        double diff = value - values[nb[direction]];
+        if (w && links_is_active(l, w, index, direction)) { /* fields.rs:821-837 */
+            double direction_modifier = direction == 1 ? 1.0 : (direction == 4 ? -1.0 : 0.0);
+            diff = diff + direction_modifier * (w->spin ? 1.0 : -1.0);
+        }
+        sum = sum + diff * diff;
+    }
+    return sum;
+}
+
+uint64_t orc_sweep_f64(const orc_lattice* l, double* values, const orc_wilson* w, double temp, uint64_t seed,
+                       uint64_t sweep, int order) {
+    uint64_t acceptance = 0;
+    for (int pass = 0; pass < (order ? 2 : 1); ++pass)
+        for (uint64_t index = 0; index < l->n_sites; ++index) {
+            const int colour = site_colour(l, index);
+            if (order && colour != pass) continue;
+            const uint32_t word = orc_site_word(seed, index, (uint32_t)colour, sweep);
+            const int coin = (int)(word >> 31);
+            const double draw = (double)(word & 0x7fffffffu) * (1.0 / 2147483648.0);
+            const double old_value = values[index];
+            const double new_value = coin ? old_value + 1.0 : old_value - 1.0; /* T::from(1_i8) */
+            const double old_action = assumed_local_action_f64(l, values, w, index, old_value);
+            const double new_action = assumed_local_action_f64(l, values, w, index, new_value);
+            const double prob = exp((old_action - new_action) * temp);
+            if (draw <= prob) {
+                values[index] = new_value;
+                ++acceptance;
+            }
+        }
+    return acceptance;
+}
+
+/* integer_energy with T = f64 (fields.rs:728-737): the reference's left-to-right folds */
+double orc_energy_f64(const orc_lattice* l, const double* values) {
+    double acc = 0.0;
+    for (uint64_t index = 0; index < l->n_sites; ++index) {
+        const uint64_t* nb = orc_neighbours(l, index);
+        double site = 0.0;
+        for (uint32_t direction = 0; direction + 1 < l->d; ++direction) {
+            double d = values[index] - values[nb[direction]];
+            site = site + d * d;
+        }
+        double dt = values[index] - values[nb[l->d - 1]];
+        site = site - dt * dt;
+        acc = acc + site;
+    }
+    return acc;
+}
+
+double orc_action_f64(const orc_lattice* l, const double* values) { /* fields.rs:719-726 */
+    double sum = 0.0;
+    for (uint64_t index = 0; index < l->n_sites; ++index)
+        for (uint32_t direction = 0; direction < l->d; ++direction) {
+            double d = values[index] - values[orc_neighbours(l, index)[direction]];
+            sum += d * d;
+        }
+    return sum;
+}
+
+void orc_correlator_f64(const orc_lattice* l, const double* values, const uint64_t* x_indices, uint64_t repetitions,
+                        double* correlation_function) { /* outputdata.rs:313-344 */
+    const uint32_t T_DIM = 2;
+    uint64_t max_t = l->size[T_DIM];
+    for (uint64_t t = 0; t < max_t; ++t) correlation_function[t] = 0.0;
+    for (uint64_t rep = 0; rep < repetitions; ++rep) {
+        uint64_t c[ORC_MAX_D];
+        orc_coords_from_index(l, x_indices[rep], c);
+        const uint64_t x_t_coord = c[T_DIM];
+        const double x_value = values[x_indices[rep]];
+        for (uint64_t index = 0; index < l->n_sites; ++index) {
+            orc_coords_from_index(l, index, c);
+            const uint64_t t = (c[T_DIM] + max_t - x_t_coord) % max_t;
+            const double diff = x_value - values[index];
+            correlation_function[t] = correlation_function[t] + diff * diff;
+        }
+    }
+}

@@ -69,6 +69,10 @@ def lib() -> C.CDLL:
             "orc_sizeof_welford": (u64, []),
             "orc_run": (u64, [vp, vp, vp, f64, u64, u64, u64, u64, u32, u32, C.c_int, vp, P(u64)]),
             "orc_bench_chains": (f64, [vp, f64, u64, u64, u32, u32, P(f64)]),
+            "orc_sweep_f64": (u64, [vp, vp, vp, f64, u64, u64, C.c_int]),
+            "orc_energy_f64": (f64, [vp, vp]),
+            "orc_action_f64": (f64, [vp, vp]),
+            "orc_correlator_f64": (None, [vp, vp, vp, u64, vp]),
             "orc_half_sweep_slab": (u64, [u32, u32, u32, u32, u32, vp, C.c_int, f64, u64, u64, u32, u32]),
         }
         for name, (res, args) in sig.items():
@@ -251,3 +255,23 @@ def half_sweep_slab(X, Y, T, t0, tl, values_with_ghosts, colour, temp, seed, swe
     v = values_with_ghosts
     assert v.dtype == np.int32 and v.flags.c_contiguous and v.size == X * Y * (tl + 2)
     return int(lib().orc_half_sweep_slab(X, Y, T, t0, tl, _ptr(v), colour, temp, seed, sweep_index, wilson[0], wilson[1]))
+
+
+def sweep_f64(lat, values, temp, seed, sweep_index, order=1, wilson=None) -> int:
+    assert values.dtype == np.float64 and values.flags.c_contiguous
+    return int(lib().orc_sweep_f64(lat._h, _ptr(values), wilson._h if wilson else None, temp, seed, sweep_index, order))
+
+
+def energy_f64(lat, values) -> float:
+    return float(lib().orc_energy_f64(lat._h, _ptr(values)))
+
+
+def action_f64(lat, values) -> float:
+    return float(lib().orc_action_f64(lat._h, _ptr(values)))
+
+
+def correlator_f64(lat, values, ref_sites) -> np.ndarray:
+    sites = np.ascontiguousarray(ref_sites, dtype=np.uint64)
+    out = np.zeros(lat.size[2], dtype=np.float64)
+    lib().orc_correlator_f64(lat._h, _ptr(values), _ptr(sites), len(sites), _ptr(out))
+    return out

@@ -347,6 +347,47 @@ def test_256cubed_properties():
         assert (eng.download(0) == v).all()
 
 
+@pytest.mark.parametrize("size,wilson", [((8, 6, 4), (0, 0)), ((16, 16, 16), (5, 16)), ((6, 10, 4), (3, 2))])
+def test_f64_fields_within_1e12(size, wilson):
+    """Field<f64> (fields.rs:573-599): post-sweep field and observables vs the f64 oracle.  The north-star
+    tolerance is 1e-12 relative; the field itself comes out identical (heights stay on start + integers)."""
+    X, Y, T = size
+    beta, seed = 0.23, 808
+    lat = O.Lattice([X, Y, T])
+    wil = O.Wilson(lat, *wilson) if wilson[0] else None
+    rng = np.random.default_rng(17)
+    v0 = rng.normal(0.0, 3.0, size=X * Y * T)          # genuinely real-valued heights
+    want = v0.copy()
+    wacc = sum(O.sweep_f64(lat, want, beta, seed, s, order=1, wilson=wil) for s in range(5))
+    sites = [int(v) for v in rng.integers(0, X * Y * T, 20)]
+    with Engine(X, Y, T, dtype="f64") as eng:
+        eng.set_chain(0, beta, seed, *wilson)
+        eng.upload(0, v0)
+        assert (eng.download(0) == v0).all()
+        acc = eng.sweep(0, 5, want_accepted=True)[0]
+        got = eng.download(0)
+        _, e_obs = eng.energy()
+        _, s_obs = eng.action()
+        corr = eng.correlator(0, ref_sites=sites)
+        e_run, _, _ = eng.run(10, sweep_base=5, energy_every=5, normalize_every=10)
+        got2 = eng.download(0)
+    assert acc == wacc
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    assert e_obs[0] == pytest.approx(beta * O.energy_f64(lat, want), rel=1e-12)
+    assert s_obs[0] == pytest.approx(beta * O.action_f64(lat, want), rel=1e-12)
+    np.testing.assert_allclose(corr, O.correlator_f64(lat, want, sites), rtol=1e-11)
+    # schedule: sweeps, energy at steps 0 and 5, normalize at step 0 (shift by the picked site's height)
+    energies = []
+    for step in range(10):
+        O.sweep_f64(lat, want, beta, seed, 5 + step, order=1, wilson=wil)
+        if step % 5 == 0:
+            energies.append(beta * O.energy_f64(lat, want))
+        if step % 10 == 0:
+            want -= want[O.pick_site(seed, 2, 5 + step, 0, X * Y * T)]
+    np.testing.assert_allclose(e_run[0], energies, rtol=1e-11)
+    np.testing.assert_allclose(got2, want, rtol=1e-12, atol=1e-12)
+
+
 def test_error_behaviour():
     from lattice_qft_b200 import LqftError
     with pytest.raises(LqftError) as ei:
