@@ -200,13 +200,17 @@ def other_configs(device: int):
     sec = timed(eng, lambda: eng.run(100, sweep_base=100, energy_every=0), 3)
     out["correlator_128^3_100_sites"]["site_updates_per_s"] = 128**3 * 100 / sec
     eng.close()
-    # config 1: the reference's own 16^3 case (one chain: launch-latency bound on a GPU)
-    eng = Engine(16, 16, 16, device=device)
-    eng.set_chain(0, 0.2, 1)
-    eng.init_hot()
-    sec = timed(eng, lambda: eng.run(2000, energy_every=10), 2)
-    out["reference_case_16^3_1_chain"] = {"site_updates_per_s": 4096 * 2000 / sec, "energy_measurements_per_s": 200 / sec}
-    eng.close()
+    # config 1: the reference's own run — 16^3, one chain per coupling of INVESTIGATE_ARY9 (lib.rs:50), energy every
+    # 10th sweep; small enough to live in shared memory: the whole schedule is one launch (kernels_resident.cuh)
+    for name, n_chains in (("reference_case_16^3_1_chain", 1), ("reference_run_16^3_10_couplings", 10)):
+        eng = Engine(16, 16, 16, n_chains=n_chains, device=device)
+        for c in range(n_chains):
+            eng.set_chain(c, 0.20 + 0.01 * c, 1 + c)
+        eng.init_hot()
+        sec = timed(eng, lambda: eng.run(4000, energy_every=10), 2)
+        out[name] = {"site_updates_per_s": n_chains * 4096 * 4000 / sec, "energy_measurements_per_s": n_chains * 400 / sec,
+                     "launches_per_call": 1}
+        eng.close()
     # energy / action measurement at the headline size
     eng = Engine(256, 256, 256, device=device)
     eng.set_chain(0, BETA, SEED)

@@ -80,6 +80,8 @@ typedef struct lqft_config {
 #define LQFT_FLAG_FORCE_V1 8u     /* use the two-pass L1-cached kernels, not the tiled ones */
 #define LQFT_FLAG_NO_STREAM 16u   /* wide rows: marching kernel instead of the streaming one */
 #define LQFT_FLAG_NO_PDL 32u      /* no programmatic dependent launch between half-sweeps     */
+#define LQFT_FLAG_NO_RESIDENT 128u /* small lattices: multi-launch path instead of the one-launch
+                                     shared-memory resident kernel */
 #define LQFT_FLAG_SELF_HALO 64u   /* world_size==1: ghost planes + the peer-memory halo path with
                                      this rank as its own neighbour (tests the multi-GPU kernel) */
 

@@ -18,6 +18,7 @@
 
 #include "../../include/lqft.h"
 #include "kernels_f64.cuh"
+#include "kernels_resident.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_v1.cuh"
@@ -173,6 +174,8 @@ struct lqft_handle {
     std::map<GraphKey, GraphVal> graphs;
     TiledPlan tiled{};
     StreamPlan streamp{};
+    bool resident_ok = false;   // small lattice: whole runs inside one launch (kernels_resident.cuh)
+    size_t smem_optin = 0;
     // peer-memory halo (world_size > 1)
     bool p2p = false;
     HaloSync* halo_d = nullptr;                 // mine
@@ -212,6 +215,15 @@ static lqft_status upload_params(lqft_handle* h) {
     if (h->is64) {
         CU(cudaMemcpyAsync(h->beta_d, h->beta.data(), sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
+    }
+    h->resident_ok = !h->is64 && !(h->cfg.flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_RESIDENT)) &&
+                     resident_fits(h->g, h->max_thr, h->smem_optin);
+    if (h->resident_ok) {
+        const int smem = (int)resident_smem_bytes(h->g, h->max_thr);
+        CU(cudaFuncSetAttribute(k_run_resident<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_run_resident<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_run_resident<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_run_resident<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
@@ -484,6 +496,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         return fail(LQFT_ERR_CUDA, "device %d is sm_%d%d; liblqft is built for sm_100a only",
                     cfg->device, prop.major, prop.minor);
     h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
 
     Geom& g = h->g;
     g.X = X; g.Y = Y; g.T = T; g.Xh = X / 2;
@@ -1259,7 +1272,26 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
     CU(cudaEventRecord(h->ev_start, h->stream));
     uint64_t step = s->first_step;
     const uint64_t end = s->first_step + s->n_steps;
-    if (use_graph) {
+    if (h->resident_ok && s->n_steps > 0) {
+        // small lattice: the whole schedule in one launch, one CTA per chain, field in shared memory
+        ResidentArgs a{h->g, s->sweep_base, s->first_step, s->n_steps, s->energy_every, s->normalize_every,
+                       h->elog_cap, h->count_accepts ? 1u : 0u};
+        const size_t smem = resident_smem_bytes(h->g, h->max_thr);
+        const bool vec = h->g.Xh % 4 == 0;
+#define LQFT_RES(W, V)                                                                                                 \
+    k_run_resident<W, V><<<nc, kResidentThreads, smem, h->stream>>>(a, h->field[0], h->field[1], h->chains_d, h->thr_d, \
+                                                                    h->offset_d, h->elog_d, h->acc_d)
+        if (h->any_wilson) {
+            if (vec) LQFT_RES(true, true); else LQFT_RES(true, false);
+        } else {
+            if (vec) LQFT_RES(false, true); else LQFT_RES(false, false);
+        }
+#undef LQFT_RES
+        CU(cudaGetLastError());
+        h->launches += 1;
+        step = end;
+    }
+    if (use_graph && step < end) {
         while (step < end && step % cycle != 0) {
             ST(launch_step(h, s, step, step, nullptr));
             ++step;

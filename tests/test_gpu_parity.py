@@ -238,7 +238,7 @@ def test_normalize_and_shift():
         assert (eng.download(0) == v - 3).all()
 
 
-@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_GRAPH])
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_RESIDENT, _lib.FLAG_NO_RESIDENT | _lib.FLAG_NO_GRAPH])
 @pytest.mark.parametrize("first_step,n_steps,energy_every", [(0, 50, 10), (3, 44, 10), (0, 25, 1), (7, 30, 4), (0, 12, 0)])
 def test_run_schedule_matches_oracle(first_step, n_steps, energy_every, flags):
     """lqft_run == loop body of Simulation::run (computation.rs:249-270), graph replay included."""
@@ -256,6 +256,39 @@ def test_run_schedule_matches_oracle(first_step, n_steps, energy_every, flags):
     assert (got == want).all()
     assert e_obs.shape == (1, len(we)) and (e_obs[0] == we).all()
     assert acc[0] == wacc
+
+
+@pytest.mark.parametrize("size,wilson", [((16, 16, 16), (5, 16)), ((24, 24, 24), (0, 0)), ((36, 36, 36), (0, 0)),
+                                         ((6, 10, 4), (3, 2)), ((12, 6, 10), (0, 0))])
+def test_resident_kernel_whole_run_in_one_launch(size, wilson):
+    """Lattices that fit one SM's shared memory (the reference's 16^3 ... 36^3) run their whole schedule in ONE
+    launch; batch of chains, Wilson chain included, identical to the multi-launch path and to the oracle."""
+    X, Y, T = size
+    n_chains = 3
+    betas, seeds = [0.2, 0.25, 0.29], [11, 12, 13]
+    steps = 12 if X * Y * T > 20000 else 40
+    res = {}
+    for flags in (0, _lib.FLAG_NO_RESIDENT):
+        with Engine(X, Y, T, n_chains=n_chains, flags=flags) as eng:
+            for c in range(n_chains):
+                eng.set_chain(c, betas[c], seeds[c], *(wilson if c == 1 else (0, 0)))
+            eng.init_hot()
+            before = eng.kernel_launches()
+            e_obs, e_int, acc = eng.run(steps, first_step=0, sweep_base=5, energy_every=4, normalize_every=10,
+                                        want_accepted=True)
+            launches = eng.kernel_launches() - before
+            res[flags] = (e_obs, acc, [eng.download(c) for c in range(n_chains)], launches, eng.energy()[0])
+    assert res[0][3] == 1 and res[_lib.FLAG_NO_RESIDENT][3] > steps
+    assert (res[0][0] == res[_lib.FLAG_NO_RESIDENT][0]).all() and res[0][1] == res[_lib.FLAG_NO_RESIDENT][1]
+    assert (res[0][4] == res[_lib.FLAG_NO_RESIDENT][4]).all()
+    for c in range(n_chains):
+        assert (res[0][2][c] == res[_lib.FLAG_NO_RESIDENT][2][c]).all()
+    # and the oracle for one of the chains
+    lat = O.Lattice([X, Y, T])
+    want = O.init_hot(lat, seeds[1])
+    wil = O.Wilson(lat, *wilson) if wilson[0] else None
+    we, wacc = O.run(lat, want, betas[1], seeds[1], 5, 0, steps, 4, 10, order=1, wilson=wil)
+    assert (res[0][0][1] == we).all() and res[0][1][1] == wacc and (res[0][2][1] == want).all()
 
 
 def test_run_wilson_chain_measures_plain_field():
