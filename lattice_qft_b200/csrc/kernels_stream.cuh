@@ -227,27 +227,60 @@ __device__ __forceinline__ void stream_chunk(int4* __restrict__ own_w, const boo
     const uint32_t ym = (y_begin == 0u) ? Y - 1u : y_begin - 1u;
     int4 om = __ldg(q.oc + ym * G);
     int4 oc = __ldg(q.oc + y_begin * G);
-    for (uint32_t s = 0; s < n_steps; s += 2) {
-        const uint32_t y = y_begin + s;
+    // Running pointers to the row that is D steps ahead (the one being prefetched); the row being updated is
+    // D rows behind pf_own, a compile-time offset.  No per-step index arithmetic.
+    const int4* pf_own = q.own + (y_begin + D) * G;
+    const int4* pf_ta = q.ta + (y_begin + D) * G;
+    const int4* pf_tb = q.tb + (y_begin + D) * G;
+    const int4* pf_on = q.oc + (y_begin + D + 1u) * G;  // other colour, one row further (wraps to row 0)
+    const int32_t* pf_ep = qp.edge + (y_begin + D) * (4u * G);
+    const int32_t* pf_en = qn.edge + (y_begin + D) * (4u * G);
+    constexpr uint32_t STAGE_BYTES = 4u * kStreamThreads * 16u;
+    constexpr uint32_t SLOT = kStreamThreads * 16u;
+    uint32_t grp = grp_row0 + y_begin * G;
+    uint32_t y = y_begin;
+    for (uint32_t s = 0; s < n_steps; s += 2, y += 2) {
         const uint32_t st0 = s & (uint32_t)(D - 1), st1 = (s + 1u) & (uint32_t)(D - 1);
         cp_async_wait<D - 1>();
-        stream_step<SEGS, WILSON, COUNT, HALO, P0>(own_w + y * G, push, s_delta, ring, edge_ring, st0, om, oc, P0 ? src_up : src_dn,
-                                             P0 ? edge_p : edge_n, grp_row0 + y * G, colour, sweep, rk, s_dn, s_up, kc,
-                                             y, Y, kq, wil_plane, wil_w, accepted);
+        stream_step<SEGS, WILSON, COUNT, HALO, P0>(const_cast<int4*>(pf_own) - D * (int)G, push, s_delta, ring, edge_ring, st0,
+                                                   om, oc, P0 ? src_up : src_dn, P0 ? edge_p : edge_n, grp, colour, sweep,
+                                                   rk, s_dn, s_up, kc, y, Y, kq, wil_plane, wil_w, accepted);
         if (s + D < n_steps) {
-            if (P0) stream_issue<SEGS, true>(qp, y + D, Y, ring, edge_ring, st0, edge_p);
-            else stream_issue<SEGS, false>(qn, y + D, Y, ring, edge_ring, st0, edge_n);
+            const uint32_t dst = ring + st0 * STAGE_BYTES;
+            cp_async16_cg(dst, pf_own);
+            cp_async16_ca(dst + SLOT, (y + D + 1u == Y) ? q.oc : pf_on);
+            cp_async16_ca(dst + 2u * SLOT, pf_ta);
+            cp_async16_ca(dst + 3u * SLOT, pf_tb);
+            if (SEGS > 1) {
+                if (P0 ? edge_p : edge_n) cp_async4_ca(edge_ring + st0 * (kStreamThreads * 4u), P0 ? pf_ep : pf_en);
+            }
         }
         cp_async_commit();
         cp_async_wait<D - 1>();
-        stream_step<SEGS, WILSON, COUNT, HALO, !P0>(own_w + (y + 1u) * G, push, s_delta, ring, edge_ring, st1, om, oc, P0 ? src_dn : src_up,
-                                              P0 ? edge_n : edge_p, grp_row0 + (y + 1u) * G, colour, sweep, rk, s_dn,
-                                              s_up, kc, y + 1u, Y, kq, wil_plane, wil_w, accepted);
+        stream_step<SEGS, WILSON, COUNT, HALO, !P0>(const_cast<int4*>(pf_own) - (D - 1) * (int)G, push, s_delta, ring, edge_ring,
+                                                    st1, om, oc, P0 ? src_dn : src_up, P0 ? edge_n : edge_p, grp + G, colour,
+                                                    sweep, rk, s_dn, s_up, kc, y + 1u, Y, kq, wil_plane, wil_w, accepted);
         if (s + 1u + D < n_steps) {
-            if (!P0) stream_issue<SEGS, true>(qp, y + 1u + D, Y, ring, edge_ring, st1, edge_p);
-            else stream_issue<SEGS, false>(qn, y + 1u + D, Y, ring, edge_ring, st1, edge_n);
+            const uint32_t dst = ring + st1 * STAGE_BYTES;
+            cp_async16_cg(dst, pf_own + G);
+            cp_async16_ca(dst + SLOT, (y + D + 2u == Y) ? q.oc : pf_on + G);
+            cp_async16_ca(dst + 2u * SLOT, pf_ta + G);
+            cp_async16_ca(dst + 3u * SLOT, pf_tb + G);
+            if (SEGS > 1) {
+                if (P0 ? edge_n : edge_p)
+                    cp_async4_ca(edge_ring + st1 * (kStreamThreads * 4u), (P0 ? pf_en : pf_ep) + 4u * G);
+            }
         }
         cp_async_commit();
+        pf_own += 2u * G;
+        pf_on += 2u * G;
+        pf_ta += 2u * G;
+        pf_tb += 2u * G;
+        if (SEGS > 1) {
+            pf_ep += 8u * G;
+            pf_en += 8u * G;
+        }
+        grp += 2u * G;
     }
     cp_async_wait<0>();
 }
