@@ -292,7 +292,7 @@ k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* _
                const uint32_t tl_first, const uint32_t n_planes, const uint32_t n_chunks, const uint32_t n_bchunks,
                int32_t* __restrict__ own_base, const int32_t* __restrict__ oth_base,
                const ChainDev* __restrict__ chains, const uint32_t* __restrict__ thr_all,
-               unsigned long long* __restrict__ acc, const HaloP2P halo) {
+               unsigned long long* __restrict__ acc, const uint32_t max_thr, const HaloP2P halo) {
     constexpr uint32_t G = 32u * SEGS;
     constexpr uint32_t RING_BYTES = (uint32_t)kStreamDepth * 4u * kStreamThreads * 16u;
     constexpr uint32_t EDGE_BYTES = SEGS > 1 ? (uint32_t)kStreamDepth * kStreamThreads * 4u : 0u;
@@ -301,13 +301,17 @@ k_sweep_stream(const Geom g, const int colour, uint64_t sweep, const uint64_t* _
     __shared__ long long s_delta[kStreamWarps];
     pdl_launch_dependents();
     const uint32_t chain = blockIdx.z;
+    // Block prologue.  The chain parameters and the threshold table are read independently of each other (the
+    // table is built for the handle's longest table; shorter chains' tails are zero, exactly what their clamp
+    // would select) and BEFORE the dependency wait, so with programmatic dependent launch this part overlaps
+    // the predecessor's tail.
     const ChainDev cd = chains[chain];
     if (COUNT && threadIdx.x == 0) s_cnt = 0;
     uint2* s_tab2 = reinterpret_cast<uint2*>(s_raw + RING_BYTES + EDGE_BYTES);
-    const int kc = build_two_sided(s_tab2, thr_all + (size_t)chain * kThrStride, cd.n_thr);
+    const int kc = build_two_sided(s_tab2, thr_all + (size_t)chain * kThrStride, max_thr);
     const uint2* s_dn = s_tab2 + kc;
     const uint2* s_up = s_tab2 + 3 * kc + 1;
-    pdl_wait();
+    pdl_wait();  // from here on the predecessor has completed
     if (ctr) sweep += *ctr;
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -477,9 +481,12 @@ inline cudaError_t stream_launch(const StreamPlan& p, const MarchArgs& a) {
     HaloP2P halo = a.halo;
     uint32_t n_bchunks = 0;
     if (halo.enabled) {
-        // boundary plane group in chunks half as long as the interior ones (at least 4 rows each)
+        // boundary plane group in chunks a fraction as long as the interior ones (at least 4 rows each): the
+        // earlier they finish, the more slack the flag has to cross NVLink before the next phase starts
+        constexpr uint32_t factor = 4;
         const uint32_t max_chunks = a.g.Y / 4 ? a.g.Y / 4 : 1;
-        n_bchunks = 2 * n_chunks < max_chunks ? 2 * n_chunks : max_chunks;
+        n_bchunks = factor * n_chunks < max_chunks ? factor * n_chunks : max_chunks;
+        if (n_bchunks == 0) n_bchunks = 1;
         grid = dim3(SEGS * (n_bchunks + (n_groups - 1) * n_chunks), 1, a.n_chains);
         halo.n_boundary_blocks = SEGS * n_bchunks * a.n_chains;
     }
@@ -495,7 +502,7 @@ inline cudaError_t stream_launch(const StreamPlan& p, const MarchArgs& a) {
     cfg.numAttrs = a.pdl ? 1 : 0;
 #define LQFT_GO(W, C, H)                                                                                                 \
     return cudaLaunchKernelEx(&cfg, k_sweep_stream<SEGS, W, C, H>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_planes, \
-                              n_chunks, n_bchunks, a.own, a.oth, a.chains, a.thr, a.acc, halo)
+                              n_chunks, n_bchunks, a.own, a.oth, a.chains, a.thr, a.acc, a.max_thr, halo)
     if (halo.enabled) {
         if (a.wilson) {
             if (a.count) LQFT_GO(true, true, true); else LQFT_GO(true, false, true);

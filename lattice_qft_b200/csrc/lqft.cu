@@ -605,6 +605,7 @@ extern "C" lqft_status lqft_set_chain(lqft_handle* h, uint32_t chain, double bet
         return fail(LQFT_ERR_INVALID, "wilson loop %ux%u does not fit the %ux%u x-t plane", wil_w, wil_h,
                     h->cfg.x, h->cfg.t);
     uint32_t* thr = h->thr_h.data() + (size_t)chain * kThrStride;
+    std::fill(thr, thr + kThrStride, 0u);  // kernels may read up to the handle's longest table: the tail must be 0
     const uint32_t n = lqft_host_threshold_table(beta, thr, kThrStride);
     if (n == 0)
         return fail(LQFT_ERR_INVALID,
