@@ -39,7 +39,7 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long* s_red)
 }
 
 // grid = n_chains, block = kResidentThreads, dynamic smem = 2 * (N/2) * 4 + table.
-template <bool WILSON, bool VEC>
+template <bool WILSON, int VEC>
 __global__ void __launch_bounds__(kResidentThreads, 1)
 k_run_resident(const ResidentArgs a, int32_t* __restrict__ c0_base, int32_t* __restrict__ c1_base,
                const ChainDev* __restrict__ chains, const uint32_t* __restrict__ thr_all,
@@ -92,7 +92,7 @@ k_run_resident(const ResidentArgs a, int32_t* __restrict__ c0_base, int32_t* __r
                 const uint32_t grp = threadIdx.x + (uint32_t)j * blockDim.x;
                 if (grp < n_groups) {
                     const u32x4 r = philox4x32_rk(grp, colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);
-                    if (VEC) {
+                    if (VEC == 4) {
                         // Xh % 4 == 0: the group is one aligned quad of a row.  128-bit shared-memory accesses (a
                         // scalar walk over 4 consecutive positions would be a 4-way bank conflict on every load).
                         const uint32_t k0 = gk[j], y = gy[j], t = gt[j];
@@ -127,6 +127,41 @@ k_run_resident(const ResidentArgs a, int32_t* __restrict__ c0_base, int32_t* __r
                         w.z = metropolis_update2<true>(v.z, ns.z, wo.z, r.z, s_dn, s_up, kc, accepted);
                         w.w = metropolis_update2<true>(v.w, ns.w, wo.w, r.w, s_dn, s_up, kc, accepted);
                         *reinterpret_cast<int4*>(own + rowo + k0) = w;
+                    } else if (VEC == 2) {
+                        // Xh % 2 == 0 (36^3: Xh = 18): the group is two aligned pairs, each inside one row;
+                        // 64-bit shared-memory accesses
+                        uint32_t k = gk[j], y = gy[j], t = gt[j];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const uint32_t p = (y + t + colour) & 1u;
+                            const uint32_t yp = (y + 1 == g.Y) ? 0 : y + 1, ym = (y == 0) ? g.Y - 1 : y - 1;
+                            const uint32_t tp = (t + 1 == g.T) ? 0 : t + 1, tm = (t == 0) ? g.T - 1 : t - 1;
+                            const uint32_t rowo = (t * g.Y + y) * g.Xh;
+                            const uint32_t kx = p ? (k + 2 == g.Xh ? 0 : k + 2) : (k == 0 ? g.Xh - 1 : k - 1);
+                            const int2 v = *reinterpret_cast<const int2*>(own + rowo + k);
+                            const int2 o = *reinterpret_cast<const int2*>(oth + rowo + k);
+                            const int ex = oth[rowo + kx];
+                            const int2 na = *reinterpret_cast<const int2*>(oth + (t * g.Y + yp) * g.Xh + k);
+                            const int2 nb = *reinterpret_cast<const int2*>(oth + (t * g.Y + ym) * g.Xh + k);
+                            const int2 nc = *reinterpret_cast<const int2*>(oth + (tp * g.Y + y) * g.Xh + k);
+                            const int2 nd = *reinterpret_cast<const int2*>(oth + (tm * g.Y + y) * g.Xh + k);
+                            const int ns0 = o.x + (p ? o.y : ex) + na.x + nb.x + nc.x + nd.x;
+                            const int ns1 = o.y + (p ? ex : o.x) + na.y + nb.y + nc.y + nd.y;
+                            int w0 = 0, w1 = 0;
+                            if (WILSON) {
+                                w0 = wilson_offset(g.Y, 2 * k + p, y, t, cd.wil_w, cd.wil_h);
+                                w1 = wilson_offset(g.Y, 2 * k + 2 + p, y, t, cd.wil_w, cd.wil_h);
+                            }
+                            int2 w;
+                            w.x = metropolis_update2<true>(v.x, ns0, w0, word_of(r, (uint32_t)(2 * e)), s_dn, s_up, kc, accepted);
+                            w.y = metropolis_update2<true>(v.y, ns1, w1, word_of(r, (uint32_t)(2 * e + 1)), s_dn, s_up, kc, accepted);
+                            *reinterpret_cast<int2*>(own + rowo + k) = w;
+                            k += 2;
+                            if (k == g.Xh) {
+                                k = 0;
+                                if (++y == g.Y) { y = 0; ++t; }
+                            }
+                        }
                     } else {
                         uint32_t k = gk[j], y = gy[j], t = gt[j];
 #pragma unroll

@@ -220,10 +220,12 @@ static lqft_status upload_params(lqft_handle* h) {
                      resident_fits(h->g, h->max_thr, h->smem_optin);
     if (h->resident_ok) {
         const int smem = (int)resident_smem_bytes(h->g, h->max_thr);
-        CU(cudaFuncSetAttribute(k_run_resident<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(k_run_resident<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(k_run_resident<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(k_run_resident<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_run_resident<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_run_resident<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_run_resident<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_run_resident<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_run_resident<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_run_resident<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
@@ -1278,14 +1280,14 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
         ResidentArgs a{h->g, s->sweep_base, s->first_step, s->n_steps, s->energy_every, s->normalize_every,
                        h->elog_cap, h->count_accepts ? 1u : 0u};
         const size_t smem = resident_smem_bytes(h->g, h->max_thr);
-        const bool vec = h->g.Xh % 4 == 0;
+        const int vec = h->g.Xh % 4 == 0 ? 4 : (h->g.Xh % 2 == 0 ? 2 : 1);
 #define LQFT_RES(W, V)                                                                                                 \
     k_run_resident<W, V><<<nc, kResidentThreads, smem, h->stream>>>(a, h->field[0], h->field[1], h->chains_d, h->thr_d, \
                                                                     h->offset_d, h->elog_d, h->acc_d)
         if (h->any_wilson) {
-            if (vec) LQFT_RES(true, true); else LQFT_RES(true, false);
+            if (vec == 4) LQFT_RES(true, 4); else if (vec == 2) LQFT_RES(true, 2); else LQFT_RES(true, 1);
         } else {
-            if (vec) LQFT_RES(false, true); else LQFT_RES(false, false);
+            if (vec == 4) LQFT_RES(false, 4); else if (vec == 2) LQFT_RES(false, 2); else LQFT_RES(false, 1);
         }
 #undef LQFT_RES
         CU(cudaGetLastError());
