@@ -48,7 +48,9 @@ typedef enum lqft_status {
 
 typedef enum lqft_dtype {
     LQFT_I32 = 0, /* Field<i32,...>: the type of every driver path (computation.rs:226,308) */
-    LQFT_F64 = 1  /* Field<f64,...>: admitted by HeightVariable (fields.rs:573-599)         */
+    LQFT_F64 = 1  /* Field<f64,...>: admitted by HeightVariable (fields.rs:573-599).  One GPU, scalar
+                     kernels; upload/download take double; integer outputs (e_int, s_int) hold the
+                     truncated f64 value; lqft_slice_moments is not defined; hot start = i8 values */
 } lqft_dtype;
 
 /* RNG stream tags: second counter word of Philox4x32-10 (see lqft_host_philox4x32). */

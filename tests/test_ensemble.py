@@ -74,6 +74,37 @@ def test_free_energy_24_and_36_within_2_sigma():
 
 
 @pytest.mark.gpu
+def test_free_energy_54_within_2_sigma():
+    """The largest published size (54^3: X % 8 != 0, so the scalar kernels carry it)."""
+    eng, e = run_chains(54, [0.24], 16, 6000, 10)
+    eng.close()
+    mean, err = analysis.chain_mean_and_error(e[0].mean(axis=1))
+    ref, ref_err = ref_energy(54, 0.24)
+    z = (mean - ref) / np.hypot(err, ref_err)
+    print(f"54^3 beta=0.24: ours {mean:.3f} +- {err:.3f}  reference {ref:.3f} +- {ref_err:.3f}  z = {z:+.2f}")
+    assert abs(z) < 2.0
+
+
+@pytest.mark.gpu
+def test_single_chain_autocorrelation_corrected_error():
+    """One long chain, error from the integrated autocorrelation time (north-star wording): must agree with the
+    reference within 2 sigma and with the chain-to-chain error estimate."""
+    eng, e = run_chains(16, [0.26], 8, 100000, 10)
+    eng.close()
+    ref, ref_err = ref_energy(16, 0.26)
+    taus = []
+    for c in range(2):
+        mean, err, tau = analysis.autocorrelation_corrected_error(e[0][c])
+        taus.append(tau)
+        z = (mean - ref) / np.hypot(err, ref_err)
+        print(f"16^3 beta=0.26 chain {c}: {mean:.3f} +- {err:.3f} (tau_int = {tau:.2f} measurements)  reference {ref:.3f} +- {ref_err:.3f}  z = {z:+.2f}")
+        assert abs(z) < 2.5
+    chain_err = analysis.chain_mean_and_error(e[0].mean(axis=1))[1] * np.sqrt(8)   # error of ONE chain from the scatter
+    assert 0.5 < err / chain_err < 2.0
+    assert 0.5 <= min(taus) and max(taus) < 5.0
+
+
+@pytest.mark.gpu
 def test_wilson_energies_16_within_2_sigma():
     """Wilson-inserted chains: sampling with the shifted sheet, energy of the PLAIN field every sweep (Q3, Q4)."""
     widths = [2, 8, 13]
