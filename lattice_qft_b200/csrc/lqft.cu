@@ -907,7 +907,7 @@ extern "C" lqft_status lqft_download(lqft_handle* h, uint32_t chain, void* value
     h->launches += 1;
     CU(cudaMemcpyAsync(values, h->staging_d, (h->is64 ? sizeof(double) : sizeof(int32_t)) * h->n_slab, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return LQFT_OK;
+    return check_halo_error(h);  // a lost neighbour must not pass for a valid field
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -982,7 +982,7 @@ static lqft_status measure(lqft_handle* h, bool moments, std::vector<long long>&
     obs.resize((size_t)nc * 2);
     CU(cudaMemcpyAsync(obs.data(), h->obs_d, sizeof(long long) * obs.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return LQFT_OK;
+    return check_halo_error(h);
 }
 
 // f64 handles: energy / action (and moments) as doubles
