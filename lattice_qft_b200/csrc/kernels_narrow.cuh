@@ -1,0 +1,399 @@
+// kernels_narrow.cuh — red-black Metropolis half-sweep on 16-bit heights (X = 256).
+//
+// The reference keeps heights in i32 (Field<i32>, fields.rs:63-67) and so does the ABI; between API calls the
+// device field is i32 too.  Inside lqft_run / lqft_sweep the engine may hold a *narrow* working copy instead:
+// u16 heights biased by kN16Bias relative to a per-chain centre (the chain's normalisation offset).  Half the
+// bytes per site, and — what matters more on this latency/issue-bound kernel — half the registers per site:
+// one thread owns 8 same-colour sites (one 16-byte load), a half-warp one row of 128 positions, a warp two
+// adjacent t-planes whose inner t-neighbour rows are exchanged by SHFL instead of being loaded.
+//
+// Same decision spec as every other kernel family (spec.cuh: Philox keying by global index, integer
+// threshold table), so results are bit-identical to the i32 kernels and to the oracle; what differs is the
+// arithmetic used to get there:
+//   * neighbour sums are formed on packed pairs: with heights in [0, 4096) a 6-term sum stays below 2^16, so
+//     plain 32-bit adds never carry from the low half into the high half;
+//   * u = 6 v + 0x6000 - sum holds d + 24576 per half, again without borrow; one VIADDMNMX.S16x2.RELU
+//     (add.s16x2 + min.s16x2.relu) turns both halves into the clamped table index d + kc in [0, 2 kc];
+//   * the coin bit of the site's Philox word is funnel-shifted into the index, so one LDS.64 fetches
+//     {threshold | coin << 31, +-1} for the proposed direction.
+//
+// Validity: a narrow segment starts only if every height is within kN16Guard of the centre and lasts at most
+// kN16Segment sweeps; a sweep moves a site by at most one, so no height can leave [0, 4096) (host logic in
+// lqft.cu, narrow_enter / narrow_exit).
+#pragma once
+#include "kernels_stream.cuh"
+
+namespace lqft {
+
+constexpr int kN16Warps = 8;                     // per block: 16 planes
+constexpr int kN16Threads = kN16Warps * 32;
+constexpr int kN16Bias = 2048;
+constexpr int kN16Guard = 1023;
+constexpr uint32_t kN16Segment = 1000;           // kN16Guard + kN16Segment < kN16Bias
+constexpr int kN16KcMax = 255;                   // threshold tables up to 256 entries (beta >= ~0.045)
+constexpr uint32_t kN16RowQ = 16;                // uint4 per row of one colour (X = 256)
+
+struct NarrowHalo {
+    uint16_t* lo_ghost = nullptr;  // lower neighbour's UPPER ghost plane of the colour being updated (chain 0)
+    uint16_t* hi_ghost = nullptr;  // upper neighbour's LOWER ghost plane
+    HaloSync* lo_sync = nullptr;
+    HaloSync* hi_sync = nullptr;
+    HaloSync* mine = nullptr;
+    unsigned long long phase = 0;
+    unsigned long long wait_for = 0;
+    uint32_t n_boundary_blocks = 0;
+    uint32_t enabled = 0;
+};
+
+// Table entry (i << 1) | coin for d = i - kc: coin 1 proposes +1 (m = d), coin 0 proposes -1 (m = -d);
+// same contents as build_two_sided (kernels_tiled.cuh), interleaved so that the coin can be shifted in.
+__device__ __forceinline__ int build_interleaved(uint2* s_tab, const uint32_t* __restrict__ thr, uint32_t n_thr) {
+    const int kc = max((int)n_thr - 1, 3);
+    for (int i = threadIdx.x; i < 2 * (2 * kc + 1); i += blockDim.x) {
+        const int up = i & 1, d = (i >> 1) - kc;
+        const int m = up ? d : -d;
+        const int k = min(max(m + 3, 0), (int)n_thr - 1);
+        s_tab[i] = make_uint2(thr[k] | (up ? 0x80000000u : 0u), up ? 1u : 0xffffffffu);
+    }
+    __syncthreads();
+    return kc;
+}
+
+__shared__ uint2 s_n16_tab[2 * (2 * kN16KcMax + 1)];
+
+// Sums and decisions of one row of 8 sites per thread.  P = x parity of the row's sites (warp uniform).
+template <int P, bool WILSON, bool COUNT>
+__device__ __forceinline__ uint4 n16_row_update(const uint4 v, const uint4 om, const uint4 oc, const uint4 on, const uint4 to,
+                                                const uint4 ti, const uint32_t edge, const u32x4 r0, const u32x4 r1,
+                                                const uint32_t c_off, const uint32_t c_max, const uint4 woff, int& accepted) {
+    uint4 sh;  // the other x neighbour of site j: position j+1 (P) or j-1 (!P)
+    if (P) {
+        sh.x = __byte_perm(oc.x, oc.y, 0x5432); sh.y = __byte_perm(oc.y, oc.z, 0x5432);
+        sh.z = __byte_perm(oc.z, oc.w, 0x5432); sh.w = __byte_perm(oc.w, edge, 0x5432);
+    } else {
+        sh.x = __byte_perm(edge, oc.x, 0x5432); sh.y = __byte_perm(oc.x, oc.y, 0x5432);
+        sh.z = __byte_perm(oc.y, oc.z, 0x5432); sh.w = __byte_perm(oc.z, oc.w, 0x5432);
+    }
+    constexpr uint32_t C = 0x60006000u;
+    uint4 w;
+#define LQFT_N16_PAIR(F, RA, RB)                                                                      \
+    {                                                                                                 \
+        const uint32_t ns = oc.F + sh.F + om.F + on.F + to.F + ti.F;                                  \
+        uint32_t u = 6u * v.F + C - ns;                                                               \
+        if (WILSON) u += woff.F;                                                                      \
+        const uint32_t idx = __viaddmin_s16x2_relu(u, c_off, c_max);                                  \
+        const uint2 ta = s_n16_tab[__funnelshift_l(RA, idx & 0xffffu, 1)];                            \
+        const uint2 tb = s_n16_tab[__funnelshift_l(RB, idx >> 16, 1)];                                \
+        const bool aa = (RA) <= ta.x, ab = (RB) <= tb.x;                                              \
+        if (COUNT) accepted += (int)aa + (int)ab;                                                     \
+        w.F = v.F + (aa ? ta.y : 0u) + ((ab ? tb.y : 0u) << 16);                                      \
+    }
+    LQFT_N16_PAIR(x, r0.x, r0.y)
+    LQFT_N16_PAIR(y, r0.z, r0.w)
+    LQFT_N16_PAIR(z, r1.x, r1.y)
+    LQFT_N16_PAIR(w, r1.z, r1.w)
+#undef LQFT_N16_PAIR
+    return w;
+}
+
+// Packed Wilson offsets of the 8 sites x = 2 (k0 + j) + p of a row next to the sheet (spec.cuh, wilson_offset).
+__device__ __forceinline__ uint4 n16_wilson(uint32_t k0, uint32_t p, int sgn, uint32_t wil_w) {
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t xa = 2u * (k0 + 2u * i) + p, xb = xa + 2u;
+        const int lo = xa < wil_w ? sgn : 0, hi = xb < wil_w ? sgn : 0;
+        o[i] = (uint32_t)lo + ((uint32_t)hi << 16);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// grid = (n_chunks, ceil(Tl / 16), n_chains); with HALO: (n_bchunks + (groups - 1) * n_chunks, 1, n_chains).
+// Lanes 0-15: plane t, row y; lanes 16-31: plane t+1, row y+1 — the same x parity, and each half's inner
+// t-neighbour row sits in the partner half's register window.
+template <bool WILSON, bool COUNT, bool HALO>
+__global__ void __launch_bounds__(kN16Threads, (HALO || COUNT) ? 3 : 4)
+k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const uint32_t n_chunks,
+            const uint32_t n_bchunks, uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
+            const ChainDev* __restrict__ chains, const uint32_t* __restrict__ thr_all,
+            unsigned long long* __restrict__ acc, const uint32_t max_thr, const NarrowHalo halo) {
+    __shared__ unsigned int s_cnt;
+    __shared__ long long s_delta[kN16Warps][2];
+    pdl_launch_dependents();
+    const uint32_t chain = blockIdx.z;
+    const ChainDev cd = chains[chain];
+    if (COUNT && threadIdx.x == 0) s_cnt = 0;
+    const int kc = build_interleaved(s_n16_tab, thr_all + (size_t)chain * kThrStride, max_thr);
+    const uint32_t c_off = (uint32_t)((kc - 24576) & 0xffff) * 0x10001u, c_max = (uint32_t)(2 * kc) * 0x10001u;
+    pdl_wait();  // from here on the predecessor has completed
+    if (ctr) sweep += *ctr;
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t half = lane >> 4, l16 = lane & 15u;
+    uint32_t chunk = blockIdx.x, group = blockIdx.y, chunks_here = n_chunks;
+    bool boundary_block = false;
+    if (HALO) {
+        // plane group 0 — rotated to {Tl-8 .. Tl-1, 0 .. 7}, i.e. both boundary planes and the planes that
+        // read the ghosts — comes first in block order and in short chunks (see k_sweep_stream)
+        if (chunk < n_bchunks) {
+            group = 0;
+            chunks_here = n_bchunks;
+            boundary_block = true;
+        } else {
+            chunk -= n_bchunks;
+            group = 1u + chunk / n_chunks;
+            chunk %= n_chunks;
+        }
+    }
+    uint32_t pl0 = group * (2u * kN16Warps) + 2u * warp;  // lower plane of this warp's pair
+    const bool pair_ok = pl0 < g.Tl;                      // Tl is even
+    if (HALO) pl0 = (pl0 + g.Tl - (uint32_t)kN16Warps % g.Tl) % g.Tl;
+    const uint32_t y0 = (uint32_t)(((uint64_t)chunk * g.Y) / chunks_here);
+    const uint32_t y1 = (uint32_t)(((uint64_t)(chunk + 1u) * g.Y) / chunks_here);
+    int accepted = 0;
+    if (pair_ok && y0 < y1) {  // warp uniform
+        const uint32_t tl = pl0 + half, tg = g.t0 + tl;
+        const size_t cbase = (size_t)chain * g.chain_stride;
+        const uint32_t planeq = g.Y * kN16RowQ;
+        // offsets in uint4 units from the chain's array base
+        const uint32_t b_own = plane_self(g, tl) * planeq + l16;
+        const uint32_t b_out = (half ? plane_above(g, tl) : plane_below(g, tl)) * planeq + l16;
+        uint4* const q_own = reinterpret_cast<uint4*>(own_base + cbase);
+        const uint4* const q_oth = reinterpret_cast<const uint4*>(oth_base + cbase);
+        bool push = false;
+        if (HALO && halo.enabled) {
+            if (pl0 == 0u && lane == 0u) halo_wait(&halo.mine->from_lo, halo.wait_for, &halo.mine->error);
+            if (pl0 + 2u == g.Tl && lane == 0u) halo_wait(&halo.mine->from_hi, halo.wait_for, &halo.mine->error);
+            const uint4* peer = nullptr;
+            if (tl == 0u) peer = reinterpret_cast<const uint4*>(halo.lo_ghost + cbase) + l16;
+            else if (tl + 1u == g.Tl) peer = reinterpret_cast<const uint4*>(halo.hi_ghost + cbase) + l16;
+            push = peer != nullptr;
+            // lanes of a half differ only by l16 on both sides: one byte offset per half-warp, kept in shared memory
+            if (push && l16 == 0u)
+                s_delta[warp][half] = reinterpret_cast<const char*>(peer) - reinterpret_cast<const char*>(q_own + b_own);
+            __syncwarp();
+        }
+        const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
+        uint32_t y = y0 + half;
+        if (y == g.Y) y = 0;  // this lane's first row
+        const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
+        uint4 wa = __ldg(q_oth + (b_own + ym * kN16RowQ)), wb = __ldg(q_oth + (b_own + y * kN16RowQ)), wc;
+        uint32_t p = (y0 + g.t0 + pl0 + (uint32_t)colour) & 1u;  // x parity of the lower half's row == the upper half's
+        const uint32_t src_r = (lane & 16u) | ((lane + 1u) & 15u), src_l = (lane & 16u) | ((lane - 1u) & 15u);
+        const uint32_t grp_base = tg * g.Y * 32u + l16 * 2u;  // Philox counter word 0 of this thread's first group at y = 0
+        const bool wil_plane = WILSON && tg < cd.wil_h;
+        const uint32_t y_one = 1u % g.Y;
+        uint32_t n = y1 - y0;
+#define LQFT_N16_STEP(OM, OC, ON)                                                                                        \
+    {                                                                                                                    \
+        const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;                                                                  \
+        uint4* const po = q_own + (b_own + y * kN16RowQ);                                                                \
+        const uint4 v = *po;                                                                                             \
+        ON = __ldg(q_oth + (b_own + yn * kN16RowQ));                                                                     \
+        const uint4 to = __ldg(q_oth + (b_out + y * kN16RowQ));                                                          \
+        /* lower half (plane t, row y) needs plane t+1 row y = partner's OM; upper (t+1, y+1) needs plane t row y+1 = partner's ON */ \
+        const uint4 snd = half ? OM : ON;                                                                                \
+        uint4 ti;                                                                                                        \
+        ti.x = __shfl_xor_sync(0xffffffffu, snd.x, 16); ti.y = __shfl_xor_sync(0xffffffffu, snd.y, 16);                  \
+        ti.z = __shfl_xor_sync(0xffffffffu, snd.z, 16); ti.w = __shfl_xor_sync(0xffffffffu, snd.w, 16);                  \
+        const uint32_t grp = grp_base + y * 32u;                                                                         \
+        const u32x4 r0 = philox4x32_rk(grp, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);             \
+        const u32x4 r1 = philox4x32_rk(grp + 1u, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);        \
+        uint4 woff = make_uint4(0, 0, 0, 0);                                                                             \
+        if (WILSON) {                                                                                                    \
+            if (wil_plane && (y == 0u || y == y_one))                                                                    \
+                woff = n16_wilson(8u * l16, p, (y == 0u ? 1 : 0) - (y == y_one ? 1 : 0), cd.wil_w);                      \
+        }                                                                                                                \
+        uint4 w;                                                                                                         \
+        if (p) {                                                                                                         \
+            const uint32_t edge = __shfl_sync(0xffffffffu, OC.x, src_r);                                                 \
+            w = n16_row_update<1, WILSON, COUNT>(v, OM, OC, ON, to, ti, edge, r0, r1, c_off, c_max, woff, accepted);     \
+        } else {                                                                                                         \
+            const uint32_t edge = __shfl_sync(0xffffffffu, OC.w, src_l);                                                 \
+            w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, to, ti, edge, r0, r1, c_off, c_max, woff, accepted);     \
+        }                                                                                                                \
+        *po = w;                                                                                                         \
+        if (HALO) {                                                                                                      \
+            if (push) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(po) + s_delta[warp][half]) = w;                  \
+        }                                                                                                                \
+        y = yn;                                                                                                          \
+        p ^= 1u;                                                                                                         \
+    }
+        // the three-row register window rotates through the names instead of being copied
+        for (;;) {
+            LQFT_N16_STEP(wa, wb, wc)
+            if (--n == 0) break;
+            LQFT_N16_STEP(wb, wc, wa)
+            if (--n == 0) break;
+            LQFT_N16_STEP(wc, wa, wb)
+            if (--n == 0) break;
+        }
+#undef LQFT_N16_STEP
+    }
+    if (COUNT)
+        block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
+    if (HALO && halo.enabled) {
+        // the last boundary block to finish publishes this launch's phase (release chain: k_sweep_stream)
+        __syncthreads();
+        if (boundary_block && threadIdx.x == 0) {
+            const unsigned int done = atom_add_acq_rel_gpu(&halo.mine->ticket, 1u);
+            if (done + 1u == halo.n_boundary_blocks) {
+                st_relaxed_gpu(&halo.mine->ticket, 0u);
+                st_release_sys(&halo.lo_sync->from_hi, halo.phase);
+                st_release_sys(&halo.hi_sync->from_lo, halo.phase);
+            }
+        }
+    }
+}
+
+// ---- i32 <-> narrow ---------------------------------------------------------------------------------------
+// Whole allocation of one colour (owned and ghost planes), 4 heights per thread.  grid = (ceil(stride/4/bd), n_chains).
+// worst = max |height - centre| over everything converted.
+__global__ void __launch_bounds__(256)
+k_narrow(const int32_t* __restrict__ f, uint16_t* __restrict__ n, uint64_t chain_stride, const int32_t* __restrict__ centre,
+         uint32_t* __restrict__ worst) {
+    const uint32_t chain = blockIdx.y;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t far = 0;
+    if (i < chain_stride / 4) {
+        const int c = centre[chain];
+        const int4 v = reinterpret_cast<const int4*>(f + (size_t)chain * chain_stride)[i];
+        // wide arithmetic: an uploaded field may hold any i32
+        const long long dx = (long long)v.x - c, dy = (long long)v.y - c, dz = (long long)v.z - c, dw = (long long)v.w - c;
+        const long long m = max(max(llabs(dx), llabs(dy)), max(llabs(dz), llabs(dw)));
+        far = (uint32_t)min(m, (long long)(1 << 24));  // capped: the word is summed over ranks
+        uint2 o;
+        o.x = ((uint32_t)(dx + kN16Bias) & 0xffffu) | ((uint32_t)(dy + kN16Bias) << 16);
+        o.y = ((uint32_t)(dz + kN16Bias) & 0xffffu) | ((uint32_t)(dw + kN16Bias) << 16);
+        reinterpret_cast<uint2*>(n + (size_t)chain * chain_stride)[i] = o;
+    }
+    far = __reduce_max_sync(0xffffffffu, far);
+    if ((threadIdx.x & 31u) == 0u && far > (uint32_t)kN16Guard) atomicMax(worst, far);
+}
+
+__global__ void __launch_bounds__(256)
+k_widen(const uint16_t* __restrict__ n, int32_t* __restrict__ f, uint64_t chain_stride, const int32_t* __restrict__ centre) {
+    const uint32_t chain = blockIdx.y;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= chain_stride / 4) return;
+    const int c = centre[chain] - kN16Bias;
+    const uint2 v = reinterpret_cast<const uint2*>(n + (size_t)chain * chain_stride)[i];
+    reinterpret_cast<int4*>(f + (size_t)chain * chain_stride)[i] =
+        make_int4((int)(v.x & 0xffffu) + c, (int)(v.x >> 16) + c, (int)(v.y & 0xffffu) + c, (int)(v.y >> 16) + c);
+}
+
+// centre[chain] := offset[chain] (the chain's pending normalisation shift: identical on every rank, and the
+// stored height of a site of the field whenever a normalize has run); *worst := 0.
+__global__ void k_narrow_begin(const int32_t* __restrict__ offset, int32_t* __restrict__ centre, uint32_t n_chains,
+                               uint32_t* __restrict__ worst) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_chains) centre[c] = offset[c];
+    if (c == 0) *worst = 0;
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+struct NarrowPlan {
+    bool enabled = false;
+    int blocks_per_sm = 0, blocks_per_sm_halo = 0;
+    int sm_count = 0;
+};
+
+struct NarrowArgs {
+    Geom g;
+    int colour;
+    uint64_t sweep;
+    const uint64_t* ctr;
+    uint32_t n_chains;
+    uint16_t* own;
+    const uint16_t* oth;
+    const ChainDev* chains;
+    const uint32_t* thr;
+    unsigned long long* acc;
+    uint32_t max_thr;
+    bool wilson, count;
+    cudaStream_t stream;
+    bool pdl;
+    NarrowHalo halo;
+};
+
+inline bool narrow_geometry_ok(const Geom& g, uint32_t max_thr) {
+    return g.X == 256 && g.Tl >= 2 && g.Tl % 2 == 0 && max_thr <= (uint32_t)kN16KcMax + 1 &&
+           (uint64_t)g.plane / 8 * (g.Tl + 2 * g.ghost) < (1ull << 32) && (uint64_t)g.T * g.Y * 32u < (1ull << 32);
+}
+
+inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, int sm_count, uint32_t max_thr, bool force_off) {
+    p.enabled = false;
+    if (force_off || !narrow_geometry_ok(g, max_thr)) return cudaSuccess;
+    p.sm_count = sm_count;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<false, false, false>, kN16Threads, 0);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm_halo, k_sweep_n16<false, false, true>, kN16Threads, 0);
+    if (e != cudaSuccess) return e;
+    p.enabled = p.blocks_per_sm > 0 && p.blocks_per_sm_halo > 0;
+    return cudaSuccess;
+}
+
+// y chunks per plane group: one wave if possible, chunks as short as that allows (cost model of stream_chunks;
+// the per-chunk prologue is worth about two rows here).
+inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_chains, bool halo) {
+    const uint64_t slots = (uint64_t)p.sm_count * (halo ? p.blocks_per_sm_halo : p.blocks_per_sm);
+    const uint64_t base = (uint64_t)((g.Tl + 2 * kN16Warps - 1) / (2 * kN16Warps)) * n_chains;
+    const uint32_t max_chunks = g.Y / 2 ? g.Y / 2 : 1;
+    uint32_t best = 1;
+    double best_cost = 1e300;
+    for (uint32_t nc = 1; nc <= max_chunks; ++nc) {
+        const uint64_t blocks = base * nc;
+        const uint64_t waves = (blocks + slots - 1) / slots;
+        const double rows = (double)((g.Y + nc - 1) / nc);
+        const double cost = (double)waves * (rows + 2.0);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = nc;
+        }
+    }
+    return best;
+}
+
+inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
+    const uint32_t n_groups = (a.g.Tl + 2 * kN16Warps - 1) / (2 * kN16Warps);
+    const uint32_t n_chunks = narrow_chunks(p, a.g, a.n_chains, a.halo.enabled != 0);
+    dim3 grid(n_chunks, n_groups, a.n_chains);
+    NarrowHalo halo = a.halo;
+    uint32_t n_bchunks = 0;
+    if (halo.enabled) {
+        constexpr uint32_t factor = 4;
+        const uint32_t max_chunks = a.g.Y / 2 ? a.g.Y / 2 : 1;
+        n_bchunks = factor * n_chunks < max_chunks ? factor * n_chunks : max_chunks;
+        grid = dim3(n_bchunks + (n_groups - 1) * n_chunks, 1, a.n_chains);
+        halo.n_boundary_blocks = n_bchunks * a.n_chains;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kN16Threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = a.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = a.pdl ? 1 : 0;
+#define LQFT_GO(W, C, H)                                                                                             \
+    return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C, H>, a.g, a.colour, a.sweep, a.ctr, n_chunks, n_bchunks, a.own, \
+                              a.oth, a.chains, a.thr, a.acc, a.max_thr, halo)
+    if (halo.enabled) {
+        if (a.wilson) {
+            if (a.count) LQFT_GO(true, true, true); else LQFT_GO(true, false, true);
+        } else {
+            if (a.count) LQFT_GO(false, true, true); else LQFT_GO(false, false, true);
+        }
+    }
+    if (a.wilson) {
+        if (a.count) LQFT_GO(true, true, false); else LQFT_GO(true, false, false);
+    } else {
+        if (a.count) LQFT_GO(false, true, false); else LQFT_GO(false, false, false);
+    }
+#undef LQFT_GO
+    return cudaGetLastError();
+}
+
+}  // namespace lqft

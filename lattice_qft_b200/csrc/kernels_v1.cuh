@@ -251,12 +251,14 @@ __global__ void k_init_hot(Geom g, int32_t* __restrict__ c0_base, int32_t* __res
 // and normalize_random (subtract the TRUE height of the picked site) simply sets offset := stored[site].
 // The offset is applied where absolute heights leave the device (k_merge, lqft_slice_moments).
 // Step 1: one thread per chain reads the stored height of the picked site (0 if another rank owns it).
-__global__ void k_pick_shift(Geom g, const int32_t* __restrict__ c0_base,
-                             const int32_t* __restrict__ c1_base,
+// H = uint16_t reads the narrow working copy: stored = biased - bias + centre[chain] (`rebase` = centre, bias).
+template <typename H>
+__global__ void k_pick_shift(Geom g, const H* __restrict__ c0_base,
+                             const H* __restrict__ c1_base,
                              const ChainDev* __restrict__ chains, uint32_t n_chains,
                              uint64_t counter, const uint64_t* __restrict__ ctr,
                              int64_t explicit_site, int32_t only_chain,
-                             int32_t* __restrict__ shift) {
+                             int32_t* __restrict__ shift, const int32_t* __restrict__ centre = nullptr, int32_t bias = 0) {
     const uint32_t chain = blockIdx.x * blockDim.x + threadIdx.x;
     if (chain >= n_chains) return;
     if (only_chain >= 0 && (int32_t)chain != only_chain) {
@@ -276,8 +278,9 @@ __global__ void k_pick_shift(Geom g, const int32_t* __restrict__ c0_base,
         const uint32_t y = i / g.Xh;
         const uint32_t x = 2 * (i - y * g.Xh) + (uint32_t)(site & 1u);
         const uint32_t col = (x + y + tg) & 1u;
-        const int32_t* f = (col ? c1_base : c0_base) + (size_t)chain * g.chain_stride;
-        s = f[(size_t)plane_self(g, tg - g.t0) * g.plane + i];
+        const H* f = (col ? c1_base : c0_base) + (size_t)chain * g.chain_stride;
+        s = (int32_t)f[(size_t)plane_self(g, tg - g.t0) * g.plane + i];
+        if (centre) s += centre[chain] - bias;
     }
     shift[chain] = s;
 }
@@ -364,8 +367,17 @@ k_observe(Geom g, const int32_t* __restrict__ c0_base, const int32_t* __restrict
 // Vectorised form of k_observe for X % 8 == 0: one thread per quad position owns four colour-0 and four
 // colour-1 sites (6 LDG.128 + 1 LDG for 8 sites).  Same exact int64 sums.
 // grid = (ceil(plane/4/bd), Tl, n_chains)
+// H = int32_t, or uint16_t for the narrow working copy (kernels_narrow.cuh): the bias cancels in every
+// difference, so the energy sums are the same; slice moments need true heights and are i32 only.
+__device__ __forceinline__ int4 load_h4(const int32_t* p) { return *reinterpret_cast<const int4*>(p); }
+__device__ __forceinline__ int4 load_h4(const uint16_t* p) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    return make_int4((int)(v.x & 0xffffu), (int)(v.x >> 16), (int)(v.y & 0xffffu), (int)(v.y >> 16));
+}
+
+template <typename H>
 __global__ void __launch_bounds__(256)
-k_observe_vec4(Geom g, const int32_t* __restrict__ c0_base, const int32_t* __restrict__ c1_base,
+k_observe_vec4(Geom g, const H* __restrict__ c0_base, const H* __restrict__ c1_base,
                unsigned long long* __restrict__ obs, unsigned long long* __restrict__ mom) {
     const uint32_t chain = blockIdx.z, tl = blockIdx.y;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,8 +385,8 @@ k_observe_vec4(Geom g, const int32_t* __restrict__ c0_base, const int32_t* __res
     const uint32_t tg = g.t0 + tl;
     const uint32_t Qx = g.Xh >> 2;
     if (i < (g.plane >> 2)) {
-        const int32_t* c0 = c0_base + (size_t)chain * g.chain_stride;
-        const int32_t* c1 = c1_base + (size_t)chain * g.chain_stride;
+        const H* c0 = c0_base + (size_t)chain * g.chain_stride;
+        const H* c1 = c1_base + (size_t)chain * g.chain_stride;
         const uint32_t y = i / Qx, k0 = (i - y * Qx) << 2;
         const uint32_t p0 = (y + tg) & 1u;  // x parity of the colour-0 sites of this row
         const size_t ps = (size_t)plane_self(g, tl) * g.plane;
@@ -383,12 +395,12 @@ k_observe_vec4(Geom g, const int32_t* __restrict__ c0_base, const int32_t* __res
         const uint32_t kn = (k0 + 4 == g.Xh) ? 0 : k0 + 4;
         const size_t up = (size_t)plane_above(g, tl) * g.plane + (size_t)y * g.Xh + k0;
         const size_t yr = ps + (size_t)yp * g.Xh + k0;
-        const int4 a = *reinterpret_cast<const int4*>(c0 + row + k0);
-        const int4 b = *reinterpret_cast<const int4*>(c1 + row + k0);
-        const int4 ay = *reinterpret_cast<const int4*>(c1 + yr), by = *reinterpret_cast<const int4*>(c0 + yr);
-        const int4 at = *reinterpret_cast<const int4*>(c1 + up), bt = *reinterpret_cast<const int4*>(c0 + up);
+        const int4 a = load_h4(c0 + row + k0);
+        const int4 b = load_h4(c1 + row + k0);
+        const int4 ay = load_h4(c1 + yr), by = load_h4(c0 + yr);
+        const int4 at = load_h4(c1 + up), bt = load_h4(c0 + up);
         // +x neighbour: the odd-x colour looks one position to the right in the other colour's row
-        const int e = (p0 ? c1 : c0)[row + kn];
+        const int e = (int)(p0 ? c1 : c0)[row + kn];
         const int4 ax = p0 ? make_int4(b.y, b.z, b.w, e) : b;
         const int4 bx = p0 ? a : make_int4(a.y, a.z, a.w, e);
         auto sq = [](int u, int v) { const long long d = (long long)u - (long long)v; return d * d; };

@@ -20,6 +20,7 @@
 #include "kernels_f64.cuh"
 #include "kernels_resident.cuh"
 #include "kernels_stream.cuh"
+#include "kernels_narrow.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_v1.cuh"
 #include "spec.cuh"
@@ -110,12 +111,13 @@ static lqft_status nccl_load() {
 // ---------------------------------------------------------------------------------------------
 struct GraphKey {
     uint32_t energy_every, normalize_every, cycle;
-    bool count;
+    bool count, narrow;
     bool operator<(const GraphKey& o) const {
         if (energy_every != o.energy_every) return energy_every < o.energy_every;
         if (normalize_every != o.normalize_every) return normalize_every < o.normalize_every;
         if (cycle != o.cycle) return cycle < o.cycle;
-        return count < o.count;
+        if (count != o.count) return count < o.count;
+        return narrow < o.narrow;
     }
 };
 struct GraphVal {
@@ -179,10 +181,18 @@ struct lqft_handle {
     // peer-memory halo (world_size > 1)
     bool p2p = false;
     HaloSync* halo_d = nullptr;                 // mine
-    void* peer_base[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [lo/hi][field0, field1, sync]
+    void* peer_base[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr},
+                             {nullptr, nullptr, nullptr, nullptr, nullptr}};  // [lo/hi][field0, field1, sync, narrow0, narrow1]
     bool peer_same = false;                     // lo and hi are the same rank (world_size == 2)
     bool self_halo = false;                     // LQFT_FLAG_SELF_HALO: this rank is its own neighbour
     unsigned long long phase = 0;               // operations that touch ghost planes so far (same on every rank)
+    // 16-bit working copy of the field (kernels_narrow.cuh): live only inside lqft_run / lqft_sweep
+    uint16_t* narrow[2] = {nullptr, nullptr};
+    int32_t* ncentre_d = nullptr;               // [n_chains] centre of the bias while a narrow segment runs
+    uint32_t* nworst_d = nullptr;               // validity word of k_narrow
+    NarrowPlan narrowp{};
+    bool narrow_active = false;
+    uint64_t narrow_segments = 0;
 };
 
 static lqft_status use_device(lqft_handle* h) {
@@ -227,11 +237,13 @@ static lqft_status upload_params(lqft_handle* h) {
         CU(cudaFuncSetAttribute(k_run_resident<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU(cudaFuncSetAttribute(k_run_resident<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
+    CU(narrow_prepare(h->narrowp, h->g, h->sm_count, h->max_thr,
+                      !h->narrow[0] || h->resident_ok || !h->streamp.enabled || (h->g.ghost != 0 && !h->p2p)));
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
     if (getenv("LQFT_DEBUG"))
         fprintf(stderr, "[lqft] %ux%ux%u chains=%u path=%s (stream: segs=%d blocks/SM=%d chunks=%u; march: g=%d rows=%d)\n",
-                h->g.X, h->g.Y, h->g.T, nc, h->streamp.enabled ? "stream" : (h->tiled.enabled ? "march" : "v1"),
+                h->g.X, h->g.Y, h->g.T, nc, h->narrowp.enabled ? "narrow+stream" : h->streamp.enabled ? "stream" : (h->tiled.enabled ? "march" : "v1"),
                 h->streamp.segs, h->streamp.blocks_per_sm,
                 h->streamp.enabled ? stream_chunks(h->streamp, h->g, h->g.Tl, nc) : 0u, h->tiled.g, h->tiled.march);
     return LQFT_OK;
@@ -349,12 +361,15 @@ extern "C" lqft_status lqft_comm_unique_id(uint8_t id[128]) {
 static lqft_status setup_p2p(lqft_handle* h) {
     h->p2p = false;
     const int ws = (int)h->cfg.world_size, r = (int)h->cfg.rank;
-    struct Handles { cudaIpcMemHandle_t f0, f1, sync; };
+    struct Handles { cudaIpcMemHandle_t f0, f1, sync, n0, n1; int has_narrow; };
     Handles mine{};
     bool ok = cudaIpcGetMemHandle(&mine.f0, h->field[0]) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.f1, h->field[1]) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.sync, h->halo_d) == cudaSuccess;
     if (!ok) cudaGetLastError();
+    mine.has_narrow = h->narrow[0] && cudaIpcGetMemHandle(&mine.n0, h->narrow[0]) == cudaSuccess &&
+                      cudaIpcGetMemHandle(&mine.n1, h->narrow[1]) == cudaSuccess;
+    if (h->narrow[0] && !mine.has_narrow) cudaGetLastError();
     // every rank takes part in the exchange (and in the vote below) even if its own export failed
     Handles* all_d = nullptr;
     CU(cudaMalloc(&all_d, sizeof(Handles) * ws));
@@ -366,19 +381,21 @@ static lqft_status setup_p2p(lqft_handle* h) {
     cudaFree(all_d);
     const int lo = (r + ws - 1) % ws, hi = (r + 1) % ws;
     h->peer_same = lo == hi;
+    bool narrow_ok = true;  // the narrow working copy needs every rank to have one (slabs may differ in shape)
+    for (int k = 0; k < ws; ++k) narrow_ok = narrow_ok && all[k].has_narrow;
     if (ok && !(h->cfg.flags & LQFT_FLAG_HALO_NCCL)) {
         for (int side = 0; side < 2 && ok; ++side) {
             if (side == 1 && h->peer_same) {
-                for (int k = 0; k < 3; ++k) h->peer_base[1][k] = h->peer_base[0][k];
+                for (int k = 0; k < 5; ++k) h->peer_base[1][k] = h->peer_base[0][k];
                 break;
             }
             const Handles& ph = all[side == 0 ? lo : hi];
-            const cudaIpcMemHandle_t* hs[3] = {&ph.f0, &ph.f1, &ph.sync};
-            for (int k = 0; k < 3 && ok; ++k)
+            const cudaIpcMemHandle_t* hs[5] = {&ph.f0, &ph.f1, &ph.sync, &ph.n0, &ph.n1};
+            for (int k = 0; k < (narrow_ok ? 5 : 3) && ok; ++k)
                 if (cudaIpcOpenMemHandle(&h->peer_base[side][k], *hs[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                     cudaGetLastError();
                     h->peer_base[side][k] = nullptr;
-                    ok = false;
+                    if (k < 3) ok = false; else narrow_ok = false;
                 }
         }
     } else {
@@ -386,15 +403,20 @@ static lqft_status setup_p2p(lqft_handle* h) {
     }
     // all ranks must agree, or one side would wait for flags the other never writes
     int* vote_d = nullptr;
-    CU(cudaMalloc(&vote_d, sizeof(int)));
-    const int v = ok ? 0 : 1;
-    CU(cudaMemcpyAsync(vote_d, &v, sizeof v, cudaMemcpyHostToDevice, h->stream));
-    NC(g_nccl.AllReduce(vote_d, vote_d, 1, ncclInt32, ncclSum, h->comm, h->stream));
-    int bad = 0;
-    CU(cudaMemcpyAsync(&bad, vote_d, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMalloc(&vote_d, 2 * sizeof(int)));
+    const int v[2] = {ok ? 0 : 1, narrow_ok ? 0 : 1};
+    CU(cudaMemcpyAsync(vote_d, v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllReduce(vote_d, vote_d, 2, ncclInt32, ncclSum, h->comm, h->stream));
+    int bad[2] = {0, 0};
+    CU(cudaMemcpyAsync(bad, vote_d, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(vote_d);
-    h->p2p = bad == 0;
+    h->p2p = bad[0] == 0;
+    if (!h->p2p || bad[1] != 0) {  // no narrow copy without the peer-memory halo
+        cudaFree(h->narrow[0]);
+        cudaFree(h->narrow[1]);
+        h->narrow[0] = h->narrow[1] = nullptr;
+    }
     if (getenv("LQFT_DEBUG")) fprintf(stderr, "[lqft] rank %d/%d halo: %s\n", r, ws, h->p2p ? "peer memory (IPC)" : "NCCL send/recv");
     return LQFT_OK;
 }
@@ -441,10 +463,11 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int side = 0; side < 2 && !h->self_halo; ++side) {
         if (side == 1 && h->peer_same) break;
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 5; ++k)
             if (h->peer_base[side][k]) cudaIpcCloseMemHandle(h->peer_base[side][k]);
     }
     cudaFree(h->halo_d);
+    cudaFree(h->narrow[0]); cudaFree(h->narrow[1]); cudaFree(h->ncentre_d); cudaFree(h->nworst_d);
     tiled_release(h->tiled);
     cudaFree(h->field[0]); cudaFree(h->field[1]);
     cudaFree(h->field64[0]); cudaFree(h->field64[1]); cudaFree(h->beta_d); cudaFree(h->offset64_d);
@@ -557,6 +580,20 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     h->diff_comp.assign(nc, nullptr);
     h->diff_count.assign(nc, 0);
 
+    const uint32_t no_narrow = LQFT_FLAG_NO_NARROW | LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_STREAM |
+                               LQFT_FLAG_HALO_NCCL;
+    if (!h->is64 && !(cfg->flags & no_narrow) && narrow_geometry_ok(g, 2)) {
+        // 16-bit working copy (+50 % field memory); without it the i32 kernels do all the work
+        const size_t nbytes = sizeof(uint16_t) * g.chain_stride * nc;
+        if (cudaMalloc(&h->narrow[0], nbytes) != cudaSuccess || cudaMalloc(&h->narrow[1], nbytes) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(h->narrow[0]);
+            h->narrow[0] = h->narrow[1] = nullptr;
+        } else {
+            CU(cudaMalloc(&h->ncentre_d, sizeof(int32_t) * nc));
+            CU(cudaMalloc(&h->nworst_d, sizeof(uint32_t)));
+        }
+    }
     if (ws > 1) {
         ST(nccl_load());
         ncclUniqueId id;
@@ -574,6 +611,8 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
             h->peer_base[side][0] = h->field[0];
             h->peer_base[side][1] = h->field[1];
             h->peer_base[side][2] = h->halo_d;
+            h->peer_base[side][3] = h->narrow[0];
+            h->peer_base[side][4] = h->narrow[1];
         }
         h->self_halo = true;
         h->p2p = true;
@@ -701,6 +740,23 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
         h->launches += 1;
         return LQFT_OK;
     }
+    if (h->narrow_active) {  // whole-slab launches only (ghost == 0, or the peer-memory halo)
+        NarrowArgs a{g, colour, sweep, ctr, h->cfg.n_chains, h->narrow[colour], h->narrow[colour ^ 1], h->chains_d, h->thr_d,
+                     h->acc_d, h->max_thr, h->any_wilson, h->count_accepts, s, !(h->cfg.flags & LQFT_FLAG_NO_PDL), NarrowHalo{}};
+        if (halo_now) {
+            a.halo.lo_ghost = (uint16_t*)h->peer_base[0][3 + colour] + (size_t)(g.Tl + 1) * g.plane;
+            a.halo.hi_ghost = (uint16_t*)h->peer_base[1][3 + colour];
+            a.halo.lo_sync = (HaloSync*)h->peer_base[0][2];
+            a.halo.hi_sync = (HaloSync*)h->peer_base[1][2];
+            a.halo.mine = h->halo_d;
+            a.halo.wait_for = h->phase;
+            a.halo.phase = ++h->phase;
+            a.halo.enabled = 1;
+        }
+        CU(narrow_half(h->narrowp, a));
+        h->launches += 1;
+        return LQFT_OK;
+    }
     int32_t* own = h->field[colour];
     const int32_t* oth = h->field[colour ^ 1];
     if (h->streamp.enabled || h->tiled.enabled) {
@@ -788,7 +844,14 @@ static lqft_status launch_observe(lqft_handle* h, bool moments) {
         const uint32_t units = g.plane / 4;
         const uint32_t bd = block_for(units);
         dim3 grid((units + bd - 1) / bd, g.Tl, h->cfg.n_chains);
-        k_observe_vec4<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->obs_d, moments ? h->mom_d : nullptr);
+        if (h->narrow_active) {
+            if (moments) return fail(LQFT_ERR_STATE, "slice moments are not available on the narrow working copy");
+            k_observe_vec4<<<grid, bd, 0, h->stream>>>(g, (const uint16_t*)h->narrow[0], (const uint16_t*)h->narrow[1], h->obs_d,
+                                                      (unsigned long long*)nullptr);
+        } else {
+            k_observe_vec4<<<grid, bd, 0, h->stream>>>(g, (const int32_t*)h->field[0], (const int32_t*)h->field[1], h->obs_d,
+                                                      moments ? h->mom_d : nullptr);
+        }
     } else {
         const uint32_t bd = block_for(g.plane);
         dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
@@ -813,8 +876,13 @@ static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint
         h->launches += 1;
         return LQFT_OK;
     }
-    k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d, nc,
-                                                         counter, ctr, explicit_site, only_chain, h->shift_d);
+    if (h->narrow_active)
+        k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(g, (const uint16_t*)h->narrow[0], (const uint16_t*)h->narrow[1],
+                                                             h->chains_d, nc, counter, ctr, explicit_site, only_chain, h->shift_d,
+                                                             (const int32_t*)h->ncentre_d, (int32_t)kN16Bias);
+    else
+        k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(g, (const int32_t*)h->field[0], (const int32_t*)h->field[1],
+                                                             h->chains_d, nc, counter, ctr, explicit_site, only_chain, h->shift_d);
     CU(cudaGetLastError());
     ST(allreduce_i32(h, h->shift_d, nc));
     k_set_offset<<<(nc + 127) / 128, 128, 0, h->stream>>>(h->shift_d, h->offset_d, nc, only_chain);
@@ -1203,6 +1271,46 @@ extern "C" lqft_status lqft_difference_read(lqft_handle* h, uint32_t chain, doub
 }
 
 // ---------------------------------------------------------------------------------------------
+// narrow working copy (kernels_narrow.cuh)
+// ---------------------------------------------------------------------------------------------
+// i32 field -> u16 copy biased around each chain's normalisation offset; *ok = every height of every rank lies
+// within kN16Guard of its centre.  A ghost operation: the neighbours push into the narrow ghost planes next.
+static lqft_status narrow_enter(lqft_handle* h, bool* ok) {
+    const Geom& g = h->g;
+    const uint32_t nc = h->cfg.n_chains;
+    *ok = false;
+    ST(ghost_op_begin(h));
+    k_narrow_begin<<<(nc + 127) / 128, 128, 0, h->stream>>>(h->offset_d, h->ncentre_d, nc, h->nworst_d);
+    dim3 grid((uint32_t)((g.chain_stride / 4 + 255) / 256), nc);
+    for (int c = 0; c < 2; ++c)
+        k_narrow<<<grid, 256, 0, h->stream>>>(h->field[c], h->narrow[c], g.chain_stride, h->ncentre_d, h->nworst_d);
+    CU(cudaGetLastError());
+    h->launches += 3;
+    ST(ghost_op_end(h));
+    ST(allreduce_i32(h, h->nworst_d, 1));  // k_narrow caps the word at 2^24: the sum over ranks cannot wrap
+    uint32_t worst = 0;
+    CU(cudaMemcpyAsync(&worst, h->nworst_d, sizeof worst, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *ok = worst == 0;
+    h->narrow_active = *ok;
+    if (*ok) h->narrow_segments += 1;
+    return LQFT_OK;
+}
+
+static lqft_status narrow_exit(lqft_handle* h) {
+    const Geom& g = h->g;
+    ST(ghost_op_begin(h));  // the neighbours' last pushes into the narrow ghost planes have landed
+    dim3 grid((uint32_t)((g.chain_stride / 4 + 255) / 256), h->cfg.n_chains);
+    for (int c = 0; c < 2; ++c)
+        k_widen<<<grid, 256, 0, h->stream>>>(h->narrow[c], h->field[c], g.chain_stride, h->ncentre_d);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    h->narrow_active = false;
+    ST(ghost_op_end(h));
+    return LQFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // fused schedule (computation.rs:229-270, 313-340)
 // ---------------------------------------------------------------------------------------------
 static lqft_status launch_energy_log(lqft_handle* h) {
@@ -1294,55 +1402,69 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
         h->launches += 1;
         step = end;
     }
-    if (use_graph && step < end) {
-        while (step < end && step % cycle != 0) {
+    // Steps left for the update kernels.  With a narrow plan they run in segments of at most kN16Segment sweeps
+    // on the 16-bit working copy, each entered only if the field is within the guard band (else this call
+    // finishes on the i32 kernels).
+    bool narrow = h->narrowp.enabled && end - step >= 4;
+    while (step < end) {
+        uint64_t seg_end = end;
+        if (narrow) {
+            bool ok = false;
+            ST(narrow_enter(h, &ok));
+            if (ok) seg_end = std::min<uint64_t>(end, step + kN16Segment);
+            else narrow = false;
+        }
+        if (use_graph && step < seg_end) {
+            while (step < seg_end && step % cycle != 0) {
+                ST(launch_step(h, s, step, step, nullptr));
+                ++step;
+            }
+            const uint64_t avail = (seg_end - step) / cycle;
+            const uint64_t reps = std::max<uint64_t>(1, std::min<uint64_t>(avail, std::max<uint64_t>(1, kGraphSteps / cycle)));
+            const uint64_t period = reps * cycle;
+            const uint64_t n_periods = (seg_end - step) / period;
+            if (n_periods) {
+                GraphKey key{s->energy_every, s->normalize_every, (uint32_t)period, h->count_accepts, h->narrow_active};
+                auto it = h->graphs.find(key);
+                if (it == h->graphs.end()) {
+                    // capture one period; every kernel reads the sweep counter from device memory
+                    const uint64_t before = h->launches;
+                    lqft_schedule rel = *s;
+                    rel.sweep_base = 0;
+                    cudaGraph_t graph = nullptr;
+                    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                    lqft_status st = LQFT_OK;
+                    for (uint64_t i = 0; i < period && st == LQFT_OK; ++i) st = launch_step(h, &rel, i, i, h->sweep_ctr_d);
+                    if (st == LQFT_OK) {
+                        k_tick<<<1, 1, 0, h->stream>>>(h->sweep_ctr_d, period);
+                        h->launches += 1;
+                    }
+                    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                    if (st != LQFT_OK) {
+                        if (graph) cudaGraphDestroy(graph);
+                        return st;
+                    }
+                    if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+                    GraphVal val;
+                    val.kernels = h->launches - before;
+                    h->launches = before;
+                    ce = cudaGraphInstantiate(&val.exec, graph, 0);
+                    cudaGraphDestroy(graph);
+                    if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+                    it = h->graphs.emplace(key, val).first;
+                }
+                const uint64_t base = s->sweep_base + step;
+                CU(cudaMemcpyAsync(h->sweep_ctr_d, &base, sizeof base, cudaMemcpyHostToDevice, h->stream));
+                for (uint64_t c = 0; c < n_periods; ++c) CU(cudaGraphLaunch(it->second.exec, h->stream));
+                h->launches += it->second.kernels * n_periods;
+                step += n_periods * period;
+            }
+        }
+        while (step < seg_end) {
             ST(launch_step(h, s, step, step, nullptr));
             ++step;
         }
-        const uint64_t avail = (end - step) / cycle;
-        const uint64_t reps = std::max<uint64_t>(1, std::min<uint64_t>(avail, std::max<uint64_t>(1, kGraphSteps / cycle)));
-        const uint64_t period = reps * cycle;
-        const uint64_t n_periods = (end - step) / period;
-        if (n_periods) {
-            GraphKey key{s->energy_every, s->normalize_every, (uint32_t)period, h->count_accepts};
-            auto it = h->graphs.find(key);
-            if (it == h->graphs.end()) {
-                // capture one period; every kernel reads the sweep counter from device memory
-                const uint64_t before = h->launches;
-                lqft_schedule rel = *s;
-                rel.sweep_base = 0;
-                cudaGraph_t graph = nullptr;
-                CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-                lqft_status st = LQFT_OK;
-                for (uint64_t i = 0; i < period && st == LQFT_OK; ++i) st = launch_step(h, &rel, i, i, h->sweep_ctr_d);
-                if (st == LQFT_OK) {
-                    k_tick<<<1, 1, 0, h->stream>>>(h->sweep_ctr_d, period);
-                    h->launches += 1;
-                }
-                cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-                if (st != LQFT_OK) {
-                    if (graph) cudaGraphDestroy(graph);
-                    return st;
-                }
-                if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-                GraphVal val;
-                val.kernels = h->launches - before;
-                h->launches = before;
-                ce = cudaGraphInstantiate(&val.exec, graph, 0);
-                cudaGraphDestroy(graph);
-                if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
-                it = h->graphs.emplace(key, val).first;
-            }
-            const uint64_t base = s->sweep_base + step;
-            CU(cudaMemcpyAsync(h->sweep_ctr_d, &base, sizeof base, cudaMemcpyHostToDevice, h->stream));
-            for (uint64_t c = 0; c < n_periods; ++c) CU(cudaGraphLaunch(it->second.exec, h->stream));
-            h->launches += it->second.kernels * n_periods;
-            step += n_periods * period;
-        }
-    }
-    while (step < end) {
-        ST(launch_step(h, s, step, step, nullptr));
-        ++step;
+        if (h->narrow_active) ST(narrow_exit(h));
     }
     CU(cudaEventRecord(h->ev_stop, h->stream));
     h->timed = true;
@@ -1392,6 +1514,12 @@ extern "C" lqft_status lqft_last_device_ms(lqft_handle* h, float* ms) {
 extern "C" lqft_status lqft_kernel_launches(lqft_handle* h, uint64_t* n) {
     if (!h || !n) return fail(LQFT_ERR_INVALID, "null argument");
     *n = h->launches;
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_narrow_segments(lqft_handle* h, uint64_t* n) {
+    if (!h || !n) return fail(LQFT_ERR_INVALID, "null argument");
+    *n = h->narrow_segments;
     return LQFT_OK;
 }
 

@@ -202,6 +202,11 @@ class Engine:
         check(lib().lqft_kernel_launches(self._h, C.byref(n)))
         return int(n.value)
 
+    def narrow_segments(self) -> int:
+        n = C.c_uint64()
+        check(lib().lqft_narrow_segments(self._h, C.byref(n)))
+        return int(n.value)
+
     def stream(self) -> int:
         s = C.c_void_p()
         check(lib().lqft_stream(self._h, C.byref(s)))

@@ -14,7 +14,8 @@ def pytest_configure(config):
 
 
 def _ensure_built():
-    from lattice_qft_b200 import _build
+    import __graft_entry__
+    _build = __graft_entry__.load_build_module()
     if _build.stale():
         _build.build()
     from oracle import oracle

@@ -96,8 +96,95 @@ def test_wide_row_kernels_bit_exact_vs_oracle(size, beta, wilson):
         assert (got2 == want2).all(), f"{int((got2 != want2).sum())} sites differ (flags={flags})"
 
 
+@pytest.mark.parametrize("size,beta,wilson", [
+    ((256, 8, 4), 0.25, (0, 0)), ((256, 4, 2), 0.2, (100, 2)), ((256, 10, 6), 0.3, (0, 0)), ((256, 36, 2), 0.25, (0, 0)),
+    ((256, 2, 34), 0.22, (255, 20)), ((256, 6, 48), 0.27, (0, 0)), ((256, 2, 2), 0.05, (3, 1)),
+])
+def test_narrow_working_copy_bit_exact_vs_oracle(size, beta, wilson):
+    """X = 256: lqft_sweep / lqft_run of >= 4 sweeps work on the 16-bit copy (kernels_narrow.cuh: packed sums,
+    s16x2 clamp, interleaved table, SHFL-shared t-neighbours).  Counting and non-counting instantiations,
+    graph and eager launches, energies and normalisation inside the run — all equal to the oracle and to the
+    i32 kernels bit for bit."""
+    X, Y, T = size
+    seed = 0xA11CE + Y * T
+    lat = O.Lattice([X, Y, T])
+    wil = O.Wilson(lat, *wilson) if wilson[0] else None
+    v0 = seeded_field(X * Y * T, seed=Y + 31 * T)
+    want = v0.copy()
+    wacc = sum(O.sweep(lat, want, beta, seed, s, order=1, wilson=wil) for s in range(10, 15))
+    for s in range(15, 21):
+        O.sweep(lat, want, beta, seed, s, order=1, wilson=wil)
+    we, _ = O.run(lat, want, beta, seed, 21, 0, 24, 4, 10, order=1, wilson=wil)
+    for flags in (0, _lib.FLAG_NO_GRAPH, _lib.FLAG_NO_NARROW):
+        with Engine(X, Y, T, flags=flags) as eng:
+            eng.set_chain(0, beta, seed, *wilson)
+            eng.upload(0, v0)
+            acc = eng.sweep(10, 5, want_accepted=True)[0]
+            eng.sweep(15, 6)
+            e_obs, _, _ = eng.run(24, sweep_base=21, energy_every=4, normalize_every=10)
+            got = eng.download(0)
+            segs = eng.narrow_segments()
+        assert acc == wacc, flags
+        assert (e_obs[0] == we).all(), flags
+        assert (got == want).all(), f"{int((got != want).sum())} sites differ (flags={flags})"
+        assert segs == (0 if flags & _lib.FLAG_NO_NARROW else 3), (flags, segs)
+
+
+def test_narrow_segments_and_guard_band():
+    """More than kN16Segment sweeps in one call are split into re-validated segments; a field outside the guard
+    band around the normalisation offset stays on the i32 kernels.  Same trajectory either way."""
+    X, Y, T = 256, 2, 2
+    beta, seed = 0.3, 77
+    lat = O.Lattice([X, Y, T])
+    v0 = seeded_field(X * Y * T, seed=5)
+    want = v0.copy()
+    we, _ = O.run(lat, want, beta, seed, 0, 0, 1100, 100, 10, order=1)
+    with Engine(X, Y, T) as eng:
+        eng.set_chain(0, beta, seed)
+        eng.upload(0, v0)
+        e_obs, _, _ = eng.run(1100, energy_every=100, normalize_every=10)
+        got = eng.download(0)
+        assert eng.narrow_segments() == 2
+    assert (e_obs[0] == we).all() and (got == want).all()
+    far = v0.copy()
+    far[::7] += 5000
+    want = far.copy()
+    for s in range(6):
+        O.sweep(lat, want, beta, seed, s, order=1)
+    with Engine(X, Y, T) as eng:
+        eng.set_chain(0, beta, seed)
+        eng.upload(0, far)
+        eng.sweep(0, 6)
+        got = eng.download(0)
+        assert eng.narrow_segments() == 0
+    assert (got == want).all()
+
+
+def test_narrow_many_chains_match_single_chain_runs():
+    X, Y, T = 256, 4, 4
+    betas = [0.2, 0.25, 0.31]
+    v0 = [seeded_field(X * Y * T, seed=40 + c) for c in range(3)]
+    single = []
+    for c in range(3):
+        with Engine(X, Y, T, flags=_lib.FLAG_NO_NARROW) as eng:
+            eng.set_chain(0, betas[c], 900 + c, 17 * c, c)
+            eng.upload(0, v0[c])
+            e, _, _ = eng.run(20, energy_every=5, normalize_every=10)
+            single.append((e[0].copy(), eng.download(0)))
+    with Engine(X, Y, T, n_chains=3) as eng:
+        for c in range(3):
+            eng.set_chain(c, betas[c], 900 + c, 17 * c, c)
+            eng.upload(c, v0[c])
+        e, _, _ = eng.run(20, energy_every=5, normalize_every=10)
+        assert eng.narrow_segments() == 1
+        for c in range(3):
+            assert (e[c] == single[c][0]).all()
+            assert (eng.download(c) == single[c][1]).all()
+
+
 @pytest.mark.parametrize("size,wilson", [((256, 8, 8), (0, 0)), ((256, 6, 4), (77, 3)), ((512, 4, 6), (0, 0)),
-                                         ((16, 16, 8), (5, 8)), ((10, 6, 4), (0, 0))])
+                                         ((16, 16, 8), (5, 8)), ((10, 6, 4), (0, 0)), ((256, 4, 40), (200, 33)),
+                                         ((256, 2, 2), (0, 0))])
 def test_self_halo_slab_path_on_one_gpu(size, wilson):
     """LQFT_FLAG_SELF_HALO: ghost planes + the multi-GPU code path (peer-memory pushes and phase flags fused in
     the streaming kernel for wide rows, boundary-first + exchange otherwise) with this rank as its own
@@ -120,6 +207,7 @@ def test_self_halo_slab_path_on_one_gpu(size, wilson):
         e_int = int(eng.energy()[0][0])
         s_int = int(eng.action()[0][0])
         eng.synchronize()
+        assert eng.narrow_segments() == (2 if X == 256 else 0)
     assert acc == wacc
     assert (e_obs[0] == we).all()
     assert (got == want).all(), f"{int((got != want).sum())} sites differ"
