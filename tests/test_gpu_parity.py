@@ -115,7 +115,8 @@ def test_narrow_working_copy_bit_exact_vs_oracle(size, beta, wilson):
     for s in range(15, 21):
         O.sweep(lat, want, beta, seed, s, order=1, wilson=wil)
     we, _ = O.run(lat, want, beta, seed, 21, 0, 24, 4, 10, order=1, wilson=wil)
-    for flags in (0, _lib.FLAG_NO_GRAPH, _lib.FLAG_NO_NARROW):
+    nores = _lib.FLAG_NO_RESIDENT  # lattices this small would otherwise run from shared memory
+    for flags in (nores, nores | _lib.FLAG_NO_GRAPH, nores | _lib.FLAG_NO_NARROW):
         with Engine(X, Y, T, flags=flags) as eng:
             eng.set_chain(0, beta, seed, *wilson)
             eng.upload(0, v0)
@@ -139,7 +140,7 @@ def test_narrow_segments_and_guard_band():
     v0 = seeded_field(X * Y * T, seed=5)
     want = v0.copy()
     we, _ = O.run(lat, want, beta, seed, 0, 0, 1100, 100, 10, order=1)
-    with Engine(X, Y, T) as eng:
+    with Engine(X, Y, T, flags=_lib.FLAG_NO_RESIDENT) as eng:
         eng.set_chain(0, beta, seed)
         eng.upload(0, v0)
         e_obs, _, _ = eng.run(1100, energy_every=100, normalize_every=10)
@@ -151,7 +152,7 @@ def test_narrow_segments_and_guard_band():
     want = far.copy()
     for s in range(6):
         O.sweep(lat, want, beta, seed, s, order=1)
-    with Engine(X, Y, T) as eng:
+    with Engine(X, Y, T, flags=_lib.FLAG_NO_RESIDENT) as eng:
         eng.set_chain(0, beta, seed)
         eng.upload(0, far)
         eng.sweep(0, 6)
@@ -166,12 +167,12 @@ def test_narrow_many_chains_match_single_chain_runs():
     v0 = [seeded_field(X * Y * T, seed=40 + c) for c in range(3)]
     single = []
     for c in range(3):
-        with Engine(X, Y, T, flags=_lib.FLAG_NO_NARROW) as eng:
+        with Engine(X, Y, T, flags=_lib.FLAG_NO_NARROW | _lib.FLAG_NO_RESIDENT) as eng:
             eng.set_chain(0, betas[c], 900 + c, 17 * c, c)
             eng.upload(0, v0[c])
             e, _, _ = eng.run(20, energy_every=5, normalize_every=10)
             single.append((e[0].copy(), eng.download(0)))
-    with Engine(X, Y, T, n_chains=3) as eng:
+    with Engine(X, Y, T, n_chains=3, flags=_lib.FLAG_NO_RESIDENT) as eng:
         for c in range(3):
             eng.set_chain(c, betas[c], 900 + c, 17 * c, c)
             eng.upload(c, v0[c])
