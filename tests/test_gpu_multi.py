@@ -19,4 +19,4 @@ def test_slab_decomposition_matches_single_gpu(ws):
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + ws), os.path.join(ROOT, "tests", "_multi_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert res.stdout.count("ok (") >= 6, res.stdout
+    assert res.stdout.count("ok (") >= 8, res.stdout
