@@ -17,6 +17,13 @@
 //   * the coin bit of the site's Philox word is funnel-shifted into the index, so one LDS.64 fetches
 //     {threshold | coin << 31, +-1} for the proposed direction.
 //
+// Slabs (world_size > 1): the narrow copy carries kN16GhostDepth ghost planes per side instead of one.  After an
+// exchange (k_n16_exchange: peer stores over NVLink plus two flag phases) all of them are valid; each half-sweep
+// then also updates the ghost planes that still have valid t-neighbours — redundantly, with the same Philox
+// words as their owner, hence identically — and the valid depth shrinks by one.  One exchange per
+// kN16GhostDepth half-sweeps replaces the per-half-sweep halo of the i32 path, and the sweep kernel itself
+// carries no flags, waits or peer stores at all.
+//
 // Validity: a narrow segment starts only if every height is within kN16Guard of the centre and lasts at most
 // kN16Segment sweeps; a sweep moves a site by at most one, so no height can leave [0, 4096) (host logic in
 // lqft.cu, narrow_enter / narrow_exit).
@@ -33,17 +40,7 @@ constexpr uint32_t kN16Segment = 1000;           // kN16Guard + kN16Segment < kN
 constexpr int kN16KcMax = 255;                   // threshold tables up to 256 entries (beta >= ~0.045)
 constexpr uint32_t kN16RowQ = 16;                // uint4 per row of one colour (X = 256)
 
-struct NarrowHalo {
-    uint16_t* lo_ghost = nullptr;  // lower neighbour's UPPER ghost plane of the colour being updated (chain 0)
-    uint16_t* hi_ghost = nullptr;  // upper neighbour's LOWER ghost plane
-    HaloSync* lo_sync = nullptr;
-    HaloSync* hi_sync = nullptr;
-    HaloSync* mine = nullptr;
-    unsigned long long phase = 0;
-    unsigned long long wait_for = 0;
-    uint32_t n_boundary_blocks = 0;
-    uint32_t enabled = 0;
-};
+constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even)
 
 // Table entry (i << 1) | coin for d = i - kc: coin 1 proposes +1 (m = d), coin 0 proposes -1 (m = -d);
 // same contents as build_two_sided (kernels_tiled.cuh), interleaved so that the coin can be shifted in.
@@ -108,17 +105,17 @@ __device__ __forceinline__ uint4 n16_wilson(uint32_t k0, uint32_t p, int sgn, ui
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// grid = (n_chunks, ceil(Tl / 16), n_chains); with HALO: (n_bchunks + (groups - 1) * n_chunks, 1, n_chains).
+// grid = (n_chunks, ceil(n_planes / 16), n_chains).  Updates local planes tl_first .. tl_first + n_planes - 1
+// (n_planes even; tl_first < 0 reaches into the lower ghost planes, tl_first + n_planes > Tl into the upper ones).
 // Lanes 0-15: plane t, row y; lanes 16-31: plane t+1, row y+1 — the same x parity, and each half's inner
 // t-neighbour row sits in the partner half's register window.
-template <bool WILSON, bool COUNT, bool HALO>
-__global__ void __launch_bounds__(kN16Threads, (HALO || COUNT) ? 3 : 4)
-k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const uint32_t n_chunks,
-            const uint32_t n_bchunks, uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
-            const ChainDev* __restrict__ chains, const uint32_t* __restrict__ thr_all,
-            unsigned long long* __restrict__ acc, const uint32_t max_thr, const NarrowHalo halo) {
+template <bool WILSON, bool COUNT>
+__global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
+k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
+            const uint32_t n_planes, const uint32_t n_chunks, uint16_t* __restrict__ own_base,
+            const uint16_t* __restrict__ oth_base, const ChainDev* __restrict__ chains,
+            const uint32_t* __restrict__ thr_all, unsigned long long* __restrict__ acc, const uint32_t max_thr) {
     __shared__ unsigned int s_cnt;
-    __shared__ long long s_delta[kN16Warps][2];
     pdl_launch_dependents();
     const uint32_t chain = blockIdx.z;
     const ChainDev cd = chains[chain];
@@ -130,29 +127,15 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t half = lane >> 4, l16 = lane & 15u;
-    uint32_t chunk = blockIdx.x, group = blockIdx.y, chunks_here = n_chunks;
-    bool boundary_block = false;
-    if (HALO) {
-        // plane group 0 — rotated to {Tl-8 .. Tl-1, 0 .. 7}, i.e. both boundary planes and the planes that
-        // read the ghosts — comes first in block order and in short chunks (see k_sweep_stream)
-        if (chunk < n_bchunks) {
-            group = 0;
-            chunks_here = n_bchunks;
-            boundary_block = true;
-        } else {
-            chunk -= n_bchunks;
-            group = 1u + chunk / n_chunks;
-            chunk %= n_chunks;
-        }
-    }
-    uint32_t pl0 = group * (2u * kN16Warps) + 2u * warp;  // lower plane of this warp's pair
-    const bool pair_ok = pl0 < g.Tl;                      // Tl is even
-    if (HALO) pl0 = (pl0 + g.Tl - (uint32_t)kN16Warps % g.Tl) % g.Tl;
-    const uint32_t y0 = (uint32_t)(((uint64_t)chunk * g.Y) / chunks_here);
-    const uint32_t y1 = (uint32_t)(((uint64_t)(chunk + 1u) * g.Y) / chunks_here);
+    const uint32_t chunk = blockIdx.x;
+    const uint32_t pl0 = blockIdx.y * (2u * kN16Warps) + 2u * warp;  // lower plane of this warp's pair within the range
+    const uint32_t y0 = (uint32_t)(((uint64_t)chunk * g.Y) / n_chunks);
+    const uint32_t y1 = (uint32_t)(((uint64_t)(chunk + 1u) * g.Y) / n_chunks);
     int accepted = 0;
-    if (pair_ok && y0 < y1) {  // warp uniform
-        const uint32_t tl = pl0 + half, tg = g.t0 + tl;
+    if (pl0 < n_planes && y0 < y1) {  // warp uniform
+        const uint32_t tl = (uint32_t)tl_first + pl0 + half;     // local plane, modulo 2^32 below the slab
+        const uint32_t tg = (g.t0 + g.T + tl) % g.T;             // global plane: keys, parity and the Wilson sheet
+        const bool owned = tl < g.Tl;
         const size_t cbase = (size_t)chain * g.chain_stride;
         const uint32_t planeq = g.Y * kN16RowQ;
         // offsets in uint4 units from the chain's array base
@@ -160,25 +143,12 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         const uint32_t b_out = (half ? plane_above(g, tl) : plane_below(g, tl)) * planeq + l16;
         uint4* const q_own = reinterpret_cast<uint4*>(own_base + cbase);
         const uint4* const q_oth = reinterpret_cast<const uint4*>(oth_base + cbase);
-        bool push = false;
-        if (HALO && halo.enabled) {
-            if (pl0 == 0u && lane == 0u) halo_wait(&halo.mine->from_lo, halo.wait_for, &halo.mine->error);
-            if (pl0 + 2u == g.Tl && lane == 0u) halo_wait(&halo.mine->from_hi, halo.wait_for, &halo.mine->error);
-            const uint4* peer = nullptr;
-            if (tl == 0u) peer = reinterpret_cast<const uint4*>(halo.lo_ghost + cbase) + l16;
-            else if (tl + 1u == g.Tl) peer = reinterpret_cast<const uint4*>(halo.hi_ghost + cbase) + l16;
-            push = peer != nullptr;
-            // lanes of a half differ only by l16 on both sides: one byte offset per half-warp, kept in shared memory
-            if (push && l16 == 0u)
-                s_delta[warp][half] = reinterpret_cast<const char*>(peer) - reinterpret_cast<const char*>(q_own + b_own);
-            __syncwarp();
-        }
         const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
         uint32_t y = y0 + half;
         if (y == g.Y) y = 0;  // this lane's first row
         const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
         uint4 wa = __ldg(q_oth + (b_own + ym * kN16RowQ)), wb = __ldg(q_oth + (b_own + y * kN16RowQ)), wc;
-        uint32_t p = (y0 + g.t0 + pl0 + (uint32_t)colour) & 1u;  // x parity of the lower half's row == the upper half's
+        uint32_t p = (y + tg + (uint32_t)colour) & 1u;  // x parity of this lane's row; the same in both halves (T is even)
         const uint32_t src_r = (lane & 16u) | ((lane + 1u) & 15u), src_l = (lane & 16u) | ((lane - 1u) & 15u);
         const uint32_t grp_base = tg * g.Y * 32u + l16 * 2u;  // Philox counter word 0 of this thread's first group at y = 0
         const bool wil_plane = WILSON && tg < cd.wil_h;
@@ -205,17 +175,16 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
                 woff = n16_wilson(8u * l16, p, (y == 0u ? 1 : 0) - (y == y_one ? 1 : 0), cd.wil_w);                      \
         }                                                                                                                \
         uint4 w;                                                                                                         \
+        int acc_row = 0;                                                                                                 \
         if (p) {                                                                                                         \
             const uint32_t edge = __shfl_sync(0xffffffffu, OC.x, src_r);                                                 \
-            w = n16_row_update<1, WILSON, COUNT>(v, OM, OC, ON, to, ti, edge, r0, r1, c_off, c_max, woff, accepted);     \
+            w = n16_row_update<1, WILSON, COUNT>(v, OM, OC, ON, to, ti, edge, r0, r1, c_off, c_max, woff, acc_row);      \
         } else {                                                                                                         \
             const uint32_t edge = __shfl_sync(0xffffffffu, OC.w, src_l);                                                 \
-            w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, to, ti, edge, r0, r1, c_off, c_max, woff, accepted);     \
+            w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, to, ti, edge, r0, r1, c_off, c_max, woff, acc_row);      \
         }                                                                                                                \
+        if (COUNT) accepted += owned ? acc_row : 0;  /* ghost planes are somebody else's sites */                        \
         *po = w;                                                                                                         \
-        if (HALO) {                                                                                                      \
-            if (push) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(po) + s_delta[warp][half]) = w;                  \
-        }                                                                                                                \
         y = yn;                                                                                                          \
         p ^= 1u;                                                                                                         \
     }
@@ -232,32 +201,76 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     }
     if (COUNT)
         block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
-    if (HALO && halo.enabled) {
-        // the last boundary block to finish publishes this launch's phase (release chain: k_sweep_stream)
-        __syncthreads();
-        if (boundary_block && threadIdx.x == 0) {
-            const unsigned int done = atom_add_acq_rel_gpu(&halo.mine->ticket, 1u);
-            if (done + 1u == halo.n_boundary_blocks) {
-                st_relaxed_gpu(&halo.mine->ticket, 0u);
-                st_release_sys(&halo.lo_sync->from_hi, halo.phase);
-                st_release_sys(&halo.hi_sync->from_lo, halo.phase);
-            }
+}
+
+// ---- deep halo exchange -------------------------------------------------------------------------------------
+// My first `depth` owned planes go to the lower neighbour's upper ghost planes, my last `depth` owned planes to
+// the upper neighbour's lower ghost planes; both colours, all chains.  Two flag phases on HaloSync (kernels_tiled.cuh):
+//   ready     = "my kernels that read my ghost planes are done: overwrite them" (sent first thing),
+//   delivered = "your ghost planes hold my boundary planes" (sent by the last block, release chain as in
+//               k_sweep_stream); the same block then waits for both neighbours' deliveries, so the kernel
+//               completes only when this rank's ghost planes are valid.
+// grid = (ceil(depth * plane / 8 / 256), 4 = side * 2 + colour, n_chains), block = 256.
+struct ExchangeArgs {
+    uint16_t* mine[2];       // my narrow arrays (colour 0, 1)
+    uint16_t* lo[2];         // lower neighbour's narrow arrays, as mapped here
+    uint16_t* hi[2];         // upper neighbour's
+    uint64_t stride_mine, stride_lo, stride_hi;  // elements per chain
+    uint32_t plane;          // elements per plane per colour
+    uint32_t depth;          // planes to send per side == ghost planes per side
+    uint32_t tl_mine, tl_lo; // owned planes here and at the lower neighbour
+    HaloSync* sync_mine;
+    HaloSync* sync_lo;
+    HaloSync* sync_hi;
+    unsigned long long ready, delivered;
+};
+
+__global__ void __launch_bounds__(256)
+k_n16_exchange(const ExchangeArgs a) {
+    const bool first = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    if (first && threadIdx.x == 0) {
+        st_release_sys(&a.sync_lo->from_hi, a.ready);
+        st_release_sys(&a.sync_hi->from_lo, a.ready);
+    }
+    const uint32_t side = blockIdx.y >> 1, colour = blockIdx.y & 1u, chain = blockIdx.z;
+    if (threadIdx.x == 0) halo_wait(side ? &a.sync_mine->from_hi : &a.sync_mine->from_lo, a.ready, &a.sync_mine->error);
+    __syncthreads();
+    const uint64_t n = (uint64_t)a.depth * a.plane / 8;  // uint4 per (side, colour, chain)
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        // storage planes: [0, depth) lower ghosts, [depth, depth + Tl) owned, then the upper ghosts
+        const uint16_t* src = a.mine[colour] + (size_t)chain * a.stride_mine +
+                              (size_t)(side ? a.tl_mine : a.depth) * a.plane;
+        uint16_t* dst = side ? a.hi[colour] + (size_t)chain * a.stride_hi
+                             : a.lo[colour] + (size_t)chain * a.stride_lo + (size_t)(a.depth + a.tl_lo) * a.plane;
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned int done = atom_add_acq_rel_gpu(&a.sync_mine->ticket, 1u);
+        if (done + 1u == total) {
+            st_relaxed_gpu(&a.sync_mine->ticket, 0u);
+            st_release_sys(&a.sync_lo->from_hi, a.delivered);
+            st_release_sys(&a.sync_hi->from_lo, a.delivered);
+            halo_wait(&a.sync_mine->from_lo, a.delivered, &a.sync_mine->error);
+            halo_wait(&a.sync_mine->from_hi, a.delivered, &a.sync_mine->error);
         }
     }
 }
 
 // ---- i32 <-> narrow ---------------------------------------------------------------------------------------
-// Whole allocation of one colour (owned and ghost planes), 4 heights per thread.  grid = (ceil(stride/4/bd), n_chains).
-// worst = max |height - centre| over everything converted.
+// Owned planes of one colour, 4 heights per thread.  grid = (ceil(n/4/256), n_chains); n = Tl * plane elements per
+// chain, src/dst point at the first owned plane of chain 0.  worst = max |height - centre| over everything converted.
 __global__ void __launch_bounds__(256)
-k_narrow(const int32_t* __restrict__ f, uint16_t* __restrict__ n, uint64_t chain_stride, const int32_t* __restrict__ centre,
-         uint32_t* __restrict__ worst) {
+k_narrow(const int32_t* __restrict__ f, uint64_t f_stride, uint16_t* __restrict__ n, uint64_t n_stride, uint64_t count,
+         const int32_t* __restrict__ centre, uint32_t* __restrict__ worst) {
     const uint32_t chain = blockIdx.y;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t far = 0;
-    if (i < chain_stride / 4) {
+    if (i < count / 4) {
         const int c = centre[chain];
-        const int4 v = reinterpret_cast<const int4*>(f + (size_t)chain * chain_stride)[i];
+        const int4 v = reinterpret_cast<const int4*>(f + (size_t)chain * f_stride)[i];
         // wide arithmetic: an uploaded field may hold any i32
         const long long dx = (long long)v.x - c, dy = (long long)v.y - c, dz = (long long)v.z - c, dw = (long long)v.w - c;
         const long long m = max(max(llabs(dx), llabs(dy)), max(llabs(dz), llabs(dw)));
@@ -265,20 +278,21 @@ k_narrow(const int32_t* __restrict__ f, uint16_t* __restrict__ n, uint64_t chain
         uint2 o;
         o.x = ((uint32_t)(dx + kN16Bias) & 0xffffu) | ((uint32_t)(dy + kN16Bias) << 16);
         o.y = ((uint32_t)(dz + kN16Bias) & 0xffffu) | ((uint32_t)(dw + kN16Bias) << 16);
-        reinterpret_cast<uint2*>(n + (size_t)chain * chain_stride)[i] = o;
+        reinterpret_cast<uint2*>(n + (size_t)chain * n_stride)[i] = o;
     }
     far = __reduce_max_sync(0xffffffffu, far);
     if ((threadIdx.x & 31u) == 0u && far > (uint32_t)kN16Guard) atomicMax(worst, far);
 }
 
 __global__ void __launch_bounds__(256)
-k_widen(const uint16_t* __restrict__ n, int32_t* __restrict__ f, uint64_t chain_stride, const int32_t* __restrict__ centre) {
+k_widen(const uint16_t* __restrict__ n, uint64_t n_stride, int32_t* __restrict__ f, uint64_t f_stride, uint64_t count,
+        const int32_t* __restrict__ centre) {
     const uint32_t chain = blockIdx.y;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= chain_stride / 4) return;
+    if (i >= count / 4) return;
     const int c = centre[chain] - kN16Bias;
-    const uint2 v = reinterpret_cast<const uint2*>(n + (size_t)chain * chain_stride)[i];
-    reinterpret_cast<int4*>(f + (size_t)chain * chain_stride)[i] =
+    const uint2 v = reinterpret_cast<const uint2*>(n + (size_t)chain * n_stride)[i];
+    reinterpret_cast<int4*>(f + (size_t)chain * f_stride)[i] =
         make_int4((int)(v.x & 0xffffu) + c, (int)(v.x >> 16) + c, (int)(v.y & 0xffffu) + c, (int)(v.y >> 16) + c);
 }
 
@@ -294,15 +308,17 @@ __global__ void k_narrow_begin(const int32_t* __restrict__ offset, int32_t* __re
 // ---- host side ----------------------------------------------------------------------------------------------
 struct NarrowPlan {
     bool enabled = false;
-    int blocks_per_sm = 0, blocks_per_sm_halo = 0;
+    int blocks_per_sm = 0;
     int sm_count = 0;
 };
 
 struct NarrowArgs {
-    Geom g;
+    Geom g;               // geometry of the narrow arrays (ghost = their ghost depth)
     int colour;
     uint64_t sweep;
     const uint64_t* ctr;
+    int32_t tl_first;
+    uint32_t n_planes;
     uint32_t n_chains;
     uint16_t* own;
     const uint16_t* oth;
@@ -313,31 +329,28 @@ struct NarrowArgs {
     bool wilson, count;
     cudaStream_t stream;
     bool pdl;
-    NarrowHalo halo;
 };
 
 inline bool narrow_geometry_ok(const Geom& g, uint32_t max_thr) {
     return g.X == 256 && g.Tl >= 2 && g.Tl % 2 == 0 && max_thr <= (uint32_t)kN16KcMax + 1 &&
-           (uint64_t)g.plane / 8 * (g.Tl + 2 * g.ghost) < (1ull << 32) && (uint64_t)g.T * g.Y * 32u < (1ull << 32);
+           (uint64_t)g.plane / 8 * (g.Tl + 2 * kN16GhostDepth) < (1ull << 32) && (uint64_t)g.T * g.Y * 32u < (1ull << 32);
 }
 
 inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, int sm_count, uint32_t max_thr, bool force_off) {
     p.enabled = false;
     if (force_off || !narrow_geometry_ok(g, max_thr)) return cudaSuccess;
     p.sm_count = sm_count;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<false, false, false>, kN16Threads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<false, false>, kN16Threads, 0);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm_halo, k_sweep_n16<false, false, true>, kN16Threads, 0);
-    if (e != cudaSuccess) return e;
-    p.enabled = p.blocks_per_sm > 0 && p.blocks_per_sm_halo > 0;
+    p.enabled = p.blocks_per_sm > 0;
     return cudaSuccess;
 }
 
 // y chunks per plane group: one wave if possible, chunks as short as that allows (cost model of stream_chunks;
 // the per-chunk prologue is worth about two rows here).
-inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_chains, bool halo) {
-    const uint64_t slots = (uint64_t)p.sm_count * (halo ? p.blocks_per_sm_halo : p.blocks_per_sm);
-    const uint64_t base = (uint64_t)((g.Tl + 2 * kN16Warps - 1) / (2 * kN16Warps)) * n_chains;
+inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_planes, uint32_t n_chains) {
+    const uint64_t slots = (uint64_t)p.sm_count * p.blocks_per_sm;
+    const uint64_t base = (uint64_t)((n_planes + 2 * kN16Warps - 1) / (2 * kN16Warps)) * n_chains;
     const uint32_t max_chunks = g.Y / 2 ? g.Y / 2 : 1;
     uint32_t best = 1;
     double best_cost = 1e300;
@@ -355,20 +368,10 @@ inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_cha
 }
 
 inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
-    const uint32_t n_groups = (a.g.Tl + 2 * kN16Warps - 1) / (2 * kN16Warps);
-    const uint32_t n_chunks = narrow_chunks(p, a.g, a.n_chains, a.halo.enabled != 0);
-    dim3 grid(n_chunks, n_groups, a.n_chains);
-    NarrowHalo halo = a.halo;
-    uint32_t n_bchunks = 0;
-    if (halo.enabled) {
-        constexpr uint32_t factor = 4;
-        const uint32_t max_chunks = a.g.Y / 2 ? a.g.Y / 2 : 1;
-        n_bchunks = factor * n_chunks < max_chunks ? factor * n_chunks : max_chunks;
-        grid = dim3(n_bchunks + (n_groups - 1) * n_chunks, 1, a.n_chains);
-        halo.n_boundary_blocks = n_bchunks * a.n_chains;
-    }
+    const uint32_t n_groups = (a.n_planes + 2 * kN16Warps - 1) / (2 * kN16Warps);
+    const uint32_t n_chunks = narrow_chunks(p, a.g, a.n_planes, a.n_chains);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
+    cfg.gridDim = dim3(n_chunks, n_groups, a.n_chains);
     cfg.blockDim = dim3(kN16Threads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = a.stream;
@@ -377,20 +380,13 @@ inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = a.pdl ? 1 : 0;
-#define LQFT_GO(W, C, H)                                                                                             \
-    return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C, H>, a.g, a.colour, a.sweep, a.ctr, n_chunks, n_bchunks, a.own, \
-                              a.oth, a.chains, a.thr, a.acc, a.max_thr, halo)
-    if (halo.enabled) {
-        if (a.wilson) {
-            if (a.count) LQFT_GO(true, true, true); else LQFT_GO(true, false, true);
-        } else {
-            if (a.count) LQFT_GO(false, true, true); else LQFT_GO(false, false, true);
-        }
-    }
+#define LQFT_GO(W, C)                                                                                                  \
+    return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_planes, n_chunks, \
+                              a.own, a.oth, a.chains, a.thr, a.acc, a.max_thr)
     if (a.wilson) {
-        if (a.count) LQFT_GO(true, true, false); else LQFT_GO(true, false, false);
+        if (a.count) LQFT_GO(true, true); else LQFT_GO(true, false);
     } else {
-        if (a.count) LQFT_GO(false, true, false); else LQFT_GO(false, false, false);
+        if (a.count) LQFT_GO(false, true); else LQFT_GO(false, false);
     }
 #undef LQFT_GO
     return cudaGetLastError();

@@ -18,7 +18,7 @@ namespace lqft {
 struct Geom {
     uint32_t X, Y, T, Xh;   // global extents, Xh = X/2
     uint32_t Tl, t0;        // owned planes, first owned global plane
-    uint32_t ghost;         // ghost planes per side (0: periodic wrap by index, 1: slab)
+    uint32_t ghost;         // ghost planes per side (0: periodic wrap by index; slabs: 1, or the deep halo of the narrow copy)
     uint32_t plane;         // Xh*Y elements per plane per colour
     uint64_t chain_stride;  // plane * (Tl + 2*ghost) elements per chain per colour
 };
@@ -34,10 +34,10 @@ constexpr uint32_t kThrStride = 2048;  // == LQFT_MAX_THRESHOLDS
 constexpr int kAccSlots = 64;          // spread of the acceptance counters per chain
 
 __device__ __forceinline__ uint32_t plane_below(const Geom& g, uint32_t tl) {
-    return g.ghost ? tl : (tl == 0 ? g.Tl - 1 : tl - 1);  // storage plane index of t-1
+    return g.ghost ? tl + g.ghost - 1 : (tl == 0 ? g.Tl - 1 : tl - 1);  // storage plane index of t-1
 }
 __device__ __forceinline__ uint32_t plane_above(const Geom& g, uint32_t tl) {
-    return g.ghost ? tl + 2 : (tl + 1 == g.Tl ? 0 : tl + 1);  // storage plane index of t+1
+    return g.ghost ? tl + g.ghost + 1 : (tl + 1 == g.Tl ? 0 : tl + 1);  // storage plane index of t+1
 }
 __device__ __forceinline__ uint32_t plane_self(const Geom& g, uint32_t tl) { return tl + g.ghost; }
 

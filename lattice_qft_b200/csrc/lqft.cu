@@ -191,6 +191,9 @@ struct lqft_handle {
     int32_t* ncentre_d = nullptr;               // [n_chains] centre of the bias while a narrow segment runs
     uint32_t* nworst_d = nullptr;               // validity word of k_narrow
     NarrowPlan narrowp{};
+    Geom gn{};                                  // geometry of the narrow arrays: slabs carry a deep halo (ghost > 1)
+    uint32_t nvalid = 0;                        // ghost planes per side of the narrow copy that are valid right now
+    uint32_t tl_lo = 0, tl_hi = 0;              // owned planes of the lower / upper neighbour
     bool narrow_active = false;
     uint64_t narrow_segments = 0;
 };
@@ -582,9 +585,23 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
 
     const uint32_t no_narrow = LQFT_FLAG_NO_NARROW | LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_STREAM |
                                LQFT_FLAG_HALO_NCCL;
+    h->gn = g;
+    if (g.ghost) {
+        // deep halo of the narrow copy: as many planes as the thinnest slab allows, at most kN16GhostDepth, even
+        uint32_t depth = kN16GhostDepth;
+        for (uint32_t r = 0; r < ws; ++r) {
+            uint32_t rt0 = 0, rnt = 0;
+            ST(lqft_host_slab(T, ws, r, &rt0, &rnt));
+            depth = std::min(depth, rnt);
+            if (r == (cfg->rank + ws - 1) % ws) h->tl_lo = rnt;
+            if (r == (cfg->rank + 1) % ws) h->tl_hi = rnt;
+        }
+        h->gn.ghost = std::max(1u, depth & ~1u);
+        h->gn.chain_stride = (uint64_t)g.plane * (g.Tl + 2 * h->gn.ghost);
+    }
     if (!h->is64 && !(cfg->flags & no_narrow) && narrow_geometry_ok(g, 2)) {
         // 16-bit working copy (+50 % field memory); without it the i32 kernels do all the work
-        const size_t nbytes = sizeof(uint16_t) * g.chain_stride * nc;
+        const size_t nbytes = sizeof(uint16_t) * h->gn.chain_stride * nc;
         if (cudaMalloc(&h->narrow[0], nbytes) != cudaSuccess || cudaMalloc(&h->narrow[1], nbytes) != cudaSuccess) {
             cudaGetLastError();
             cudaFree(h->narrow[0]);
@@ -740,19 +757,12 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
         h->launches += 1;
         return LQFT_OK;
     }
-    if (h->narrow_active) {  // whole-slab launches only (ghost == 0, or the peer-memory halo)
-        NarrowArgs a{g, colour, sweep, ctr, h->cfg.n_chains, h->narrow[colour], h->narrow[colour ^ 1], h->chains_d, h->thr_d,
-                     h->acc_d, h->max_thr, h->any_wilson, h->count_accepts, s, !(h->cfg.flags & LQFT_FLAG_NO_PDL), NarrowHalo{}};
-        if (halo_now) {
-            a.halo.lo_ghost = (uint16_t*)h->peer_base[0][3 + colour] + (size_t)(g.Tl + 1) * g.plane;
-            a.halo.hi_ghost = (uint16_t*)h->peer_base[1][3 + colour];
-            a.halo.lo_sync = (HaloSync*)h->peer_base[0][2];
-            a.halo.hi_sync = (HaloSync*)h->peer_base[1][2];
-            a.halo.mine = h->halo_d;
-            a.halo.wait_for = h->phase;
-            a.halo.phase = ++h->phase;
-            a.halo.enabled = 1;
-        }
+    if (h->narrow_active) {
+        // tl_first / n_planes are reinterpreted: tl_first = planes of ghost zone to include on each side
+        const int32_t extra = (int32_t)tl_first;
+        NarrowArgs a{h->gn, colour, sweep, ctr, -extra, g.Tl + 2u * (uint32_t)extra, h->cfg.n_chains, h->narrow[colour],
+                     h->narrow[colour ^ 1], h->chains_d, h->thr_d, h->acc_d, h->max_thr, h->any_wilson, h->count_accepts, s,
+                     !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
         CU(narrow_half(h->narrowp, a));
         h->launches += 1;
         return LQFT_OK;
@@ -800,8 +810,24 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
 }
 
 // One full red-black sweep.  `sweep` + (*ctr if ctr) is the RNG sweep counter.
+static lqft_status narrow_exchange(lqft_handle* h);
+
 static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* ctr) {
     const Geom& g = h->g;
+    if (h->narrow_active) {
+        // narrow copy: on slabs every half-sweep also updates the ghost planes that still have valid neighbours,
+        // and the valid depth shrinks by one; an exchange restores it (kernels_narrow.cuh)
+        for (int colour = 0; colour < 2; ++colour) {
+            uint32_t extra = 0;
+            if (h->gn.ghost) {
+                if (h->nvalid == 0) ST(narrow_exchange(h));
+                extra = h->nvalid - 1;
+                h->nvalid -= 1;
+            }
+            ST(launch_half(h, colour, sweep, ctr, extra, g.Tl, h->stream));
+        }
+        return LQFT_OK;
+    }
     if (g.ghost == 0) {
         ST(launch_half(h, 0, sweep, ctr, 0, g.Tl, h->stream));
         ST(launch_half(h, 1, sweep, ctr, 0, g.Tl, h->stream));
@@ -839,19 +865,25 @@ static lqft_status launch_observe(lqft_handle* h, bool moments) {
         h->launches += 2;
         return LQFT_OK;
     }
+    if (h->narrow_active) {
+        if (moments) return fail(LQFT_ERR_STATE, "slice moments are not available on the narrow working copy");
+        if (h->gn.ghost && h->nvalid == 0) ST(narrow_exchange(h));  // the last owned plane looks one plane up
+        const uint32_t units = g.plane / 4;
+        const uint32_t bd = block_for(units);
+        dim3 grid((units + bd - 1) / bd, g.Tl, h->cfg.n_chains);
+        k_observe_vec4<<<grid, bd, 0, h->stream>>>(h->gn, (const uint16_t*)h->narrow[0], (const uint16_t*)h->narrow[1], h->obs_d,
+                                                  (unsigned long long*)nullptr);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        return LQFT_OK;
+    }
     ST(ghost_op_begin(h));
     if (g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) {
         const uint32_t units = g.plane / 4;
         const uint32_t bd = block_for(units);
         dim3 grid((units + bd - 1) / bd, g.Tl, h->cfg.n_chains);
-        if (h->narrow_active) {
-            if (moments) return fail(LQFT_ERR_STATE, "slice moments are not available on the narrow working copy");
-            k_observe_vec4<<<grid, bd, 0, h->stream>>>(g, (const uint16_t*)h->narrow[0], (const uint16_t*)h->narrow[1], h->obs_d,
-                                                      (unsigned long long*)nullptr);
-        } else {
-            k_observe_vec4<<<grid, bd, 0, h->stream>>>(g, (const int32_t*)h->field[0], (const int32_t*)h->field[1], h->obs_d,
-                                                      moments ? h->mom_d : nullptr);
-        }
+        k_observe_vec4<<<grid, bd, 0, h->stream>>>(g, (const int32_t*)h->field[0], (const int32_t*)h->field[1], h->obs_d,
+                                                  moments ? h->mom_d : nullptr);
     } else {
         const uint32_t bd = block_for(g.plane);
         dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
@@ -877,7 +909,7 @@ static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint
         return LQFT_OK;
     }
     if (h->narrow_active)
-        k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(g, (const uint16_t*)h->narrow[0], (const uint16_t*)h->narrow[1],
+        k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(h->gn, (const uint16_t*)h->narrow[0], (const uint16_t*)h->narrow[1],
                                                              h->chains_d, nc, counter, ctr, explicit_site, only_chain, h->shift_d,
                                                              (const int32_t*)h->ncentre_d, (int32_t)kN16Bias);
     else
@@ -1279,34 +1311,68 @@ static lqft_status narrow_enter(lqft_handle* h, bool* ok) {
     const Geom& g = h->g;
     const uint32_t nc = h->cfg.n_chains;
     *ok = false;
-    ST(ghost_op_begin(h));
     k_narrow_begin<<<(nc + 127) / 128, 128, 0, h->stream>>>(h->offset_d, h->ncentre_d, nc, h->nworst_d);
-    dim3 grid((uint32_t)((g.chain_stride / 4 + 255) / 256), nc);
+    const uint64_t count = (uint64_t)g.Tl * g.plane;  // owned planes; ghost planes are filled by the first exchange
+    dim3 grid((uint32_t)((count / 4 + 255) / 256), nc);
     for (int c = 0; c < 2; ++c)
-        k_narrow<<<grid, 256, 0, h->stream>>>(h->field[c], h->narrow[c], g.chain_stride, h->ncentre_d, h->nworst_d);
+        k_narrow<<<grid, 256, 0, h->stream>>>(h->field[c] + (size_t)g.ghost * g.plane, g.chain_stride,
+                                              h->narrow[c] + (size_t)h->gn.ghost * g.plane, h->gn.chain_stride, count,
+                                              h->ncentre_d, h->nworst_d);
     CU(cudaGetLastError());
     h->launches += 3;
-    ST(ghost_op_end(h));
     ST(allreduce_i32(h, h->nworst_d, 1));  // k_narrow caps the word at 2^24: the sum over ranks cannot wrap
     uint32_t worst = 0;
     CU(cudaMemcpyAsync(&worst, h->nworst_d, sizeof worst, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     *ok = worst == 0;
     h->narrow_active = *ok;
+    h->nvalid = 0;
     if (*ok) h->narrow_segments += 1;
     return LQFT_OK;
 }
 
 static lqft_status narrow_exit(lqft_handle* h) {
     const Geom& g = h->g;
-    ST(ghost_op_begin(h));  // the neighbours' last pushes into the narrow ghost planes have landed
-    dim3 grid((uint32_t)((g.chain_stride / 4 + 255) / 256), h->cfg.n_chains);
+    const uint64_t count = (uint64_t)g.Tl * g.plane;
+    dim3 grid((uint32_t)((count / 4 + 255) / 256), h->cfg.n_chains);
     for (int c = 0; c < 2; ++c)
-        k_widen<<<grid, 256, 0, h->stream>>>(h->narrow[c], h->field[c], g.chain_stride, h->ncentre_d);
+        k_widen<<<grid, 256, 0, h->stream>>>(h->narrow[c] + (size_t)h->gn.ghost * g.plane, h->gn.chain_stride,
+                                             h->field[c] + (size_t)g.ghost * g.plane, g.chain_stride, count, h->ncentre_d);
     CU(cudaGetLastError());
     h->launches += 2;
     h->narrow_active = false;
-    ST(ghost_op_end(h));
+    if (g.ghost) h->ghosts_valid = false;  // the i32 ghost planes were not maintained meanwhile
+    return LQFT_OK;
+}
+
+// Deep halo exchange of the narrow copy with both neighbours (k_n16_exchange): two phases of the flag protocol.
+static lqft_status narrow_exchange(lqft_handle* h) {
+    const Geom& gn = h->gn;
+    ExchangeArgs a{};
+    for (int c = 0; c < 2; ++c) {
+        a.mine[c] = h->narrow[c];
+        a.lo[c] = (uint16_t*)h->peer_base[0][3 + c];
+        a.hi[c] = (uint16_t*)h->peer_base[1][3 + c];
+    }
+    a.stride_mine = gn.chain_stride;
+    a.stride_lo = (uint64_t)gn.plane * (h->tl_lo + 2 * gn.ghost);
+    a.stride_hi = (uint64_t)gn.plane * (h->tl_hi + 2 * gn.ghost);
+    a.plane = gn.plane;
+    a.depth = gn.ghost;
+    a.tl_mine = gn.Tl;
+    a.tl_lo = h->tl_lo;
+    a.sync_mine = h->halo_d;
+    a.sync_lo = (HaloSync*)h->peer_base[0][2];
+    a.sync_hi = (HaloSync*)h->peer_base[1][2];
+    a.ready = h->phase + 1;
+    a.delivered = h->phase + 2;
+    h->phase += 2;
+    const uint64_t n = (uint64_t)a.depth * a.plane / 8;
+    dim3 grid((uint32_t)((n + 255) / 256), 4, h->cfg.n_chains);
+    k_n16_exchange<<<grid, 256, 0, h->stream>>>(a);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->nvalid = gn.ghost;
     return LQFT_OK;
 }
 
@@ -1414,6 +1480,7 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
             if (ok) seg_end = std::min<uint64_t>(end, step + kN16Segment);
             else narrow = false;
         }
+        if (!h->narrow_active) ST(refresh_ghosts(h));  // a narrow segment leaves the i32 ghost planes stale
         if (use_graph && step < seg_end) {
             while (step < seg_end && step % cycle != 0) {
                 ST(launch_step(h, s, step, step, nullptr));
