@@ -41,6 +41,7 @@ constexpr int kN16KcMax = 255;                   // threshold tables up to 256 e
 constexpr uint32_t kN16RowQ = 16;                // uint4 per row of one colour (X = 256)
 
 constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even)
+constexpr uint32_t kN16Overlap = 3;              // half-sweeps whose interior runs underneath an exchange
 
 // Table entry (i << 1) | coin for d = i - kc: coin 1 proposes +1 (m = d), coin 0 proposes -1 (m = -d);
 // same contents as build_two_sided (kernels_tiled.cuh), interleaved so that the coin can be shifted in.
@@ -105,14 +106,17 @@ __device__ __forceinline__ uint4 n16_wilson(uint32_t k0, uint32_t p, int sgn, ui
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// grid = (n_chunks, ceil(n_planes / 16), n_chains).  Updates local planes tl_first .. tl_first + n_planes - 1
-// (n_planes even; tl_first < 0 reaches into the lower ghost planes, tl_first + n_planes > Tl into the upper ones).
+// grid = (n_chunks, ceil(n_planes / 16), n_chains).  Updates n_planes local planes (even): the first n_first of
+// them start at tl_first, the rest at tl_second (two wedges next to the slab boundaries in one launch; one range
+// when n_first == n_planes).  Negative plane numbers reach into the lower ghost planes, numbers >= Tl into the
+// upper ones.
 // Lanes 0-15: plane t, row y; lanes 16-31: plane t+1, row y+1 — the same x parity, and each half's inner
 // t-neighbour row sits in the partner half's register window.
 template <bool WILSON, bool COUNT>
 __global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
 k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
-            const uint32_t n_planes, const uint32_t n_chunks, uint16_t* __restrict__ own_base,
+            const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
+            uint16_t* __restrict__ own_base,
             const uint16_t* __restrict__ oth_base, const ChainDev* __restrict__ chains,
             const uint32_t* __restrict__ thr_all, unsigned long long* __restrict__ acc, const uint32_t max_thr) {
     __shared__ unsigned int s_cnt;
@@ -133,7 +137,8 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     const uint32_t y1 = (uint32_t)(((uint64_t)(chunk + 1u) * g.Y) / n_chunks);
     int accepted = 0;
     if (pl0 < n_planes && y0 < y1) {  // warp uniform
-        const uint32_t tl = (uint32_t)tl_first + pl0 + half;     // local plane, modulo 2^32 below the slab
+        // local plane, modulo 2^32 below the slab (n_first is even: a pair never straddles the two ranges)
+        const uint32_t tl = (pl0 < n_first ? (uint32_t)tl_first + pl0 : (uint32_t)tl_second + (pl0 - n_first)) + half;
         const uint32_t tg = (g.t0 + g.T + tl) % g.T;             // global plane: keys, parity and the Wilson sheet
         const bool owned = tl < g.Tl;
         const size_t cbase = (size_t)chain * g.chain_stride;
@@ -318,6 +323,8 @@ struct NarrowArgs {
     uint64_t sweep;
     const uint64_t* ctr;
     int32_t tl_first;
+    uint32_t n_first;     // planes of the first range (== n_planes for one range)
+    int32_t tl_second;
     uint32_t n_planes;
     uint32_t n_chains;
     uint16_t* own;
@@ -381,8 +388,8 @@ inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
     cfg.attrs = attr;
     cfg.numAttrs = a.pdl ? 1 : 0;
 #define LQFT_GO(W, C)                                                                                                  \
-    return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_planes, n_chunks, \
-                              a.own, a.oth, a.chains, a.thr, a.acc, a.max_thr)
+    return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_first, a.tl_second, \
+                              a.n_planes, n_chunks, a.own, a.oth, a.chains, a.thr, a.acc, a.max_thr)
     if (a.wilson) {
         if (a.count) LQFT_GO(true, true); else LQFT_GO(true, false);
     } else {

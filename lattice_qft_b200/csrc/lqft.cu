@@ -193,6 +193,9 @@ struct lqft_handle {
     NarrowPlan narrowp{};
     Geom gn{};                                  // geometry of the narrow arrays: slabs carry a deep halo (ghost > 1)
     uint32_t nvalid = 0;                        // ghost planes per side of the narrow copy that are valid right now
+    struct Wedge { int colour; uint64_t sweep; int32_t lo_first, hi_first; uint32_t n_each; };
+    std::vector<Wedge> wedges;                  // boundary parts of half-sweeps issued underneath an exchange
+    bool exchange_inflight = false;
     uint32_t tl_lo = 0, tl_hi = 0;              // owned planes of the lower / upper neighbour
     bool narrow_active = false;
     uint64_t narrow_segments = 0;
@@ -739,6 +742,18 @@ static inline uint32_t block_for(uint32_t units) {
     return std::min(256u, std::max(32u, b));
 }
 
+// Narrow copy: one half-sweep of colour `colour` over local planes [first, first + n_first) and, if
+// n_second, [second, second + n_second).
+static lqft_status launch_half_narrow(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr, int32_t first,
+                                      uint32_t n_first, int32_t second, uint32_t n_second) {
+    NarrowArgs a{h->gn, colour, sweep, ctr, first, n_first, second, n_first + n_second, h->cfg.n_chains, h->narrow[colour],
+                 h->narrow[colour ^ 1], h->chains_d, h->thr_d, h->acc_d, h->max_thr, h->any_wilson, h->count_accepts,
+                 h->stream, !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
+    CU(narrow_half(h->narrowp, a));
+    h->launches += 1;
+    return LQFT_OK;
+}
+
 // One half-sweep of colour `colour` over local planes tl_first .. tl_first + n_planes - 1.
 static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr,
                                uint32_t tl_first, uint32_t n_planes, cudaStream_t s, bool halo_now = false) {
@@ -754,16 +769,6 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
             k_sweep_generic_f64<false><<<grid, bd, 0, s>>>(g, colour, sweep, ctr, h->field64[colour], h->field64[colour ^ 1],
                                                            h->chains_d, h->beta_d, h->acc_d);
         CU(cudaGetLastError());
-        h->launches += 1;
-        return LQFT_OK;
-    }
-    if (h->narrow_active) {
-        // tl_first / n_planes are reinterpreted: tl_first = planes of ghost zone to include on each side
-        const int32_t extra = (int32_t)tl_first;
-        NarrowArgs a{h->gn, colour, sweep, ctr, -extra, g.Tl + 2u * (uint32_t)extra, h->cfg.n_chains, h->narrow[colour],
-                     h->narrow[colour ^ 1], h->chains_d, h->thr_d, h->acc_d, h->max_thr, h->any_wilson, h->count_accepts, s,
-                     !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
-        CU(narrow_half(h->narrowp, a));
         h->launches += 1;
         return LQFT_OK;
     }
@@ -810,21 +815,33 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
 }
 
 // One full red-black sweep.  `sweep` + (*ctr if ctr) is the RNG sweep counter.
-static lqft_status narrow_exchange(lqft_handle* h);
+static lqft_status narrow_exchange_begin(lqft_handle* h);
+static lqft_status narrow_exchange_end(lqft_handle* h);
 
 static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* ctr) {
     const Geom& g = h->g;
     if (h->narrow_active) {
         // narrow copy: on slabs every half-sweep also updates the ghost planes that still have valid neighbours,
         // and the valid depth shrinks by one; an exchange restores it (kernels_narrow.cuh)
+        const uint32_t depth = h->gn.ghost;
         for (int colour = 0; colour < 2; ++colour) {
-            uint32_t extra = 0;
-            if (h->gn.ghost) {
-                if (h->nvalid == 0) ST(narrow_exchange(h));
-                extra = h->nvalid - 1;
-                h->nvalid -= 1;
+            if (depth == 0) {
+                ST(launch_half_narrow(h, colour, sweep, ctr, 0, g.Tl, 0, 0));
+                continue;
             }
-            ST(launch_half(h, colour, sweep, ctr, extra, g.Tl, h->stream));
+            if (h->nvalid == 0) ST(narrow_exchange_begin(h));
+            const uint32_t extra = h->nvalid - 1;  // ghost planes per side this half-sweep may still update
+            h->nvalid -= 1;
+            if (h->exchange_inflight && h->wedges.size() < kN16Overlap && g.Tl >= 2 * (depth + kN16Overlap + 1)) {
+                // underneath the exchange: planes that need neither the ghost planes nor the planes being sent;
+                // k-th deferred half-sweep: interior [depth + k + 1, Tl - depth - k - 1), wedges of 2 * depth planes
+                const uint32_t k = (uint32_t)h->wedges.size(), a = depth + k + 1;
+                ST(launch_half_narrow(h, colour, sweep, ctr, (int32_t)a, g.Tl - 2 * a, 0, 0));
+                h->wedges.push_back({colour, sweep, -(int32_t)extra, (int32_t)(g.Tl - a), extra + a});
+                continue;
+            }
+            ST(narrow_exchange_end(h));
+            ST(launch_half_narrow(h, colour, sweep, ctr, -(int32_t)extra, g.Tl + 2 * extra, 0, 0));
         }
         return LQFT_OK;
     }
@@ -867,7 +884,10 @@ static lqft_status launch_observe(lqft_handle* h, bool moments) {
     }
     if (h->narrow_active) {
         if (moments) return fail(LQFT_ERR_STATE, "slice moments are not available on the narrow working copy");
-        if (h->gn.ghost && h->nvalid == 0) ST(narrow_exchange(h));  // the last owned plane looks one plane up
+        if (h->gn.ghost) {  // the last owned plane looks one plane up
+            if (h->nvalid == 0) ST(narrow_exchange_begin(h));
+            ST(narrow_exchange_end(h));
+        }
         const uint32_t units = g.plane / 4;
         const uint32_t bd = block_for(units);
         dim3 grid((units + bd - 1) / bd, g.Tl, h->cfg.n_chains);
@@ -908,6 +928,7 @@ static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint
         h->launches += 1;
         return LQFT_OK;
     }
+    if (h->narrow_active) ST(narrow_exchange_end(h));  // the picked site may lie in a wedge that is still behind
     if (h->narrow_active)
         k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(h->gn, (const uint16_t*)h->narrow[0], (const uint16_t*)h->narrow[1],
                                                              h->chains_d, nc, counter, ctr, explicit_site, only_chain, h->shift_d,
@@ -1333,6 +1354,7 @@ static lqft_status narrow_enter(lqft_handle* h, bool* ok) {
 
 static lqft_status narrow_exit(lqft_handle* h) {
     const Geom& g = h->g;
+    ST(narrow_exchange_end(h));
     const uint64_t count = (uint64_t)g.Tl * g.plane;
     dim3 grid((uint32_t)((count / 4 + 255) / 256), h->cfg.n_chains);
     for (int c = 0; c < 2; ++c)
@@ -1345,9 +1367,12 @@ static lqft_status narrow_exit(lqft_handle* h) {
     return LQFT_OK;
 }
 
-// Deep halo exchange of the narrow copy with both neighbours (k_n16_exchange): two phases of the flag protocol.
-static lqft_status narrow_exchange(lqft_handle* h) {
+// Deep halo exchange of the narrow copy with both neighbours (k_n16_exchange, two phases of the flag protocol),
+// issued on the second stream: the caller may keep updating interior planes on the main stream until
+// narrow_exchange_end.
+static lqft_status narrow_exchange_begin(lqft_handle* h) {
     const Geom& gn = h->gn;
+    ST(narrow_exchange_end(h));
     ExchangeArgs a{};
     for (int c = 0; c < 2; ++c) {
         a.mine[c] = h->narrow[c];
@@ -1369,10 +1394,25 @@ static lqft_status narrow_exchange(lqft_handle* h) {
     h->phase += 2;
     const uint64_t n = (uint64_t)a.depth * a.plane / 8;
     dim3 grid((uint32_t)((n + 255) / 256), 4, h->cfg.n_chains);
-    k_n16_exchange<<<grid, 256, 0, h->stream>>>(a);
+    CU(cudaEventRecord(h->ev_bnd, h->stream));
+    CU(cudaStreamWaitEvent(h->comm_stream, h->ev_bnd, 0));
+    k_n16_exchange<<<grid, 256, 0, h->comm_stream>>>(a);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_comm, h->comm_stream));
     h->launches += 1;
     h->nvalid = gn.ghost;
+    h->exchange_inflight = true;
+    return LQFT_OK;
+}
+
+// Join the exchange and catch up, in order, the wedges of the half-sweeps that ran underneath it.
+static lqft_status narrow_exchange_end(lqft_handle* h) {
+    if (!h->exchange_inflight) return LQFT_OK;
+    CU(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    h->exchange_inflight = false;
+    for (const auto& w : h->wedges)
+        ST(launch_half_narrow(h, w.colour, w.sweep, nullptr, w.lo_first, w.n_each, w.hi_first, w.n_each));
+    h->wedges.clear();
     return LQFT_OK;
 }
 
