@@ -41,7 +41,8 @@ constexpr int kN16KcMax = 255;                   // threshold tables up to 256 e
 constexpr uint32_t kN16RowQ = 16;                // uint4 per row of one colour (X = 256)
 
 constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even)
-constexpr uint32_t kN16Overlap = 3;              // half-sweeps whose interior runs underneath an exchange
+constexpr uint32_t kN16ExchangeBlocks = 16;      // per (side, colour, chain)
+constexpr uint32_t kN16Overlap = 1;              // half-sweeps whose interior runs underneath an exchange
 
 // Table entry (i << 1) | coin for d = i - kc: coin 1 proposes +1 (m = d), coin 0 proposes -1 (m = -d);
 // same contents as build_two_sided (kernels_tiled.cuh), interleaved so that the coin can be shifted in.
@@ -215,7 +216,7 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
 //   delivered = "your ghost planes hold my boundary planes" (sent by the last block, release chain as in
 //               k_sweep_stream); the same block then waits for both neighbours' deliveries, so the kernel
 //               completes only when this rank's ghost planes are valid.
-// grid = (ceil(depth * plane / 8 / 256), 4 = side * 2 + colour, n_chains), block = 256.
+// grid = (kN16ExchangeBlocks, 4 = side * 2 + colour, n_chains), block = 256.
 struct ExchangeArgs {
     uint16_t* mine[2];       // my narrow arrays (colour 0, 1)
     uint16_t* lo[2];         // lower neighbour's narrow arrays, as mapped here
@@ -227,28 +228,33 @@ struct ExchangeArgs {
     HaloSync* sync_mine;
     HaloSync* sync_lo;
     HaloSync* sync_hi;
-    unsigned long long ready, delivered;
+    unsigned long long* phase;  // device copy of the handle's phase counter: ready = *phase + 1, delivered = *phase + 2
 };
 
 __global__ void __launch_bounds__(256)
 k_n16_exchange(const ExchangeArgs a) {
+    // the phase lives in device memory so that a captured graph can be replayed; it is advanced by the last
+    // block, after every block has passed the ticket and therefore read it
+    const unsigned long long ready = *reinterpret_cast<const volatile unsigned long long*>(a.phase) + 1ull;
+    const unsigned long long delivered = ready + 1ull;
     const bool first = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     if (first && threadIdx.x == 0) {
-        st_release_sys(&a.sync_lo->from_hi, a.ready);
-        st_release_sys(&a.sync_hi->from_lo, a.ready);
+        st_release_sys(&a.sync_lo->from_hi, ready);
+        st_release_sys(&a.sync_hi->from_lo, ready);
     }
     const uint32_t side = blockIdx.y >> 1, colour = blockIdx.y & 1u, chain = blockIdx.z;
-    if (threadIdx.x == 0) halo_wait(side ? &a.sync_mine->from_hi : &a.sync_mine->from_lo, a.ready, &a.sync_mine->error);
+    if (threadIdx.x == 0) halo_wait(side ? &a.sync_mine->from_hi : &a.sync_mine->from_lo, ready, &a.sync_mine->error);
     __syncthreads();
     const uint64_t n = (uint64_t)a.depth * a.plane / 8;  // uint4 per (side, colour, chain)
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
+    {
         // storage planes: [0, depth) lower ghosts, [depth, depth + Tl) owned, then the upper ghosts
         const uint16_t* src = a.mine[colour] + (size_t)chain * a.stride_mine +
                               (size_t)(side ? a.tl_mine : a.depth) * a.plane;
         uint16_t* dst = side ? a.hi[colour] + (size_t)chain * a.stride_hi
                              : a.lo[colour] + (size_t)chain * a.stride_lo + (size_t)(a.depth + a.tl_lo) * a.plane;
-        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+        // few, long-lived blocks: the kernel shares the GPU with a half-sweep that fills every SM
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+            reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -256,10 +262,11 @@ k_n16_exchange(const ExchangeArgs a) {
         const unsigned int done = atom_add_acq_rel_gpu(&a.sync_mine->ticket, 1u);
         if (done + 1u == total) {
             st_relaxed_gpu(&a.sync_mine->ticket, 0u);
-            st_release_sys(&a.sync_lo->from_hi, a.delivered);
-            st_release_sys(&a.sync_hi->from_lo, a.delivered);
-            halo_wait(&a.sync_mine->from_lo, a.delivered, &a.sync_mine->error);
-            halo_wait(&a.sync_mine->from_hi, a.delivered, &a.sync_mine->error);
+            *a.phase = delivered;
+            st_release_sys(&a.sync_lo->from_hi, delivered);
+            st_release_sys(&a.sync_hi->from_lo, delivered);
+            halo_wait(&a.sync_mine->from_lo, delivered, &a.sync_mine->error);
+            halo_wait(&a.sync_mine->from_hi, delivered, &a.sync_mine->error);
         }
     }
 }

@@ -123,6 +123,7 @@ struct GraphKey {
 struct GraphVal {
     cudaGraphExec_t exec = nullptr;
     uint64_t kernels = 0;
+    uint64_t phases = 0;  // halo phases one replay goes through (deep-halo exchanges of the narrow copy)
 };
 
 struct lqft_handle {
@@ -193,7 +194,8 @@ struct lqft_handle {
     NarrowPlan narrowp{};
     Geom gn{};                                  // geometry of the narrow arrays: slabs carry a deep halo (ghost > 1)
     uint32_t nvalid = 0;                        // ghost planes per side of the narrow copy that are valid right now
-    struct Wedge { int colour; uint64_t sweep; int32_t lo_first, hi_first; uint32_t n_each; };
+    struct Wedge { int colour; uint64_t sweep; const uint64_t* ctr; int32_t lo_first, hi_first; uint32_t n_each; };
+    unsigned long long* phase_d = nullptr;      // device copy of `phase` while a narrow segment runs on a slab
     std::vector<Wedge> wedges;                  // boundary parts of half-sweeps issued underneath an exchange
     bool exchange_inflight = false;
     uint32_t tl_lo = 0, tl_hi = 0;              // owned planes of the lower / upper neighbour
@@ -473,7 +475,7 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
             if (h->peer_base[side][k]) cudaIpcCloseMemHandle(h->peer_base[side][k]);
     }
     cudaFree(h->halo_d);
-    cudaFree(h->narrow[0]); cudaFree(h->narrow[1]); cudaFree(h->ncentre_d); cudaFree(h->nworst_d);
+    cudaFree(h->narrow[0]); cudaFree(h->narrow[1]); cudaFree(h->ncentre_d); cudaFree(h->nworst_d); cudaFree(h->phase_d);
     tiled_release(h->tiled);
     cudaFree(h->field[0]); cudaFree(h->field[1]);
     cudaFree(h->field64[0]); cudaFree(h->field64[1]); cudaFree(h->beta_d); cudaFree(h->offset64_d);
@@ -541,7 +543,12 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
 
     const uint32_t nc = cfg->n_chains;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    {
+        // the second stream carries halo traffic underneath update kernels that fill every SM: highest priority
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, greatest));
+    }
     CU(cudaEventCreate(&h->ev_start));
     CU(cudaEventCreate(&h->ev_stop));
     CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
@@ -592,6 +599,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     if (g.ghost) {
         // deep halo of the narrow copy: as many planes as the thinnest slab allows, at most kN16GhostDepth, even
         uint32_t depth = kN16GhostDepth;
+        if (const char* e = getenv("LQFT_N16_DEPTH")) depth = (uint32_t)atoi(e);  // tuning knob
         for (uint32_t r = 0; r < ws; ++r) {
             uint32_t rt0 = 0, rnt = 0;
             ST(lqft_host_slab(T, ws, r, &rt0, &rnt));
@@ -612,6 +620,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         } else {
             CU(cudaMalloc(&h->ncentre_d, sizeof(int32_t) * nc));
             CU(cudaMalloc(&h->nworst_d, sizeof(uint32_t)));
+            CU(cudaMalloc(&h->phase_d, sizeof(unsigned long long)));
         }
     }
     if (ws > 1) {
@@ -832,12 +841,13 @@ static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* 
             if (h->nvalid == 0) ST(narrow_exchange_begin(h));
             const uint32_t extra = h->nvalid - 1;  // ghost planes per side this half-sweep may still update
             h->nvalid -= 1;
-            if (h->exchange_inflight && h->wedges.size() < kN16Overlap && g.Tl >= 2 * (depth + kN16Overlap + 1)) {
+            static const uint32_t overlap = getenv("LQFT_N16_OVERLAP") ? (uint32_t)atoi(getenv("LQFT_N16_OVERLAP")) : kN16Overlap;
+            if (h->exchange_inflight && h->wedges.size() < overlap && g.Tl >= 2 * (depth + overlap + 1)) {
                 // underneath the exchange: planes that need neither the ghost planes nor the planes being sent;
                 // k-th deferred half-sweep: interior [depth + k + 1, Tl - depth - k - 1), wedges of 2 * depth planes
                 const uint32_t k = (uint32_t)h->wedges.size(), a = depth + k + 1;
                 ST(launch_half_narrow(h, colour, sweep, ctr, (int32_t)a, g.Tl - 2 * a, 0, 0));
-                h->wedges.push_back({colour, sweep, -(int32_t)extra, (int32_t)(g.Tl - a), extra + a});
+                h->wedges.push_back({colour, sweep, ctr, -(int32_t)extra, (int32_t)(g.Tl - a), extra + a});
                 continue;
             }
             ST(narrow_exchange_end(h));
@@ -1348,6 +1358,8 @@ static lqft_status narrow_enter(lqft_handle* h, bool* ok) {
     *ok = worst == 0;
     h->narrow_active = *ok;
     h->nvalid = 0;
+    if (*ok && g.ghost)
+        CU(cudaMemcpyAsync(h->phase_d, &h->phase, sizeof h->phase, cudaMemcpyHostToDevice, h->stream));
     if (*ok) h->narrow_segments += 1;
     return LQFT_OK;
 }
@@ -1389,11 +1401,9 @@ static lqft_status narrow_exchange_begin(lqft_handle* h) {
     a.sync_mine = h->halo_d;
     a.sync_lo = (HaloSync*)h->peer_base[0][2];
     a.sync_hi = (HaloSync*)h->peer_base[1][2];
-    a.ready = h->phase + 1;
-    a.delivered = h->phase + 2;
-    h->phase += 2;
-    const uint64_t n = (uint64_t)a.depth * a.plane / 8;
-    dim3 grid((uint32_t)((n + 255) / 256), 4, h->cfg.n_chains);
+    a.phase = h->phase_d;
+    h->phase += 2;  // host mirror of what the kernel does to *phase_d
+    dim3 grid(kN16ExchangeBlocks, 4, h->cfg.n_chains);
     CU(cudaEventRecord(h->ev_bnd, h->stream));
     CU(cudaStreamWaitEvent(h->comm_stream, h->ev_bnd, 0));
     k_n16_exchange<<<grid, 256, 0, h->comm_stream>>>(a);
@@ -1411,7 +1421,7 @@ static lqft_status narrow_exchange_end(lqft_handle* h) {
     CU(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
     h->exchange_inflight = false;
     for (const auto& w : h->wedges)
-        ST(launch_half_narrow(h, w.colour, w.sweep, nullptr, w.lo_first, w.n_each, w.hi_first, w.n_each));
+        ST(launch_half_narrow(h, w.colour, w.sweep, w.ctr, w.lo_first, w.n_each, w.hi_first, w.n_each));
     h->wedges.clear();
     return LQFT_OK;
 }
@@ -1483,8 +1493,7 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
     const uint64_t cycle = ee / gcd64(ee, ne) * ne;
     // one captured graph = `reps` cycles (about kGraphSteps sweeps); it is replayed while whole periods remain
     constexpr uint64_t kGraphSteps = 32;
-    const bool use_graph = !(h->cfg.flags & LQFT_FLAG_NO_GRAPH) && h->g.ghost == 0 && cycle <= 64 &&
-                           s->n_steps >= 2 * cycle && s->n_steps >= 8;
+    const bool graph_ok = !(h->cfg.flags & LQFT_FLAG_NO_GRAPH) && cycle <= 64 && s->n_steps >= 2 * cycle && s->n_steps >= 8;
 
     CU(cudaEventRecord(h->ev_start, h->stream));
     uint64_t step = s->first_step;
@@ -1521,6 +1530,9 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
             else narrow = false;
         }
         if (!h->narrow_active) ST(refresh_ghosts(h));  // a narrow segment leaves the i32 ghost planes stale
+        // slabs replay graphs only on the narrow copy: its halo phases live in device memory (k_n16_exchange)
+        const bool use_graph = graph_ok && (h->g.ghost == 0 || h->narrow_active);
+        const bool deep = h->narrow_active && h->gn.ghost != 0;
         if (use_graph && step < seg_end) {
             while (step < seg_end && step % cycle != 0) {
                 ST(launch_step(h, s, step, step, nullptr));
@@ -1534,7 +1546,13 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
                 GraphKey key{s->energy_every, s->normalize_every, (uint32_t)period, h->count_accepts, h->narrow_active};
                 auto it = h->graphs.find(key);
                 if (it == h->graphs.end()) {
-                    // capture one period; every kernel reads the sweep counter from device memory
+                    // capture one period; every kernel reads the sweep counter from device memory.  On slabs a
+                    // period starts with an exchange and ends with all wedges caught up, whatever came before.
+                    if (deep) {
+                        ST(narrow_exchange_end(h));
+                        h->nvalid = 0;
+                    }
+                    const unsigned long long phase_before = h->phase;
                     const uint64_t before = h->launches;
                     lqft_schedule rel = *s;
                     rel.sweep_base = 0;
@@ -1542,11 +1560,14 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
                     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                     lqft_status st = LQFT_OK;
                     for (uint64_t i = 0; i < period && st == LQFT_OK; ++i) st = launch_step(h, &rel, i, i, h->sweep_ctr_d);
+                    if (st == LQFT_OK && deep) st = narrow_exchange_end(h);  // joins the second stream
                     if (st == LQFT_OK) {
                         k_tick<<<1, 1, 0, h->stream>>>(h->sweep_ctr_d, period);
                         h->launches += 1;
                     }
                     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                    h->wedges.clear();
+                    h->exchange_inflight = false;
                     if (st != LQFT_OK) {
                         if (graph) cudaGraphDestroy(graph);
                         return st;
@@ -1554,16 +1575,23 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
                     if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
                     GraphVal val;
                     val.kernels = h->launches - before;
+                    val.phases = h->phase - phase_before;
                     h->launches = before;
+                    h->phase = phase_before;
                     ce = cudaGraphInstantiate(&val.exec, graph, 0);
                     cudaGraphDestroy(graph);
                     if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
                     it = h->graphs.emplace(key, val).first;
                 }
+                if (deep) {
+                    ST(narrow_exchange_end(h));
+                    h->nvalid = 0;  // what every replay ends with
+                }
                 const uint64_t base = s->sweep_base + step;
                 CU(cudaMemcpyAsync(h->sweep_ctr_d, &base, sizeof base, cudaMemcpyHostToDevice, h->stream));
                 for (uint64_t c = 0; c < n_periods; ++c) CU(cudaGraphLaunch(it->second.exec, h->stream));
                 h->launches += it->second.kernels * n_periods;
+                h->phase += it->second.phases * n_periods;
                 step += n_periods * period;
             }
         }

@@ -35,6 +35,7 @@ def check(size, beta, seed, wilson, n_sweeps, flags=0):
     eng.upload(0, D.scatter_slab(full, X, Y, T, rank, ws))
     acc = eng.sweep(0, n_sweeps, want_accepted=True)[0]
     e_obs, e_int, _ = eng.run(12, first_step=0, sweep_base=n_sweeps, energy_every=4, normalize_every=10)
+    g_obs, g_int, _ = eng.run(24, first_step=0, sweep_base=n_sweeps + 12, energy_every=2, normalize_every=4)  # graph replay
     e_now = eng.energy()
     s_now = eng.action()
     s1, s2 = eng.slice_moments(0)
@@ -49,6 +50,8 @@ def check(size, beta, seed, wilson, n_sweeps, flags=0):
         ref.upload(0, full)
         racc = ref.sweep(0, n_sweeps, want_accepted=True)[0]
         r_obs, r_int, _ = ref.run(12, first_step=0, sweep_base=n_sweeps, energy_every=4, normalize_every=10)
+        q_obs, q_int, _ = ref.run(24, first_step=0, sweep_base=n_sweeps + 12, energy_every=2, normalize_every=4)
+        assert (q_int == g_int).all() and (q_obs == g_obs).all()
         assert int(acc_t.item()) == racc, (int(acc_t.item()), racc)
         assert (r_int == e_int).all() and (r_obs == e_obs).all()
         assert (ref.energy()[0] == e_now[0]).all() and (ref.action()[0] == s_now[0]).all()

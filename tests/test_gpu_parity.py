@@ -209,6 +209,15 @@ def test_self_halo_slab_path_on_one_gpu(size, wilson):
         s_int = int(eng.action()[0][0])
         eng.synchronize()
         assert eng.narrow_segments() == (2 if X == 256 else 0)
+        # a schedule short-cycled enough for graph replay (on slabs: narrow copy only, exchanges inside the graph)
+        want3 = want.copy()
+        we3, _ = O.run(lat, want3, beta, seed, 16, 0, 40, 2, 4, order=1, wilson=wil)
+        e3, _, _ = eng.run(40, sweep_base=16, energy_every=2, normalize_every=4)
+        got3 = eng.download(0)
+        e_int3 = int(eng.energy()[0][0])
+    assert (e3[0] == we3).all()
+    assert (got3 == want3).all(), f"{int((got3 != want3).sum())} sites differ after the graph-replayed run"
+    assert e_int3 == O.integer_energy(lat, want3)[0]
     assert acc == wacc
     assert (e_obs[0] == we).all()
     assert (got == want).all(), f"{int((got != want).sum())} sites differ"
