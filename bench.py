@@ -40,11 +40,11 @@ METRIC = "site updates/sec"
 UNIT = "site-updates/s"
 
 
-def measured_traffic(lattice):
+def measured_traffic(lattice, kernel):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            t = json.load(fh).get("x".join(str(v) for v in lattice))
+            t = json.load(fh).get("x".join(str(v) for v in lattice) + ":" + kernel)
         return (t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]) if t else (None, None)
     except Exception:
         return None, None
@@ -227,7 +227,8 @@ def workload_config(n_gpus: int):
         "workload": f"{X}x{Y}x{t} periodic lattice, 1 chain, i32 heights, beta={BETA}, red-black Metropolis, "
                     f"{SWEEPS_PER_STEP} sweeps per step, pre-thermalised {THERMALISE} sweeps from seeded hot start",
         "lattice": [X, Y, t], "sweeps_per_step": SWEEPS_PER_STEP, "beta": BETA,
-        "decomposition": "none" if n_gpus == 1 else f"t-slabs of {T_PER_GPU} planes per GPU, halo exchange per colour",
+        "decomposition": "none" if n_gpus == 1 else f"t-slabs of {T_PER_GPU} planes per GPU; 16-bit working copy with an 8-plane "
+                         "deep halo exchanged over peer memory once per 8 half-sweeps",
         "l2": "L2 flushed (256 MiB write) between timed steps; the 64 MiB/GPU field itself is L2-resident by nature",
     }
 
@@ -321,6 +322,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = eng.kernel_launches() - launches0
+    narrow_segments = eng.narrow_segments()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -366,7 +368,10 @@ def main():
         per_launch_s = (ms * 1e-3) / n_sweep_launches
         alg_bytes_per_launch = BYTES_PER_UPDATE * (n_local / 2)
         achieved = alg_bytes_per_launch / per_launch_s / 1e9
-        traffic, traffic_src = measured_traffic([X, Y, T_PER_GPU]) if world == 1 else (None, None)
+        # which kernel family did the sweeps: the 16-bit working copy (kernels_narrow.cuh) or the i32 streaming kernel
+        kernel = "k_sweep_n16" if narrow_segments > 0 else "k_sweep_stream"
+        moved = (4 if narrow_segments > 0 else 8) * (n_local / 2)
+        traffic, traffic_src = measured_traffic([X, Y, T_PER_GPU], kernel) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -379,8 +384,14 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": "half-sweep (one colour) of the red-black Metropolis sweep",
+                         "kernel": f"{kernel}: half-sweep (one colour) of the red-black Metropolis sweep",
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                         "algorithmic_bytes_note": "SURVEY.md 8(d): 8 B per update = one i32 read + one i32 write, the "
+                                                   "reference's storage type; `achieved` and `frac` use this figure",
+                         "kernel_bytes_per_launch": moved,
+                         "kernel_bytes_note": "own-colour heights the kernel itself must read + write: 4 B per update on "
+                                              "the 16-bit working copy, 8 B on i32; frac_kernel_bytes = that / time / peak",
+                         "frac_kernel_bytes": moved / per_launch_s / 1e9 / peak,
                          "avg_launch_us": per_launch_s * 1e6},
         }
         if other:
