@@ -113,17 +113,19 @@ __device__ __forceinline__ uint4 n16_wilson(uint32_t k0, uint32_t p, int sgn, ui
 // upper ones.
 // Lanes 0-15: plane t, row y; lanes 16-31: plane t+1, row y+1 — the same x parity, and each half's inner
 // t-neighbour row sits in the partner half's register window.
-template <bool WILSON, bool COUNT>
+// SINGLE: one chain, its parameters arrive as a kernel argument: the Philox key then lives in the parameter bank
+// and the ten round keys derived from it in uniform registers, instead of twenty vector registers per thread.
+template <bool WILSON, bool COUNT, bool SINGLE>
 __global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
 k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
             const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
             uint16_t* __restrict__ own_base,
-            const uint16_t* __restrict__ oth_base, const ChainDev* __restrict__ chains,
+            const uint16_t* __restrict__ oth_base, const ChainDev* __restrict__ chains, const ChainDev chain0,
             const uint32_t* __restrict__ thr_all, unsigned long long* __restrict__ acc, const uint32_t max_thr) {
     __shared__ unsigned int s_cnt;
     pdl_launch_dependents();
-    const uint32_t chain = blockIdx.z;
-    const ChainDev cd = chains[chain];
+    const uint32_t chain = SINGLE ? 0u : blockIdx.z;
+    const ChainDev cd = SINGLE ? chain0 : chains[chain];
     if (COUNT && threadIdx.x == 0) s_cnt = 0;
     const int kc = build_interleaved(s_n16_tab, thr_all + (size_t)chain * kThrStride, max_thr);
     const uint32_t c_off = (uint32_t)((kc - 24576) & 0xffff) * 0x10001u, c_max = (uint32_t)(2 * kc) * 0x10001u;
@@ -133,28 +135,40 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t half = lane >> 4, l16 = lane & 15u;
     const uint32_t chunk = blockIdx.x;
-    const uint32_t pl0 = blockIdx.y * (2u * kN16Warps) + 2u * warp;  // lower plane of this warp's pair within the range
-    const uint32_t y0 = (uint32_t)(((uint64_t)chunk * g.Y) / n_chunks);
-    const uint32_t y1 = (uint32_t)(((uint64_t)(chunk + 1u) * g.Y) / n_chunks);
+    const uint32_t pl0_raw = blockIdx.y * (2u * kN16Warps) + 2u * warp;  // lower plane of this warp's pair within the range
+    const uint32_t y0 = chunk * g.Y / n_chunks, y1 = (chunk + 1u) * g.Y / n_chunks;  // n_chunks <= Y / 2, Y < 2^24
     int accepted = 0;
-    if (pl0 < n_planes && y0 < y1) {  // warp uniform
+    // Warps past the end of the plane range (last group of a range that is no multiple of 16 planes) walk pair 0
+    // with their stores switched off instead of branching around the body: the condition is warp uniform, but
+    // ptxas cannot know that, and only in control flow it knows to be convergent does it keep the Philox round
+    // keys in uniform registers and the shuffles free of divergence handling.  n_chunks <= Y: no empty chunks.
+    const bool live = pl0_raw < n_planes;
+    const uint32_t pl0 = live ? pl0_raw : 0u;  // addresses and keys only: see `p` below
+    {
         // local plane, modulo 2^32 below the slab (n_first is even: a pair never straddles the two ranges)
-        const uint32_t tl = (pl0 < n_first ? (uint32_t)tl_first + pl0 : (uint32_t)tl_second + (pl0 - n_first)) + half;
+        const uint32_t tl_first_of_pair = pl0 < n_first ? (uint32_t)tl_first + pl0 : (uint32_t)tl_second + (pl0 - n_first);
+        const uint32_t tl = tl_first_of_pair + half;
         const uint32_t tg = (g.t0 + g.T + tl) % g.T;             // global plane: keys, parity and the Wilson sheet
-        const bool owned = tl < g.Tl;
-        const size_t cbase = (size_t)chain * g.chain_stride;
+        const bool owned = live && tl < g.Tl;
         const uint32_t planeq = g.Y * kN16RowQ;
-        // offsets in uint4 units from the chain's array base
-        const uint32_t b_own = plane_self(g, tl) * planeq + l16;
-        const uint32_t b_out = (half ? plane_above(g, tl) : plane_below(g, tl)) * planeq + l16;
-        uint4* const q_own = reinterpret_cast<uint4*>(own_base + cbase);
-        const uint4* const q_oth = reinterpret_cast<const uint4*>(oth_base + cbase);
+        // offsets in uint4 units from the array bases, chain included (narrow_geometry_ok: the arrays stay below
+        // 2^32 uint4): the bases themselves then come straight from the parameter bank, not from registers
+        const uint32_t cq = chain * (uint32_t)(g.chain_stride / 8);
+        const uint32_t b_own = cq + plane_self(g, tl) * planeq + l16;
+        const uint32_t b_out = cq + (half ? plane_above(g, tl) : plane_below(g, tl)) * planeq + l16;
+        uint4* const q_own = reinterpret_cast<uint4*>(own_base);
+        const uint4* const q_oth = reinterpret_cast<const uint4*>(oth_base);
         const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
         uint32_t y = y0 + half;
         if (y == g.Y) y = 0;  // this lane's first row
         const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
         uint4 wa = __ldg(q_oth + (b_own + ym * kN16RowQ)), wb = __ldg(q_oth + (b_own + y * kN16RowQ)), wc;
-        uint32_t p = (y + tg + (uint32_t)colour) & 1u;  // x parity of this lane's row; the same in both halves (T is even)
+        // x parity of the lower half's row; the upper half (row + 1, plane + 1) has the same.  Written without any
+        // lane-dependent term (T is even, so the wrap of tg does not matter) to keep the branch on it uniform.
+        // Nor any select on the plane number: ptxas treats threadIdx.x >> 5 as warp uniform, but not what a
+        // comparison on it selects.  The second range starts at the parity the first one would have continued
+        // with (launch_sweep: Tl is even), so tl_first + pl0_raw has the right parity in both.
+        uint32_t p = (y0 + g.t0 + (uint32_t)tl_first + pl0_raw + (uint32_t)colour) & 1u;
         const uint32_t src_r = (lane & 16u) | ((lane + 1u) & 15u), src_l = (lane & 16u) | ((lane - 1u) & 15u);
         const uint32_t grp_base = tg * g.Y * 32u + l16 * 2u;  // Philox counter word 0 of this thread's first group at y = 0
         const bool wil_plane = WILSON && tg < cd.wil_h;
@@ -190,7 +204,7 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
             w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, to, ti, edge, r0, r1, c_off, c_max, woff, acc_row);      \
         }                                                                                                                \
         if (COUNT) accepted += owned ? acc_row : 0;  /* ghost planes are somebody else's sites */                        \
-        *po = w;                                                                                                         \
+        if (live) *po = w;                                                                                               \
         y = yn;                                                                                                          \
         p ^= 1u;                                                                                                         \
     }
@@ -337,6 +351,7 @@ struct NarrowArgs {
     uint16_t* own;
     const uint16_t* oth;
     const ChainDev* chains;
+    ChainDev chain0;      // host copy of chain 0's parameters (used when n_chains == 1)
     const uint32_t* thr;
     unsigned long long* acc;
     uint32_t max_thr;
@@ -345,16 +360,17 @@ struct NarrowArgs {
     bool pdl;
 };
 
-inline bool narrow_geometry_ok(const Geom& g, uint32_t max_thr) {
+inline bool narrow_geometry_ok(const Geom& g, uint32_t max_thr, uint32_t n_chains) {
     return g.X == 256 && g.Tl >= 2 && g.Tl % 2 == 0 && max_thr <= (uint32_t)kN16KcMax + 1 &&
-           (uint64_t)g.plane / 8 * (g.Tl + 2 * kN16GhostDepth) < (1ull << 32) && (uint64_t)g.T * g.Y * 32u < (1ull << 32);
+           (uint64_t)g.plane / 8 * (g.Tl + 2 * kN16GhostDepth) * n_chains < (1ull << 32) &&
+           (uint64_t)g.T * g.Y * 32u < (1ull << 32);
 }
 
-inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, int sm_count, uint32_t max_thr, bool force_off) {
+inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, uint32_t n_chains, int sm_count, uint32_t max_thr, bool force_off) {
     p.enabled = false;
-    if (force_off || !narrow_geometry_ok(g, max_thr)) return cudaSuccess;
+    if (force_off || !narrow_geometry_ok(g, max_thr, n_chains)) return cudaSuccess;
     p.sm_count = sm_count;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<false, false>, kN16Threads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<false, false, true>, kN16Threads, 0);
     if (e != cudaSuccess) return e;
     p.enabled = p.blocks_per_sm > 0;
     return cudaSuccess;
@@ -394,13 +410,20 @@ inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = a.pdl ? 1 : 0;
-#define LQFT_GO(W, C)                                                                                                  \
-    return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_first, a.tl_second, \
-                              a.n_planes, n_chunks, a.own, a.oth, a.chains, a.thr, a.acc, a.max_thr)
+#define LQFT_GO(W, C, S)                                                                                                  \
+    return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C, S>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_first, a.tl_second, \
+                              a.n_planes, n_chunks, a.own, a.oth, a.chains, a.chain0, a.thr, a.acc, a.max_thr)
+    if (a.n_chains == 1) {
+        if (a.wilson) {
+            if (a.count) LQFT_GO(true, true, true); else LQFT_GO(true, false, true);
+        } else {
+            if (a.count) LQFT_GO(false, true, true); else LQFT_GO(false, false, true);
+        }
+    }
     if (a.wilson) {
-        if (a.count) LQFT_GO(true, true); else LQFT_GO(true, false);
+        if (a.count) LQFT_GO(true, true, false); else LQFT_GO(true, false, false);
     } else {
-        if (a.count) LQFT_GO(false, true); else LQFT_GO(false, false);
+        if (a.count) LQFT_GO(false, true, false); else LQFT_GO(false, false, false);
     }
 #undef LQFT_GO
     return cudaGetLastError();

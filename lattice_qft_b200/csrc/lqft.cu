@@ -245,7 +245,7 @@ static lqft_status upload_params(lqft_handle* h) {
         CU(cudaFuncSetAttribute(k_run_resident<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU(cudaFuncSetAttribute(k_run_resident<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
-    CU(narrow_prepare(h->narrowp, h->g, h->sm_count, h->max_thr,
+    CU(narrow_prepare(h->narrowp, h->g, nc, h->sm_count, h->max_thr,
                       !h->narrow[0] || h->resident_ok || !h->streamp.enabled || (h->g.ghost != 0 && !h->p2p)));
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
@@ -610,7 +610,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         h->gn.ghost = std::max(1u, depth & ~1u);
         h->gn.chain_stride = (uint64_t)g.plane * (g.Tl + 2 * h->gn.ghost);
     }
-    if (!h->is64 && !(cfg->flags & no_narrow) && narrow_geometry_ok(g, 2)) {
+    if (!h->is64 && !(cfg->flags & no_narrow) && narrow_geometry_ok(g, 2, nc)) {
         // 16-bit working copy (+50 % field memory); without it the i32 kernels do all the work
         const size_t nbytes = sizeof(uint16_t) * h->gn.chain_stride * nc;
         if (cudaMalloc(&h->narrow[0], nbytes) != cudaSuccess || cudaMalloc(&h->narrow[1], nbytes) != cudaSuccess) {
@@ -756,7 +756,7 @@ static inline uint32_t block_for(uint32_t units) {
 static lqft_status launch_half_narrow(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr, int32_t first,
                                       uint32_t n_first, int32_t second, uint32_t n_second) {
     NarrowArgs a{h->gn, colour, sweep, ctr, first, n_first, second, n_first + n_second, h->cfg.n_chains, h->narrow[colour],
-                 h->narrow[colour ^ 1], h->chains_d, h->thr_d, h->acc_d, h->max_thr, h->any_wilson, h->count_accepts,
+                 h->narrow[colour ^ 1], h->chains_d, h->chains_h[0], h->thr_d, h->acc_d, h->max_thr, h->any_wilson, h->count_accepts,
                  h->stream, !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
     CU(narrow_half(h->narrowp, a));
     h->launches += 1;
