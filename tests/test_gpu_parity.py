@@ -226,6 +226,34 @@ def test_self_halo_slab_path_on_one_gpu(size, wilson):
     assert e_int == O.integer_energy(lat, want)[0] and float(s_int) == O.float_action(lat, want)
 
 
+def test_self_halo_many_chains_deep_halo():
+    """Three chains with different couplings and Wilson sheets on a self-neighbouring slab (narrow copy, deep halo,
+    exchange per chain) equal three single-chain runs on the plain periodic lattice."""
+    X, Y, T = 256, 4, 32
+    betas = [0.21, 0.25, 0.3]
+    v0 = [seeded_field(X * Y * T, seed=70 + c) for c in range(3)]
+    single = []
+    for c in range(3):
+        with Engine(X, Y, T, flags=_lib.FLAG_NO_NARROW | _lib.FLAG_NO_RESIDENT) as eng:
+            eng.set_chain(0, betas[c], 300 + c, 40 * c, 5 * c)
+            eng.upload(0, v0[c])
+            acc = eng.sweep(0, 6, want_accepted=True)[0]
+            e, _, _ = eng.run(20, sweep_base=6, energy_every=5, normalize_every=10)
+            single.append((acc, e[0].copy(), eng.download(0)))
+    with Engine(X, Y, T, n_chains=3, flags=_lib.FLAG_SELF_HALO) as eng:
+        for c in range(3):
+            eng.set_chain(c, betas[c], 300 + c, 40 * c, 5 * c)
+            eng.upload(c, v0[c])
+        acc = eng.sweep(0, 6, want_accepted=True)
+        e, _, _ = eng.run(20, sweep_base=6, energy_every=5, normalize_every=10)
+        assert eng.narrow_segments() == 2
+        for c in range(3):
+            assert acc[c] == single[c][0]
+            assert (e[c] == single[c][1]).all()
+            assert (eng.download(c) == single[c][2]).all()
+        eng.synchronize()
+
+
 def test_hot_start_matches_oracle():
     with Engine(16, 8, 4) as eng:
         eng.set_chain(0, 0.2, 99)
