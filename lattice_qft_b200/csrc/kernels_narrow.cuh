@@ -1,4 +1,4 @@
-// kernels_narrow.cuh — red-black Metropolis half-sweep on 16-bit heights (X = 256).
+// kernels_narrow.cuh — red-black Metropolis half-sweep on 16-bit heights (X = 256; wider rows: k_sweep_n16w).
 //
 // The reference keeps heights in i32 (Field<i32>, fields.rs:63-67) and so does the ABI; between API calls the
 // device field is i32 too.  Inside lqft_run / lqft_sweep the engine may hold a *narrow* working copy instead:
@@ -165,9 +165,10 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         uint4 wa = __ldg(q_oth + (b_own + ym * kN16RowQ)), wb = __ldg(q_oth + (b_own + y * kN16RowQ)), wc;
         // x parity of the lower half's row; the upper half (row + 1, plane + 1) has the same.  Written without any
         // lane-dependent term (T is even, so the wrap of tg does not matter) to keep the branch on it uniform.
-        // Nor any select on the plane number: ptxas treats threadIdx.x >> 5 as warp uniform, but not what a
-        // comparison on it selects.  The second range starts at the parity the first one would have continued
-        // with (launch_sweep: Tl is even), so tl_first + pl0_raw has the right parity in both.
+        // Nor any select on the plane number, nor the warp index itself: ptxas does not know that threadIdx.x >> 5 is
+        // warp uniform.  pl0_raw = 16 blockIdx.y + 2 warp is even, so the warp drops out of the parity altogether.
+        // The second range starts at the parity the first one would have continued with (launch_sweep: Tl is
+        // even), so tl_first + pl0_raw has the right parity in both.
         uint32_t p = (y0 + g.t0 + (uint32_t)tl_first + pl0_raw + (uint32_t)colour) & 1u;
         const uint32_t src_r = (lane & 16u) | ((lane + 1u) & 15u), src_l = (lane & 16u) | ((lane - 1u) & 15u);
         const uint32_t grp_base = tg * g.Y * 32u + l16 * 2u;  // Philox counter word 0 of this thread's first group at y = 0
@@ -218,6 +219,117 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
             if (--n == 0) break;
         }
 #undef LQFT_N16_STEP
+    }
+    if (COUNT)
+        block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
+}
+
+// ---- wider rows: X = 512 (SEGS = 1) and X = 1024 (SEGS = 2) ---------------------------------------------------
+// A warp is one 256-position segment of a row of ONE plane (no plane pairing: both t-neighbour rows are loaded);
+// with two segments the x-neighbour across the segment edge is one predicated 4-byte load.  Everything else —
+// packed sums, clamp, table, Philox keying, plane ranges, surplus warps — as in k_sweep_n16.
+// grid = (n_chunks * SEGS, ceil(n_planes / 8), n_chains).
+template <int SEGS, bool WILSON, bool COUNT, bool SINGLE>
+__global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
+k_sweep_n16w(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
+             const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
+             uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
+             const ChainDev* __restrict__ chains, const ChainDev chain0, const uint32_t* __restrict__ thr_all,
+             unsigned long long* __restrict__ acc, const uint32_t max_thr) {
+    constexpr uint32_t ROWQ = 32u * SEGS;  // uint4 per row of one colour
+    __shared__ unsigned int s_cnt;
+    pdl_launch_dependents();
+    const uint32_t chain = SINGLE ? 0u : blockIdx.z;
+    const ChainDev cd = SINGLE ? chain0 : chains[chain];
+    if (COUNT && threadIdx.x == 0) s_cnt = 0;
+    const int kc = build_interleaved(s_n16_tab, thr_all + (size_t)chain * kThrStride, max_thr);
+    const uint32_t c_off = (uint32_t)((kc - 24576) & 0xffff) * 0x10001u, c_max = (uint32_t)(2 * kc) * 0x10001u;
+    pdl_wait();
+    if (ctr) sweep += *ctr;
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t seg = SEGS > 1 ? blockIdx.x % SEGS : 0u, chunk = blockIdx.x / SEGS;
+    // Blocks 2m and 2m+1 share 16 consecutive planes: the even ones go to block 2m, the odd ones to 2m+1.  All
+    // warps of a block then work on planes of one parity, and the x parity of their rows depends on blockIdx only:
+    // ptxas has to see that the branch on it is uniform (it does not know that threadIdx.x >> 5 is).
+    const uint32_t pl_raw = (blockIdx.y >> 1) * (2u * kN16Warps) + 2u * warp + (blockIdx.y & 1u);
+    const uint32_t y0 = chunk * g.Y / n_chunks, y1 = (chunk + 1u) * g.Y / n_chunks;
+    int accepted = 0;
+    const bool live = pl_raw < n_planes;              // surplus warps: plane 0 of the range, stores off (see k_sweep_n16)
+    const uint32_t pl = live ? pl_raw : 0u;
+    {
+        const uint32_t tl = pl < n_first ? (uint32_t)tl_first + pl : (uint32_t)tl_second + (pl - n_first);
+        const uint32_t tg = (g.t0 + g.T + tl) % g.T;
+        const bool owned = live && tl < g.Tl;
+        const uint32_t kq = seg * 32u + lane;          // uint4 column of this thread within the row
+        const uint32_t planeq = g.Y * ROWQ;
+        const uint32_t cq = chain * (uint32_t)(g.chain_stride / 8);
+        const uint32_t r_own = cq + plane_self(g, tl) * planeq;  // row 0 of this plane
+        const uint32_t b_own = r_own + kq;
+        const uint32_t b_ta = cq + plane_above(g, tl) * planeq + kq, b_tb = cq + plane_below(g, tl) * planeq + kq;
+        uint4* const q_own = reinterpret_cast<uint4*>(own_base);
+        const uint4* const q_oth = reinterpret_cast<const uint4*>(oth_base);
+        const uint32_t* const w_oth = reinterpret_cast<const uint32_t*>(oth_base);
+        // 32-bit word of the other-colour row that holds the x neighbour across the segment edge (SEGS > 1):
+        // first word of the column to the right / last word of the column to the left, periodic in the row
+        const uint32_t e_right = (r_own + (kq + 1u) % ROWQ) * 4u, e_left = (r_own + (kq + ROWQ - 1u) % ROWQ) * 4u + 3u;
+        const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
+        uint32_t y = y0;
+        const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
+        uint4 wa = __ldg(q_oth + (b_own + ym * ROWQ)), wb = __ldg(q_oth + (b_own + y * ROWQ)), wc;
+        // parity from threadIdx.x >> 5 arithmetic only (see k_sweep_n16); the second range continues the first one's
+        uint32_t p = (y0 + g.t0 + (uint32_t)tl_first + (blockIdx.y & 1u) + (uint32_t)colour) & 1u;
+        const uint32_t src_r = (lane + 1u) & 31u, src_l = (lane - 1u) & 31u;
+        const uint32_t grp_base = tg * g.Y * (64u * SEGS) + kq * 2u;
+        const bool wil_plane = WILSON && tg < cd.wil_h;
+        const uint32_t y_one = 1u % g.Y;
+        uint32_t n = y1 - y0;
+#define LQFT_N16W_STEP(OM, OC, ON)                                                                                       \
+    {                                                                                                                    \
+        const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;                                                                  \
+        uint4* const po = q_own + (b_own + y * ROWQ);                                                                    \
+        const uint4 v = *po;                                                                                             \
+        ON = __ldg(q_oth + (b_own + yn * ROWQ));                                                                         \
+        const uint4 ta = __ldg(q_oth + (b_ta + y * ROWQ));                                                               \
+        const uint4 tb = __ldg(q_oth + (b_tb + y * ROWQ));                                                               \
+        uint32_t e_ld = 0;                                                                                               \
+        const bool e_lane = SEGS > 1 && (p ? lane == 31u : lane == 0u);                                                  \
+        if (SEGS > 1) {                                                                                                  \
+            if (e_lane) e_ld = __ldg(w_oth + ((p ? e_right : e_left) + y * (ROWQ * 4u)));                                \
+        }                                                                                                                \
+        const uint32_t grp = grp_base + y * (64u * SEGS);                                                                \
+        const u32x4 r0 = philox4x32_rk(grp, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);             \
+        const u32x4 r1 = philox4x32_rk(grp + 1u, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);        \
+        uint4 woff = make_uint4(0, 0, 0, 0);                                                                             \
+        if (WILSON) {                                                                                                    \
+            if (wil_plane && (y == 0u || y == y_one))                                                                    \
+                woff = n16_wilson(8u * kq, p, (y == 0u ? 1 : 0) - (y == y_one ? 1 : 0), cd.wil_w);                       \
+        }                                                                                                                \
+        uint4 w;                                                                                                         \
+        int acc_row = 0;                                                                                                 \
+        if (p) {                                                                                                         \
+            uint32_t edge = __shfl_sync(0xffffffffu, OC.x, src_r);                                                       \
+            if (SEGS > 1) edge = e_lane ? e_ld : edge;                                                                   \
+            w = n16_row_update<1, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, c_off, c_max, woff, acc_row);      \
+        } else {                                                                                                         \
+            uint32_t edge = __shfl_sync(0xffffffffu, OC.w, src_l);                                                       \
+            if (SEGS > 1) edge = e_lane ? e_ld : edge;                                                                   \
+            w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, c_off, c_max, woff, acc_row);      \
+        }                                                                                                                \
+        if (COUNT) accepted += owned ? acc_row : 0;                                                                      \
+        if (live) *po = w;                                                                                               \
+        y = yn;                                                                                                          \
+        p ^= 1u;                                                                                                         \
+    }
+        for (;;) {
+            LQFT_N16W_STEP(wa, wb, wc)
+            if (--n == 0) break;
+            LQFT_N16W_STEP(wb, wc, wa)
+            if (--n == 0) break;
+            LQFT_N16W_STEP(wc, wa, wb)
+            if (--n == 0) break;
+        }
+#undef LQFT_N16W_STEP
     }
     if (COUNT)
         block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
@@ -334,6 +446,7 @@ __global__ void k_narrow_begin(const int32_t* __restrict__ offset, int32_t* __re
 // ---- host side ----------------------------------------------------------------------------------------------
 struct NarrowPlan {
     bool enabled = false;
+    int segs = 0;          // 0: X = 256 (k_sweep_n16, two planes per warp); 1, 2: X = 512, 1024 (k_sweep_n16w)
     int blocks_per_sm = 0;
     int sm_count = 0;
 };
@@ -361,16 +474,21 @@ struct NarrowArgs {
 };
 
 inline bool narrow_geometry_ok(const Geom& g, uint32_t max_thr, uint32_t n_chains) {
-    return g.X == 256 && g.Tl >= 2 && g.Tl % 2 == 0 && max_thr <= (uint32_t)kN16KcMax + 1 &&
-           (uint64_t)g.plane / 8 * (g.Tl + 2 * kN16GhostDepth) * n_chains < (1ull << 32) &&
-           (uint64_t)g.T * g.Y * 32u < (1ull << 32);
+    return (g.X == 256 || g.X == 512 || g.X == 1024) && g.Tl >= 2 && g.Tl % 2 == 0 &&
+           max_thr <= (uint32_t)kN16KcMax + 1 &&
+           (uint64_t)g.plane / 8 * (g.Tl + 2 * kN16GhostDepth) * n_chains < (1ull << 30) &&  // uint4 and word offsets in 32 bits
+           (uint64_t)g.T * g.Y * (g.X / 8) < (1ull << 32);
 }
 
 inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, uint32_t n_chains, int sm_count, uint32_t max_thr, bool force_off) {
     p.enabled = false;
     if (force_off || !narrow_geometry_ok(g, max_thr, n_chains)) return cudaSuccess;
     p.sm_count = sm_count;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<false, false, true>, kN16Threads, 0);
+    p.segs = g.X == 256 ? 0 : (int)(g.X / 512);
+    cudaError_t e;
+    if (p.segs == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<false, false, true>, kN16Threads, 0);
+    else if (p.segs == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16w<1, false, false, true>, kN16Threads, 0);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16w<2, false, false, true>, kN16Threads, 0);
     if (e != cudaSuccess) return e;
     p.enabled = p.blocks_per_sm > 0;
     return cudaSuccess;
@@ -380,7 +498,8 @@ inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, uint32_t n_chain
 // the per-chunk prologue is worth about two rows here).
 inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_planes, uint32_t n_chains) {
     const uint64_t slots = (uint64_t)p.sm_count * p.blocks_per_sm;
-    const uint64_t base = (uint64_t)((n_planes + 2 * kN16Warps - 1) / (2 * kN16Warps)) * n_chains;
+    // blocks per chunk: 16 planes per block (X = 256), or two blocks of 8 per 16 planes times the row segments
+    const uint64_t base = (uint64_t)((n_planes + 2 * kN16Warps - 1) / (2 * kN16Warps)) * (p.segs ? 2 * p.segs : 1) * n_chains;
     const uint32_t max_chunks = g.Y / 2 ? g.Y / 2 : 1;
     uint32_t best = 1;
     double best_cost = 1e300;
@@ -398,10 +517,10 @@ inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_pla
 }
 
 inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
-    const uint32_t n_groups = (a.n_planes + 2 * kN16Warps - 1) / (2 * kN16Warps);
+    const uint32_t n_groups = (a.n_planes + 2 * kN16Warps - 1) / (2 * kN16Warps) * (p.segs ? 2u : 1u);
     const uint32_t n_chunks = narrow_chunks(p, a.g, a.n_planes, a.n_chains);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_chunks, n_groups, a.n_chains);
+    cfg.gridDim = dim3(n_chunks * (p.segs ? p.segs : 1), n_groups, a.n_chains);
     cfg.blockDim = dim3(kN16Threads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = a.stream;
@@ -410,22 +529,28 @@ inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = a.pdl ? 1 : 0;
-#define LQFT_GO(W, C, S)                                                                                                  \
-    return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C, S>, a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_first, a.tl_second, \
-                              a.n_planes, n_chunks, a.own, a.oth, a.chains, a.chain0, a.thr, a.acc, a.max_thr)
+#define LQFT_ARGS a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_first, a.tl_second, a.n_planes, n_chunks, a.own, a.oth, a.chains, \
+                  a.chain0, a.thr, a.acc, a.max_thr
+#define LQFT_GO(W, C, S)                                                                         \
+    {                                                                                            \
+        if (p.segs == 0) return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C, S>, LQFT_ARGS);       \
+        if (p.segs == 1) return cudaLaunchKernelEx(&cfg, k_sweep_n16w<1, W, C, S>, LQFT_ARGS);   \
+        return cudaLaunchKernelEx(&cfg, k_sweep_n16w<2, W, C, S>, LQFT_ARGS);                    \
+    }
     if (a.n_chains == 1) {
         if (a.wilson) {
-            if (a.count) LQFT_GO(true, true, true); else LQFT_GO(true, false, true);
+            if (a.count) LQFT_GO(true, true, true) else LQFT_GO(true, false, true)
         } else {
-            if (a.count) LQFT_GO(false, true, true); else LQFT_GO(false, false, true);
+            if (a.count) LQFT_GO(false, true, true) else LQFT_GO(false, false, true)
         }
     }
     if (a.wilson) {
-        if (a.count) LQFT_GO(true, true, false); else LQFT_GO(true, false, false);
+        if (a.count) LQFT_GO(true, true, false) else LQFT_GO(true, false, false)
     } else {
-        if (a.count) LQFT_GO(false, true, false); else LQFT_GO(false, false, false);
+        if (a.count) LQFT_GO(false, true, false) else LQFT_GO(false, false, false)
     }
 #undef LQFT_GO
+#undef LQFT_ARGS
     return cudaGetLastError();
 }
 

@@ -99,10 +99,13 @@ def test_wide_row_kernels_bit_exact_vs_oracle(size, beta, wilson):
 @pytest.mark.parametrize("size,beta,wilson", [
     ((256, 8, 4), 0.25, (0, 0)), ((256, 4, 2), 0.2, (100, 2)), ((256, 10, 6), 0.3, (0, 0)), ((256, 36, 2), 0.25, (0, 0)),
     ((256, 2, 34), 0.22, (255, 20)), ((256, 6, 48), 0.27, (0, 0)), ((256, 2, 2), 0.05, (3, 1)),
+    ((512, 4, 4), 0.25, (0, 0)), ((512, 6, 2), 0.22, (300, 1)), ((512, 2, 20), 0.24, (77, 9)), ((512, 2, 36), 0.3, (511, 36)),
+    ((1024, 4, 2), 0.25, (0, 0)), ((1024, 2, 4), 0.28, (1000, 3)), ((1024, 2, 18), 0.26, (513, 7)),
 ])
 def test_narrow_working_copy_bit_exact_vs_oracle(size, beta, wilson):
-    """X = 256: lqft_sweep / lqft_run of >= 4 sweeps work on the 16-bit copy (kernels_narrow.cuh: packed sums,
-    s16x2 clamp, interleaved table, SHFL-shared t-neighbours).  Counting and non-counting instantiations,
+    """X = 256 / 512 / 1024: lqft_sweep / lqft_run of >= 4 sweeps work on the 16-bit copy (kernels_narrow.cuh: packed
+    sums, s16x2 clamp, interleaved table; X = 256: SHFL-shared t-neighbours, wider rows: one plane per warp, x-edge
+    across row segments by a predicated load).  Counting and non-counting instantiations,
     graph and eager launches, energies and normalisation inside the run — all equal to the oracle and to the
     i32 kernels bit for bit."""
     X, Y, T = size
@@ -185,7 +188,7 @@ def test_narrow_many_chains_match_single_chain_runs():
 
 @pytest.mark.parametrize("size,wilson", [((256, 8, 8), (0, 0)), ((256, 6, 4), (77, 3)), ((512, 4, 6), (0, 0)),
                                          ((16, 16, 8), (5, 8)), ((10, 6, 4), (0, 0)), ((256, 4, 40), (200, 33)),
-                                         ((256, 2, 2), (0, 0))])
+                                         ((256, 2, 2), (0, 0)), ((512, 2, 40), (400, 30)), ((1024, 2, 24), (0, 0))])
 def test_self_halo_slab_path_on_one_gpu(size, wilson):
     """LQFT_FLAG_SELF_HALO: ghost planes + the multi-GPU code path (peer-memory pushes and phase flags fused in
     the streaming kernel for wide rows, boundary-first + exchange otherwise) with this rank as its own
@@ -208,7 +211,7 @@ def test_self_halo_slab_path_on_one_gpu(size, wilson):
         e_int = int(eng.energy()[0][0])
         s_int = int(eng.action()[0][0])
         eng.synchronize()
-        assert eng.narrow_segments() == (2 if X == 256 else 0)
+        assert eng.narrow_segments() == (2 if X in (256, 512, 1024) else 0)
         # a schedule short-cycled enough for graph replay (on slabs: narrow copy only, exchanges inside the graph)
         want3 = want.copy()
         we3, _ = O.run(lat, want3, beta, seed, 16, 0, 40, 2, 4, order=1, wilson=wil)
