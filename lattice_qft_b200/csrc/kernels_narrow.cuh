@@ -1,11 +1,10 @@
-// kernels_narrow.cuh — red-black Metropolis half-sweep on 16-bit heights (X = 256; wider rows: k_sweep_n16w).
+// kernels_narrow.cuh — red-black Metropolis half-sweep on 16-bit heights (X = 256; wider rows: k_sweep_n16).
 //
 // The reference keeps heights in i32 (Field<i32>, fields.rs:63-67) and so does the ABI; between API calls the
 // device field is i32 too.  Inside lqft_run / lqft_sweep the engine may hold a *narrow* working copy instead:
 // u16 heights biased by kN16Bias relative to a per-chain centre (the chain's normalisation offset).  Half the
 // bytes per site, and — what matters more on this latency/issue-bound kernel — half the registers per site:
-// one thread owns 8 same-colour sites (one 16-byte load), a half-warp one row of 128 positions, a warp two
-// adjacent t-planes whose inner t-neighbour rows are exchanged by SHFL instead of being loaded.
+// one thread owns 8 same-colour sites (one 16-byte load), 16 lanes a row segment of 128 positions.
 //
 // Same decision spec as every other kernel family (spec.cuh: Philox keying by global index, integer
 // threshold table), so results are bit-identical to the i32 kernels and to the oracle; what differs is the
@@ -32,13 +31,12 @@
 
 namespace lqft {
 
-constexpr int kN16Warps = 8;                     // per block: 16 planes
+constexpr int kN16Warps = 8;                     // per block: 8 planes of one parity (16 for X = 256)
 constexpr int kN16Threads = kN16Warps * 32;
 constexpr int kN16Bias = 2048;
 constexpr int kN16Guard = 1023;
 constexpr uint32_t kN16Segment = 1000;           // kN16Guard + kN16Segment < kN16Bias
 constexpr int kN16KcMax = 255;                   // threshold tables up to 256 entries (beta >= ~0.045)
-constexpr uint32_t kN16RowQ = 16;                // uint4 per row of one colour (X = 256)
 
 constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even)
 constexpr uint32_t kN16ExchangeBlocks = 16;      // per (side, colour, chain)
@@ -107,136 +105,34 @@ __device__ __forceinline__ uint4 n16_wilson(uint32_t k0, uint32_t p, int sgn, ui
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// grid = (n_chunks, ceil(n_planes / 16), n_chains).  Updates n_planes local planes (even): the first n_first of
-// them start at tl_first, the rest at tl_second (two wedges next to the slab boundaries in one launch; one range
-// when n_first == n_planes).  Negative plane numbers reach into the lower ghost planes, numbers >= Tl into the
-// upper ones.
-// Lanes 0-15: plane t, row y; lanes 16-31: plane t+1, row y+1 — the same x parity, and each half's inner
-// t-neighbour row sits in the partner half's register window.
-// SINGLE: one chain, its parameters arrive as a kernel argument: the Philox key then lives in the parameter bank
-// and the ten round keys derived from it in uniform registers, instead of twenty vector registers per thread.
-template <bool WILSON, bool COUNT, bool SINGLE>
-__global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
-k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
-            const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
-            uint16_t* __restrict__ own_base,
-            const uint16_t* __restrict__ oth_base, const ChainDev* __restrict__ chains, const ChainDev chain0,
-            const uint32_t* __restrict__ thr_all, unsigned long long* __restrict__ acc, const uint32_t max_thr) {
-    __shared__ unsigned int s_cnt;
-    pdl_launch_dependents();
-    const uint32_t chain = SINGLE ? 0u : blockIdx.z;
-    const ChainDev cd = SINGLE ? chain0 : chains[chain];
-    if (COUNT && threadIdx.x == 0) s_cnt = 0;
-    const int kc = build_interleaved(s_n16_tab, thr_all + (size_t)chain * kThrStride, max_thr);
-    const uint32_t c_off = (uint32_t)((kc - 24576) & 0xffff) * 0x10001u, c_max = (uint32_t)(2 * kc) * 0x10001u;
-    pdl_wait();  // from here on the predecessor has completed
-    if (ctr) sweep += *ctr;
-
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t half = lane >> 4, l16 = lane & 15u;
-    const uint32_t chunk = blockIdx.x;
-    const uint32_t pl0_raw = blockIdx.y * (2u * kN16Warps) + 2u * warp;  // lower plane of this warp's pair within the range
-    const uint32_t y0 = chunk * g.Y / n_chunks, y1 = (chunk + 1u) * g.Y / n_chunks;  // n_chunks <= Y / 2, Y < 2^24
-    int accepted = 0;
-    // Warps past the end of the plane range (last group of a range that is no multiple of 16 planes) walk pair 0
-    // with their stores switched off instead of branching around the body: the condition is warp uniform, but
-    // ptxas cannot know that, and only in control flow it knows to be convergent does it keep the Philox round
-    // keys in uniform registers and the shuffles free of divergence handling.  n_chunks <= Y: no empty chunks.
-    const bool live = pl0_raw < n_planes;
-    const uint32_t pl0 = live ? pl0_raw : 0u;  // addresses and keys only: see `p` below
-    {
-        // local plane, modulo 2^32 below the slab (n_first is even: a pair never straddles the two ranges)
-        const uint32_t tl_first_of_pair = pl0 < n_first ? (uint32_t)tl_first + pl0 : (uint32_t)tl_second + (pl0 - n_first);
-        const uint32_t tl = tl_first_of_pair + half;
-        const uint32_t tg = (g.t0 + g.T + tl) % g.T;             // global plane: keys, parity and the Wilson sheet
-        const bool owned = live && tl < g.Tl;
-        const uint32_t planeq = g.Y * kN16RowQ;
-        // offsets in uint4 units from the array bases, chain included (narrow_geometry_ok: the arrays stay below
-        // 2^32 uint4): the bases themselves then come straight from the parameter bank, not from registers
-        const uint32_t cq = chain * (uint32_t)(g.chain_stride / 8);
-        const uint32_t b_own = cq + plane_self(g, tl) * planeq + l16;
-        const uint32_t b_out = cq + (half ? plane_above(g, tl) : plane_below(g, tl)) * planeq + l16;
-        uint4* const q_own = reinterpret_cast<uint4*>(own_base);
-        const uint4* const q_oth = reinterpret_cast<const uint4*>(oth_base);
-        const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
-        uint32_t y = y0 + half;
-        if (y == g.Y) y = 0;  // this lane's first row
-        const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
-        uint4 wa = __ldg(q_oth + (b_own + ym * kN16RowQ)), wb = __ldg(q_oth + (b_own + y * kN16RowQ)), wc;
-        // x parity of the lower half's row; the upper half (row + 1, plane + 1) has the same.  Written without any
-        // lane-dependent term (T is even, so the wrap of tg does not matter) to keep the branch on it uniform.
-        // Nor any select on the plane number, nor the warp index itself: ptxas does not know that threadIdx.x >> 5 is
-        // warp uniform.  pl0_raw = 16 blockIdx.y + 2 warp is even, so the warp drops out of the parity altogether.
-        // The second range starts at the parity the first one would have continued with (launch_sweep: Tl is
-        // even), so tl_first + pl0_raw has the right parity in both.
-        uint32_t p = (y0 + g.t0 + (uint32_t)tl_first + pl0_raw + (uint32_t)colour) & 1u;
-        const uint32_t src_r = (lane & 16u) | ((lane + 1u) & 15u), src_l = (lane & 16u) | ((lane - 1u) & 15u);
-        const uint32_t grp_base = tg * g.Y * 32u + l16 * 2u;  // Philox counter word 0 of this thread's first group at y = 0
-        const bool wil_plane = WILSON && tg < cd.wil_h;
-        const uint32_t y_one = 1u % g.Y;
-        uint32_t n = y1 - y0;
-#define LQFT_N16_STEP(OM, OC, ON)                                                                                        \
-    {                                                                                                                    \
-        const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;                                                                  \
-        uint4* const po = q_own + (b_own + y * kN16RowQ);                                                                \
-        const uint4 v = *po;                                                                                             \
-        ON = __ldg(q_oth + (b_own + yn * kN16RowQ));                                                                     \
-        const uint4 to = __ldg(q_oth + (b_out + y * kN16RowQ));                                                          \
-        /* lower half (plane t, row y) needs plane t+1 row y = partner's OM; upper (t+1, y+1) needs plane t row y+1 = partner's ON */ \
-        const uint4 snd = half ? OM : ON;                                                                                \
-        uint4 ti;                                                                                                        \
-        ti.x = __shfl_xor_sync(0xffffffffu, snd.x, 16); ti.y = __shfl_xor_sync(0xffffffffu, snd.y, 16);                  \
-        ti.z = __shfl_xor_sync(0xffffffffu, snd.z, 16); ti.w = __shfl_xor_sync(0xffffffffu, snd.w, 16);                  \
-        const uint32_t grp = grp_base + y * 32u;                                                                         \
-        const u32x4 r0 = philox4x32_rk(grp, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);             \
-        const u32x4 r1 = philox4x32_rk(grp + 1u, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);        \
-        uint4 woff = make_uint4(0, 0, 0, 0);                                                                             \
-        if (WILSON) {                                                                                                    \
-            if (wil_plane && (y == 0u || y == y_one))                                                                    \
-                woff = n16_wilson(8u * l16, p, (y == 0u ? 1 : 0) - (y == y_one ? 1 : 0), cd.wil_w);                      \
-        }                                                                                                                \
-        uint4 w;                                                                                                         \
-        int acc_row = 0;                                                                                                 \
-        if (p) {                                                                                                         \
-            const uint32_t edge = __shfl_sync(0xffffffffu, OC.x, src_r);                                                 \
-            w = n16_row_update<1, WILSON, COUNT>(v, OM, OC, ON, to, ti, edge, r0, r1, c_off, c_max, woff, acc_row);      \
-        } else {                                                                                                         \
-            const uint32_t edge = __shfl_sync(0xffffffffu, OC.w, src_l);                                                 \
-            w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, to, ti, edge, r0, r1, c_off, c_max, woff, acc_row);      \
-        }                                                                                                                \
-        if (COUNT) accepted += owned ? acc_row : 0;  /* ghost planes are somebody else's sites */                        \
-        if (live) *po = w;                                                                                               \
-        y = yn;                                                                                                          \
-        p ^= 1u;                                                                                                         \
-    }
-        // the three-row register window rotates through the names instead of being copied
-        for (;;) {
-            LQFT_N16_STEP(wa, wb, wc)
-            if (--n == 0) break;
-            LQFT_N16_STEP(wb, wc, wa)
-            if (--n == 0) break;
-            LQFT_N16_STEP(wc, wa, wb)
-            if (--n == 0) break;
-        }
-#undef LQFT_N16_STEP
-    }
-    if (COUNT)
-        block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
-}
-
-// ---- wider rows: X = 512 (SEGS = 1) and X = 1024 (SEGS = 2) ---------------------------------------------------
-// A warp is one 256-position segment of a row of ONE plane (no plane pairing: both t-neighbour rows are loaded);
-// with two segments the x-neighbour across the segment edge is one predicated 4-byte load.  Everything else —
-// packed sums, clamp, table, Philox keying, plane ranges, surplus warps — as in k_sweep_n16.
-// grid = (n_chunks * SEGS, ceil(n_planes / 8), n_chains).
+// ---- the half-sweep: X = 256 (SEGS = 0), 512 (SEGS = 1), 1024 (SEGS = 2) ------------------------------------------
+// A warp is one 256-position segment of a row of ONE plane — for X = 256 two half-warps on two planes of the same
+// parity; with two segments the x-neighbour across the segment edge is one predicated 4-byte load.  Per step and
+// thread: own row (read + write), the other colour's rows y+1 (y-1 and y stay in a rotating register window), t+1
+// and t-1: 4 LDG.128 + 1 STG.128, two Philox blocks, 8 decisions.
+//
+// Updates n_planes local planes: the first n_first of them start at tl_first, the rest at tl_second (two wedges
+// next to the slab boundaries in one launch; one range when n_first == n_planes).  Negative plane numbers reach
+// into the lower ghost planes, numbers >= Tl into the upper ones.
+//
+// Control flow is kept visibly uniform: ptxas uses the uniform datapath (Philox round keys in uniform registers)
+// and plain shuffles only where it can prove convergence, and it does not know that threadIdx.x >> 5 is warp
+// uniform.  Hence (a) no guard around the body — surplus warps past the end of the plane range walk plane 0 with
+// their stores predicated off, (b) the branch on the x parity depends on blockIdx only: blocks 2m and 2m+1 share
+// P consecutive planes, the even ones in block 2m, the odd ones in 2m+1 (P = 16; 32 for X = 256, where a warp
+// carries two planes), (c) SINGLE: a lone chain's parameters arrive as a kernel argument, so that the key is a
+// parameter-bank constant.  Without these the same source compiles to 1400 instead of 1024 instructions and runs
+// 18 % slower.
+// grid = (n_chunks * max(SEGS, 1), 2 * ceil(n_planes / P), n_chains).
 template <int SEGS, bool WILSON, bool COUNT, bool SINGLE>
 __global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
-k_sweep_n16w(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
+k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
              const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
              uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
              const ChainDev* __restrict__ chains, const ChainDev chain0, const uint32_t* __restrict__ thr_all,
              unsigned long long* __restrict__ acc, const uint32_t max_thr) {
-    constexpr uint32_t ROWQ = 32u * SEGS;  // uint4 per row of one colour
+    constexpr uint32_t ROWQ = SEGS ? 32u * SEGS : 16u;  // uint4 per row of one colour
+    constexpr uint32_t LPR = SEGS ? 32u : 16u;           // lanes of a warp on one row
     __shared__ unsigned int s_cnt;
     pdl_launch_dependents();
     const uint32_t chain = SINGLE ? 0u : blockIdx.z;
@@ -248,20 +144,20 @@ k_sweep_n16w(const Geom g, const int colour, uint64_t sweep, const uint64_t* __r
     if (ctr) sweep += *ctr;
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t seg = SEGS > 1 ? blockIdx.x % SEGS : 0u, chunk = blockIdx.x / SEGS;
-    // Blocks 2m and 2m+1 share 16 consecutive planes: the even ones go to block 2m, the odd ones to 2m+1.  All
-    // warps of a block then work on planes of one parity, and the x parity of their rows depends on blockIdx only:
-    // ptxas has to see that the branch on it is uniform (it does not know that threadIdx.x >> 5 is).
-    const uint32_t pl_raw = (blockIdx.y >> 1) * (2u * kN16Warps) + 2u * warp + (blockIdx.y & 1u);
+    const uint32_t seg = SEGS > 1 ? blockIdx.x % SEGS : 0u, chunk = SEGS > 1 ? blockIdx.x / SEGS : blockIdx.x;
+    // all planes of a block have the parity of blockIdx.y (see above)
+    const uint32_t sub = SEGS ? 0u : lane >> 4;
+    const uint32_t slot = SEGS ? warp : 2u * warp + sub;  // plane slot within the block
+    const uint32_t pl_raw = (blockIdx.y >> 1) * (SEGS ? 2u * kN16Warps : 4u * kN16Warps) + 2u * slot + (blockIdx.y & 1u);
     const uint32_t y0 = chunk * g.Y / n_chunks, y1 = (chunk + 1u) * g.Y / n_chunks;
     int accepted = 0;
-    const bool live = pl_raw < n_planes;              // surplus warps: plane 0 of the range, stores off (see k_sweep_n16)
+    const bool live = pl_raw < n_planes;              // surplus warps: plane 0 of the range, stores off
     const uint32_t pl = live ? pl_raw : 0u;
     {
         const uint32_t tl = pl < n_first ? (uint32_t)tl_first + pl : (uint32_t)tl_second + (pl - n_first);
         const uint32_t tg = (g.t0 + g.T + tl) % g.T;
         const bool owned = live && tl < g.Tl;
-        const uint32_t kq = seg * 32u + lane;          // uint4 column of this thread within the row
+        const uint32_t kq = SEGS ? seg * 32u + lane : lane & 15u;  // uint4 column of this thread within the row
         const uint32_t planeq = g.Y * ROWQ;
         const uint32_t cq = chain * (uint32_t)(g.chain_stride / 8);
         const uint32_t r_own = cq + plane_self(g, tl) * planeq;  // row 0 of this plane
@@ -277,14 +173,15 @@ k_sweep_n16w(const Geom g, const int colour, uint64_t sweep, const uint64_t* __r
         uint32_t y = y0;
         const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
         uint4 wa = __ldg(q_oth + (b_own + ym * ROWQ)), wb = __ldg(q_oth + (b_own + y * ROWQ)), wc;
-        // parity from threadIdx.x >> 5 arithmetic only (see k_sweep_n16); the second range continues the first one's
+        // x parity of the first row, no thread-dependent term; the second range starts at the parity the first one
+        // would have continued with (launch_sweep: Tl is even)
         uint32_t p = (y0 + g.t0 + (uint32_t)tl_first + (blockIdx.y & 1u) + (uint32_t)colour) & 1u;
-        const uint32_t src_r = (lane + 1u) & 31u, src_l = (lane - 1u) & 31u;
-        const uint32_t grp_base = tg * g.Y * (64u * SEGS) + kq * 2u;
+        const uint32_t src_r = (lane & ~(LPR - 1u)) | ((lane + 1u) & (LPR - 1u)), src_l = (lane & ~(LPR - 1u)) | ((lane - 1u) & (LPR - 1u));
+        const uint32_t grp_base = tg * g.Y * (2u * ROWQ) + kq * 2u;
         const bool wil_plane = WILSON && tg < cd.wil_h;
         const uint32_t y_one = 1u % g.Y;
         uint32_t n = y1 - y0;
-#define LQFT_N16W_STEP(OM, OC, ON)                                                                                       \
+#define LQFT_N16_STEP(OM, OC, ON)                                                                                       \
     {                                                                                                                    \
         const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;                                                                  \
         uint4* const po = q_own + (b_own + y * ROWQ);                                                                    \
@@ -297,7 +194,7 @@ k_sweep_n16w(const Geom g, const int colour, uint64_t sweep, const uint64_t* __r
         if (SEGS > 1) {                                                                                                  \
             if (e_lane) e_ld = __ldg(w_oth + ((p ? e_right : e_left) + y * (ROWQ * 4u)));                                \
         }                                                                                                                \
-        const uint32_t grp = grp_base + y * (64u * SEGS);                                                                \
+        const uint32_t grp = grp_base + y * (2u * ROWQ);                                                                 \
         const u32x4 r0 = philox4x32_rk(grp, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);             \
         const u32x4 r1 = philox4x32_rk(grp + 1u, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);        \
         uint4 woff = make_uint4(0, 0, 0, 0);                                                                             \
@@ -322,14 +219,14 @@ k_sweep_n16w(const Geom g, const int colour, uint64_t sweep, const uint64_t* __r
         p ^= 1u;                                                                                                         \
     }
         for (;;) {
-            LQFT_N16W_STEP(wa, wb, wc)
+            LQFT_N16_STEP(wa, wb, wc)
             if (--n == 0) break;
-            LQFT_N16W_STEP(wb, wc, wa)
+            LQFT_N16_STEP(wb, wc, wa)
             if (--n == 0) break;
-            LQFT_N16W_STEP(wc, wa, wb)
+            LQFT_N16_STEP(wc, wa, wb)
             if (--n == 0) break;
         }
-#undef LQFT_N16W_STEP
+#undef LQFT_N16_STEP
     }
     if (COUNT)
         block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
@@ -446,7 +343,7 @@ __global__ void k_narrow_begin(const int32_t* __restrict__ offset, int32_t* __re
 // ---- host side ----------------------------------------------------------------------------------------------
 struct NarrowPlan {
     bool enabled = false;
-    int segs = 0;          // 0: X = 256 (k_sweep_n16, two planes per warp); 1, 2: X = 512, 1024 (k_sweep_n16w)
+    int segs = 0;          // row segments of 256 positions: 0 (X = 256, half a warp per row), 1 (X = 512), 2 (X = 1024)
     int blocks_per_sm = 0;
     int sm_count = 0;
 };
@@ -486,20 +383,26 @@ inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, uint32_t n_chain
     p.sm_count = sm_count;
     p.segs = g.X == 256 ? 0 : (int)(g.X / 512);
     cudaError_t e;
-    if (p.segs == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<false, false, true>, kN16Threads, 0);
-    else if (p.segs == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16w<1, false, false, true>, kN16Threads, 0);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16w<2, false, false, true>, kN16Threads, 0);
+    if (p.segs == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<0, false, false, true>, kN16Threads, 0);
+    else if (p.segs == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<1, false, false, true>, kN16Threads, 0);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<2, false, false, true>, kN16Threads, 0);
     if (e != cudaSuccess) return e;
     p.enabled = p.blocks_per_sm > 0;
     return cudaSuccess;
+}
+
+// grid.y: blocks along the planes: block pairs (even / odd planes) over 16 planes, or over 32 for X = 256 where a
+// warp carries two planes.
+inline uint32_t narrow_groups(const NarrowPlan& p, uint32_t n_planes) {
+    const uint32_t per_pair = p.segs ? 2 * kN16Warps : 4 * kN16Warps;
+    return 2 * ((n_planes + per_pair - 1) / per_pair);
 }
 
 // y chunks per plane group: one wave if possible, chunks as short as that allows (cost model of stream_chunks;
 // the per-chunk prologue is worth about two rows here).
 inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_planes, uint32_t n_chains) {
     const uint64_t slots = (uint64_t)p.sm_count * p.blocks_per_sm;
-    // blocks per chunk: 16 planes per block (X = 256), or two blocks of 8 per 16 planes times the row segments
-    const uint64_t base = (uint64_t)((n_planes + 2 * kN16Warps - 1) / (2 * kN16Warps)) * (p.segs ? 2 * p.segs : 1) * n_chains;
+    const uint64_t base = narrow_groups(p, n_planes) * (uint64_t)(p.segs ? p.segs : 1) * n_chains;  // blocks per chunk
     const uint32_t max_chunks = g.Y / 2 ? g.Y / 2 : 1;
     uint32_t best = 1;
     double best_cost = 1e300;
@@ -517,7 +420,7 @@ inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_pla
 }
 
 inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
-    const uint32_t n_groups = (a.n_planes + 2 * kN16Warps - 1) / (2 * kN16Warps) * (p.segs ? 2u : 1u);
+    const uint32_t n_groups = narrow_groups(p, a.n_planes);
     const uint32_t n_chunks = narrow_chunks(p, a.g, a.n_planes, a.n_chains);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_chunks * (p.segs ? p.segs : 1), n_groups, a.n_chains);
@@ -533,9 +436,9 @@ inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
                   a.chain0, a.thr, a.acc, a.max_thr
 #define LQFT_GO(W, C, S)                                                                         \
     {                                                                                            \
-        if (p.segs == 0) return cudaLaunchKernelEx(&cfg, k_sweep_n16<W, C, S>, LQFT_ARGS);       \
-        if (p.segs == 1) return cudaLaunchKernelEx(&cfg, k_sweep_n16w<1, W, C, S>, LQFT_ARGS);   \
-        return cudaLaunchKernelEx(&cfg, k_sweep_n16w<2, W, C, S>, LQFT_ARGS);                    \
+        if (p.segs == 0) return cudaLaunchKernelEx(&cfg, k_sweep_n16<0, W, C, S>, LQFT_ARGS);   \
+        if (p.segs == 1) return cudaLaunchKernelEx(&cfg, k_sweep_n16<1, W, C, S>, LQFT_ARGS);   \
+        return cudaLaunchKernelEx(&cfg, k_sweep_n16<2, W, C, S>, LQFT_ARGS);                    \
     }
     if (a.n_chains == 1) {
         if (a.wilson) {
