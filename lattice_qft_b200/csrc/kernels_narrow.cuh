@@ -38,7 +38,7 @@ constexpr int kN16Guard = 1023;
 constexpr uint32_t kN16Segment = 1000;           // kN16Guard + kN16Segment < kN16Bias
 constexpr int kN16KcMax = 255;                   // threshold tables up to 256 entries (beta >= ~0.045)
 
-constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even)
+constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even); fewer for large planes
 constexpr uint32_t kN16ExchangeBlocks = 16;      // per (side, colour, chain)
 constexpr uint32_t kN16Overlap = 1;              // half-sweeps whose interior runs underneath an exchange
 

@@ -598,7 +598,12 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     h->gn = g;
     if (g.ghost) {
         // deep halo of the narrow copy: as many planes as the thinnest slab allows, at most kN16GhostDepth, even
-        uint32_t depth = kN16GhostDepth;
+        // The exchange volume per half-sweep does not depend on the depth; depth trades the exchange latency
+        // (~20 us, amortised over `depth` half-sweeps) against redundant planes ((depth - 1) / Tl of the work).
+        // Small planes are latency dominated, large ones are not (measured on 2 GPUs: 256^2 planes 8 > 4 > 2,
+        // 1024^2 planes 2 > 4 > 8).
+        const uint64_t plane_bytes = (uint64_t)g.plane * sizeof(uint16_t);
+        uint32_t depth = plane_bytes <= (128u << 10) ? kN16GhostDepth : (plane_bytes <= (512u << 10) ? 4u : 2u);
         if (const char* e = getenv("LQFT_N16_DEPTH")) depth = (uint32_t)atoi(e);  // tuning knob
         for (uint32_t r = 0; r < ws; ++r) {
             uint32_t rt0 = 0, rnt = 0;
