@@ -227,8 +227,8 @@ def workload_config(n_gpus: int):
         "workload": f"{X}x{Y}x{t} periodic lattice, 1 chain, i32 heights, beta={BETA}, red-black Metropolis, "
                     f"{SWEEPS_PER_STEP} sweeps per step, pre-thermalised {THERMALISE} sweeps from seeded hot start",
         "lattice": [X, Y, t], "sweeps_per_step": SWEEPS_PER_STEP, "beta": BETA,
-        "decomposition": "none" if n_gpus == 1 else f"t-slabs of {T_PER_GPU} planes per GPU; 16-bit working copy with an 8-plane "
-                         "deep halo exchanged over peer memory once per 8 half-sweeps",
+        "decomposition": "none" if n_gpus == 1 else f"t-slabs of {T_PER_GPU} planes per GPU; 16-bit working copy with a deep halo "
+                         "(8 ghost planes at this plane size) exchanged over peer memory once per 8 half-sweeps",
         "l2": "L2 flushed (256 MiB write) between timed steps; the 64 MiB/GPU field itself is L2-resident by nature",
     }
 

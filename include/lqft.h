@@ -84,7 +84,7 @@ typedef struct lqft_config {
 #define LQFT_FLAG_NO_PDL 32u      /* no programmatic dependent launch between half-sweeps     */
 #define LQFT_FLAG_NO_RESIDENT 128u /* small lattices: multi-launch path instead of the one-launch
                                      shared-memory resident kernel */
-#define LQFT_FLAG_NO_NARROW 256u   /* X == 256: keep the i32 kernels inside lqft_run / lqft_sweep instead of the
+#define LQFT_FLAG_NO_NARROW 256u   /* X in {256, 512, 1024}: keep the i32 kernels inside lqft_run / lqft_sweep instead of the
                                      16-bit working copy (same results, used by the tests to cross-check) */
 #define LQFT_FLAG_SELF_HALO 64u   /* world_size==1: ghost planes + the peer-memory halo path with
                                      this rank as its own neighbour (tests the multi-GPU kernel) */
@@ -189,7 +189,7 @@ lqft_status lqft_last_device_ms(lqft_handle* h, float* ms);
 /* Number of kernels this handle has launched so far (graph replays count their nodes). */
 lqft_status lqft_kernel_launches(lqft_handle* h, uint64_t* n);
 /* Number of update segments this handle has run on the 16-bit working copy so far (0 = every sweep went
- * through the i32 kernels: other extents than X == 256, LQFT_FLAG_NO_NARROW, or heights outside the guard
+ * through the i32 kernels: other extents than X in {256, 512, 1024}, LQFT_FLAG_NO_NARROW, or heights outside the guard
  * band around the chain's normalisation offset). */
 lqft_status lqft_narrow_segments(lqft_handle* h, uint64_t* n);
 /* The handle's cudaStream_t (for callers that time with their own events). */
