@@ -961,6 +961,8 @@ static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint
 
 static lqft_status ready(lqft_handle* h) {
     if (!h) return fail(LQFT_ERR_INVALID, "null handle");
+    if (h->narrow_active)  // only possible after a device error in the middle of lqft_run: the i32 field is stale
+        return fail(LQFT_ERR_STATE, "an earlier call failed inside a narrow segment; the field is undefined, upload it again");
     ST(use_device(h));
     ST(upload_params(h));
     ST(refresh_ghosts(h));
@@ -986,6 +988,7 @@ extern "C" lqft_status lqft_init_hot(lqft_handle* h) {
     CU(cudaGetLastError());
     h->launches += 1;
     h->ghosts_valid = false;
+    h->narrow_active = false;
     return LQFT_OK;
 }
 
@@ -1021,6 +1024,7 @@ extern "C" lqft_status lqft_upload(lqft_handle* h, uint32_t chain, const void* v
     CU(cudaGetLastError());
     h->launches += 1;
     h->ghosts_valid = false;
+    h->narrow_active = false;  // (after a failed run: every chain has to be uploaded again, the caller's business)
     CU(cudaStreamSynchronize(h->stream));  // the host buffer may be reused on return
     return LQFT_OK;
 }
