@@ -1,4 +1,4 @@
-// kernels_narrow.cuh — red-black Metropolis half-sweep on 16-bit heights (X = 256; wider rows: k_sweep_n16).
+// kernels_narrow.cuh — red-black Metropolis half-sweep on 16-bit heights (X = 256, 512, 1024).
 //
 // The reference keeps heights in i32 (Field<i32>, fields.rs:63-67) and so does the ABI; between API calls the
 // device field is i32 too.  Inside lqft_run / lqft_sweep the engine may hold a *narrow* working copy instead:
@@ -16,12 +16,14 @@
 //   * the coin bit of the site's Philox word is funnel-shifted into the index, so one LDS.64 fetches
 //     {threshold | coin << 31, +-1} for the proposed direction.
 //
-// Slabs (world_size > 1): the narrow copy carries kN16GhostDepth ghost planes per side instead of one.  After an
-// exchange (k_n16_exchange: peer stores over NVLink plus two flag phases) all of them are valid; each half-sweep
-// then also updates the ghost planes that still have valid t-neighbours — redundantly, with the same Philox
-// words as their owner, hence identically — and the valid depth shrinks by one.  One exchange per
-// kN16GhostDepth half-sweeps replaces the per-half-sweep halo of the i32 path, and the sweep kernel itself
-// carries no flags, waits or peer stores at all.
+// Slabs (world_size > 1): the narrow copy carries up to kN16GhostDepth ghost planes per side instead of one.
+// After an exchange (k_n16_exchange: peer stores over NVLink plus two flag phases) all of them are valid; each
+// half-sweep then also updates the ghost planes that still have valid t-neighbours — redundantly, with the same
+// Philox words as their owner, hence identically — and the valid depth shrinks by one.  One exchange per `depth`
+// half-sweeps replaces the per-half-sweep halo of the i32 path, and the sweep kernel itself carries no flags,
+// waits or peer stores at all.  The exchange runs on a second stream underneath the next kN16Overlap
+// half-sweeps, which update only the planes far enough from the boundaries; the wedges they leave out are caught
+// up, in order, once the ghost planes have arrived (lqft.cu: launch_sweep, narrow_exchange_begin / _end).
 //
 // Validity: a narrow segment starts only if every height is within kN16Guard of the centre and lasts at most
 // kN16Segment sweeps; a sweep moves a site by at most one, so no height can leave [0, 4096) (host logic in
@@ -127,10 +129,10 @@ __device__ __forceinline__ uint4 n16_wilson(uint32_t k0, uint32_t p, int sgn, ui
 template <int SEGS, bool WILSON, bool COUNT, bool SINGLE>
 __global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
 k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
-             const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
-             uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
-             const ChainDev* __restrict__ chains, const ChainDev chain0, const uint32_t* __restrict__ thr_all,
-             unsigned long long* __restrict__ acc, const uint32_t max_thr) {
+            const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
+            uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
+            const ChainDev* __restrict__ chains, const ChainDev chain0, const uint32_t* __restrict__ thr_all,
+            unsigned long long* __restrict__ acc, const uint32_t max_thr) {
     constexpr uint32_t ROWQ = SEGS ? 32u * SEGS : 16u;  // uint4 per row of one colour
     constexpr uint32_t LPR = SEGS ? 32u : 16u;           // lanes of a warp on one row
     __shared__ unsigned int s_cnt;
