@@ -229,6 +229,32 @@ def test_self_halo_slab_path_on_one_gpu(size, wilson):
     assert e_int == O.integer_energy(lat, want)[0] and float(s_int) == O.float_action(lat, want)
 
 
+@pytest.mark.parametrize("depth", [2, 4, 6])
+@pytest.mark.parametrize("size", [(256, 4, 40), (512, 2, 24), (1024, 2, 20)])
+def test_self_halo_other_ghost_depths(size, depth, monkeypatch):
+    """Large planes get a shallower deep halo (lqft.cu picks 8 / 4 / 2 by plane size); the test lattices are small,
+    so the depth is forced through the tuning knob.  Interior-under-exchange + wedges at every depth."""
+    X, Y, T = size
+    monkeypatch.setenv("LQFT_N16_DEPTH", str(depth))
+    beta, seed, wilson = 0.26, 99 + depth, (X // 3, T - 3)
+    lat = O.Lattice([X, Y, T])
+    wil = O.Wilson(lat, *wilson)
+    v0 = seeded_field(X * Y * T, seed=depth + T)
+    want = v0.copy()
+    wacc = sum(O.sweep(lat, want, beta, seed, s, order=1, wilson=wil) for s in range(7))
+    we, _ = O.run(lat, want, beta, seed, 7, 0, 30, 3, 10, order=1, wilson=wil)
+    with Engine(X, Y, T, flags=_lib.FLAG_SELF_HALO) as eng:
+        eng.set_chain(0, beta, seed, *wilson)
+        eng.upload(0, v0)
+        acc = eng.sweep(0, 7, want_accepted=True)[0]
+        e_obs, _, _ = eng.run(30, sweep_base=7, energy_every=3, normalize_every=10)
+        got = eng.download(0)
+        assert eng.narrow_segments() == 2
+        eng.synchronize()
+    assert acc == wacc and (e_obs[0] == we).all()
+    assert (got == want).all(), f"{int((got != want).sum())} sites differ (depth {depth})"
+
+
 def test_self_halo_many_chains_deep_halo():
     """Three chains with different couplings and Wilson sheets on a self-neighbouring slab (narrow copy, deep halo,
     exchange per chain) equal three single-chain runs on the plain periodic lattice."""
