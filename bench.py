@@ -230,6 +230,10 @@ def workload_config(n_gpus: int):
         "decomposition": "none" if n_gpus == 1 else f"t-slabs of {T_PER_GPU} planes per GPU; 16-bit working copy with a deep halo "
                          "(8 ghost planes at this plane size) exchanged over peer memory once per 8 half-sweeps",
         "l2": "L2 flushed (256 MiB write) between timed steps; the 64 MiB/GPU field itself is L2-resident by nature",
+        "working_copy": "inside lqft_sweep / lqft_run the update kernels work on a u16 copy of the i32 field (heights biased "
+                        "around the normalisation offset; exact integers, bit-identical to the i32 kernels and the oracle; "
+                        "outside a +-1023 guard band the call stays on i32); host buffers and the device field between "
+                        "calls are i32",
     }
 
 
