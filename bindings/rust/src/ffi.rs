@@ -66,6 +66,7 @@ extern "C" {
     pub fn lqft_last_device_ms(h: *mut lqft_handle, ms: *mut f32) -> i32;
     pub fn lqft_kernel_launches(h: *mut lqft_handle, n: *mut u64) -> i32;
     pub fn lqft_narrow_segments(h: *mut lqft_handle, n: *mut u64) -> i32;
+    pub fn lqft_plan_info(h: *mut lqft_handle, buf: *mut c_char, cap: usize) -> i32;
     pub fn lqft_stream(h: *mut lqft_handle, stream: *mut *mut c_void) -> i32;
     pub fn lqft_host_philox4x32(seed: u64, ctr: *const u32, out: *mut u32);
     pub fn lqft_host_site_word(seed: u64, idx: u64, colour: u32, sweep: u64) -> u32;

@@ -192,6 +192,10 @@ lqft_status lqft_kernel_launches(lqft_handle* h, uint64_t* n);
  * through the i32 kernels: other extents than X in {256, 512, 1024}, LQFT_FLAG_NO_NARROW, or heights outside the guard
  * band around the chain's normalisation offset). */
 lqft_status lqft_narrow_segments(lqft_handle* h, uint64_t* n);
+/* One line describing the launch plan the handle would use for its update kernels right now, e.g.
+ * "path=narrow chunks=37 rows_per_chunk=7 plane_blocks=16 blocks_per_sm=4 ghost_depth=0 p2p=0" (for logs and for
+ * tests that must know which kernel and which chunking a parity check exercised). */
+lqft_status lqft_plan_info(lqft_handle* h, char* buf, size_t cap);
 /* The handle's cudaStream_t (for callers that time with their own events). */
 lqft_status lqft_stream(lqft_handle* h, void** stream);
 

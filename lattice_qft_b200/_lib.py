@@ -66,6 +66,7 @@ SIGNATURES = {
     "lqft_last_device_ms": (C.c_int, [vp, P(C.c_float)]),
     "lqft_kernel_launches": (C.c_int, [vp, P(u64)]),
     "lqft_narrow_segments": (C.c_int, [vp, P(u64)]),
+    "lqft_plan_info": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
     "lqft_stream": (C.c_int, [vp, P(vp)]),
     "lqft_host_philox4x32": (None, [u64, P(u32), P(u32)]),
     "lqft_host_site_word": (u32, [u64, u64, u32, u64]),

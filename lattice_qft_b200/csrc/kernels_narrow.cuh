@@ -348,6 +348,7 @@ struct NarrowPlan {
     int segs = 0;          // row segments of 256 positions: 0 (X = 256, half a warp per row), 1 (X = 512), 2 (X = 1024)
     int blocks_per_sm = 0;
     int sm_count = 0;
+    uint32_t forced_chunks = 0;  // LQFT_N16_CHUNKS (tests): y chunks per plane group instead of the cost model's choice
 };
 
 struct NarrowArgs {
@@ -390,6 +391,8 @@ inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, uint32_t n_chain
     else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<2, false, false, true>, kN16Threads, 0);
     if (e != cudaSuccess) return e;
     p.enabled = p.blocks_per_sm > 0;
+    p.forced_chunks = 0;
+    if (const char* e = getenv("LQFT_N16_CHUNKS")) p.forced_chunks = (uint32_t)atoi(e);
     return cudaSuccess;
 }
 
@@ -406,6 +409,7 @@ inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_pla
     const uint64_t slots = (uint64_t)p.sm_count * p.blocks_per_sm;
     const uint64_t base = narrow_groups(p, n_planes) * (uint64_t)(p.segs ? p.segs : 1) * n_chains;  // blocks per chunk
     const uint32_t max_chunks = g.Y / 2 ? g.Y / 2 : 1;
+    if (p.forced_chunks) return p.forced_chunks < g.Y ? p.forced_chunks : g.Y;
     uint32_t best = 1;
     double best_cost = 1e300;
     for (uint32_t nc = 1; nc <= max_chunks; ++nc) {

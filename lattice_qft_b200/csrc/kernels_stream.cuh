@@ -89,17 +89,22 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// Spin until *flag >= need.  Bounded: after 4 s the error word is set and the caller proceeds, so a lost
-// neighbour surfaces as LQFT_ERR_STATE on the host instead of a hung device.
+// Spin until *flag >= need.  Bounded (g_halo_timeout_ns, 30 s unless LQFT_HALO_TIMEOUT_S says otherwise: ranks are
+// separate processes and may be seconds apart — module load, graph instantiation, a rank writing CSVs): on
+// expiry the error word is set and the kernel traps.  A lost neighbour therefore never yields a result computed
+// from stale ghost planes: the launch fails, every later call on the handle returns LQFT_ERR_CUDA, and
+// lqft_synchronize / lqft_download report the halo timeout.  The handle has to be destroyed after that.
+__device__ unsigned long long g_halo_timeout_ns = 30000000000ull;
 __device__ __forceinline__ void halo_wait(const unsigned long long* flag, unsigned long long need, unsigned int* error) {
     if (ld_acquire_sys(flag) >= need) return;
-    if (*reinterpret_cast<volatile unsigned int*>(error)) return;  // already broken: do not stack timeouts
     const unsigned long long t0 = global_timer_ns();
+    const unsigned long long limit = *reinterpret_cast<volatile unsigned long long*>(&g_halo_timeout_ns);
     while (ld_acquire_sys(flag) < need) {
         __nanosleep(64);
-        if (global_timer_ns() - t0 > 4000000000ull) {
+        if (global_timer_ns() - t0 > limit) {
             atomicExch(error, 1u);
-            break;
+            __threadfence_system();
+            __trap();
         }
     }
 }

@@ -450,6 +450,19 @@ static lqft_status ghost_op_end(lqft_handle* h) {
     return LQFT_OK;
 }
 
+static lqft_status set_halo_timeout() {
+    if (const char* e = getenv("LQFT_HALO_TIMEOUT_S")) {
+        const double sec = atof(e);
+        if (sec > 0.0) {
+            const unsigned long long ns = (unsigned long long)(sec * 1e9);
+            CU(cudaMemcpyToSymbol(g_halo_timeout_ns, &ns, sizeof ns));
+        }
+    }
+    return LQFT_OK;
+}
+
+// A halo wait that expired has set the error word and trapped (kernels_stream.cuh, halo_wait): the context is
+// gone, so the copy below fails with LQFT_ERR_CUDA; the word itself is reported when the trap has not landed yet.
 static lqft_status check_halo_error(lqft_handle* h) {
     if (!h->halo_d) return LQFT_OK;
     HaloSync s{};
@@ -635,6 +648,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         NC(g_nccl.CommInitRank(&h->comm, (int)ws, id, (int)cfg->rank));
         CU(cudaMalloc(&h->halo_d, sizeof(HaloSync)));
         CU(cudaMemsetAsync(h->halo_d, 0, sizeof(HaloSync), h->stream));
+        ST(set_halo_timeout());
         ST(setup_p2p(h));
     } else if (self_halo) {
         // one rank that is its own lower and upper neighbour: the whole peer-memory halo path (pushes,
@@ -1635,6 +1649,8 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
             }
     }
     if (accepted) ST(read_accepted(h, accepted));
+    // slabs: a call that handed results back has synchronised; say so if a neighbour was lost on the way
+    if (h->g.ghost && (accepted || (n_meas && (e_obs || e_int)))) ST(check_halo_error(h));
     return LQFT_OK;
 }
 
@@ -1664,6 +1680,23 @@ extern "C" lqft_status lqft_kernel_launches(lqft_handle* h, uint64_t* n) {
 extern "C" lqft_status lqft_narrow_segments(lqft_handle* h, uint64_t* n) {
     if (!h || !n) return fail(LQFT_ERR_INVALID, "null argument");
     *n = h->narrow_segments;
+    return LQFT_OK;
+}
+
+extern "C" lqft_status lqft_plan_info(lqft_handle* h, char* buf, size_t cap) {
+    if (!h || !buf || cap == 0) return fail(LQFT_ERR_INVALID, "null argument");
+    ST(use_device(h));
+    ST(upload_params(h));
+    const char* path = h->is64 ? "f64" : h->resident_ok ? "resident" : h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream"
+                       : h->tiled.enabled ? "march" : ((h->g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) ? "vec4" : "generic");
+    uint32_t chunks = 0, rows = 0, groups = 0;
+    if (h->narrowp.enabled) {
+        chunks = narrow_chunks(h->narrowp, h->gn, h->g.Tl, h->cfg.n_chains);
+        rows = (h->g.Y + chunks - 1) / chunks;
+        groups = narrow_groups(h->narrowp, h->g.Tl);
+    }
+    snprintf(buf, cap, "path=%s chunks=%u rows_per_chunk=%u plane_blocks=%u blocks_per_sm=%d ghost_depth=%u p2p=%d", path, chunks, rows,
+             groups, h->narrowp.enabled ? h->narrowp.blocks_per_sm : 0, h->narrowp.enabled ? h->gn.ghost : h->g.ghost, h->p2p ? 1 : 0);
     return LQFT_OK;
 }
 

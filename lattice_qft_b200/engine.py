@@ -207,6 +207,16 @@ class Engine:
         check(lib().lqft_narrow_segments(self._h, C.byref(n)))
         return int(n.value)
 
+    def plan_info(self) -> dict:
+        """Launch plan of the update kernels as a dict (path, chunks, rows_per_chunk, ...)."""
+        buf = C.create_string_buffer(256)
+        check(lib().lqft_plan_info(self._h, buf, len(buf)))
+        out = {}
+        for kv in buf.value.decode().split():
+            k, v = kv.split("=", 1)
+            out[k] = int(v) if v.lstrip("-").isdigit() else v
+        return out
+
     def stream(self) -> int:
         s = C.c_void_p()
         check(lib().lqft_stream(self._h, C.byref(s)))

@@ -1,0 +1,123 @@
+"""Parity of k_sweep_n16 (kernels_narrow.cuh) on y-chunks LONGER than two rows: the third leg of the rotating
+register window, the loop-back, odd chunk starts and uneven chunk lengths — the shapes the throughput numbers are
+measured on (256^3: 37 chunks of 6-7 rows; 512^3 and 1024^2 x 128: 56-57 rows).  The reference logic these check is
+metropolis_single (algorithm.rs:127-158) through oracle/lqft_oracle.c (lqft_oracle_sweep)."""
+import numpy as np
+import pytest
+
+from lattice_qft_b200 import Engine, _lib
+from oracle import oracle as O
+from conftest import seeded_field
+
+pytestmark = pytest.mark.gpu
+NORES = _lib.FLAG_NO_RESIDENT
+
+
+def _oracle_trajectory(size, v0, beta, seed, wilson):
+    """5 counted sweeps, 4 plain ones, then a 12-step run (energy every 3rd, normalize every 10th)."""
+    lat = O.Lattice(list(size))
+    wil = O.Wilson(lat, *wilson) if wilson[0] else None
+    want = v0.copy()
+    acc = sum(O.sweep(lat, want, beta, seed, s, order=1, wilson=wil) for s in range(5))
+    for s in range(5, 9):
+        O.sweep(lat, want, beta, seed, s, order=1, wilson=wil)
+    e, _ = O.run(lat, want, beta, seed, 9, 0, 12, 3, 10, order=1, wilson=wil)
+    return want, acc, e
+
+
+def _engine_trajectory(eng, v0, beta, seed, wilson):
+    eng.set_chain(0, beta, seed, *wilson)
+    eng.upload(0, v0)
+    acc = eng.sweep(0, 5, want_accepted=True)[0]
+    eng.sweep(5, 4)
+    e, _, _ = eng.run(12, sweep_base=9, energy_every=3, normalize_every=10)
+    return eng.download(0), acc, e[0]
+
+
+@pytest.mark.parametrize("chunks", [1, 2, 3])
+@pytest.mark.parametrize("size,wilson", [
+    ((256, 14, 4), (0, 0)), ((256, 10, 6), (100, 5)), ((256, 22, 2), (0, 0)), ((256, 6, 34), (255, 20)),
+    ((512, 14, 4), (300, 3)), ((512, 10, 2), (0, 0)), ((1024, 10, 2), (0, 0)), ((1024, 14, 4), (513, 3)),
+])
+def test_narrow_rows_per_chunk_ge_3_vs_oracle(size, wilson, chunks, monkeypatch):
+    """LQFT_N16_CHUNKS forces 1, 2 or 3 y-chunks: rows per chunk 3 ... 22, chunk starts at odd y (3 chunks of 14 rows
+    start at 0, 4, 9), lengths that differ between chunks.  Counting / Wilson / plain instantiations, eager and
+    graph-replayed launches; all bit-equal to the oracle."""
+    monkeypatch.setenv("LQFT_N16_CHUNKS", str(chunks))
+    X, Y, T = size
+    beta, seed = 0.23 + 0.01 * chunks, 0xD1CE + Y
+    v0 = seeded_field(X * Y * T, seed=11 * Y + T)
+    want, wacc, we = _oracle_trajectory(size, v0, beta, seed, wilson)
+    for flags in (NORES, NORES | _lib.FLAG_NO_GRAPH):
+        with Engine(X, Y, T, flags=flags) as eng:
+            got, acc, e = _engine_trajectory(eng, v0, beta, seed, wilson)
+            plan = eng.plan_info()
+            assert plan["path"] == "narrow" and plan["chunks"] == chunks and plan["rows_per_chunk"] >= 3, plan
+            assert eng.narrow_segments() == 3
+        assert acc == wacc
+        assert (e == we).all()
+        assert (got == want).all(), f"{int((got != want).sum())} sites differ (chunks={chunks}, flags={flags})"
+
+
+@pytest.mark.parametrize("chunks", [1, 3])
+@pytest.mark.parametrize("size,wilson", [((256, 10, 40), (77, 33)), ((512, 14, 24), (0, 0)), ((1024, 6, 20), (600, 9))])
+def test_self_halo_rows_per_chunk_ge_3_vs_oracle(size, wilson, chunks, monkeypatch):
+    """The slab path (deep halo, interior under the exchange, two-range wedge launches) with long chunks."""
+    monkeypatch.setenv("LQFT_N16_CHUNKS", str(chunks))
+    X, Y, T = size
+    beta, seed = 0.25, 0x5E1F + chunks
+    v0 = seeded_field(X * Y * T, seed=Y + T)
+    want, wacc, we = _oracle_trajectory(size, v0, beta, seed, wilson)
+    with Engine(X, Y, T, flags=_lib.FLAG_SELF_HALO) as eng:
+        got, acc, e = _engine_trajectory(eng, v0, beta, seed, wilson)
+        plan = eng.plan_info()
+        assert plan["path"] == "narrow" and plan["rows_per_chunk"] >= 3 and plan["ghost_depth"] >= 2, plan
+        eng.synchronize()
+    assert acc == wacc and (e == we).all()
+    assert (got == want).all(), f"{int((got != want).sum())} sites differ"
+
+
+@pytest.mark.parametrize("size,min_rows", [((256, 256, 128), 3), ((256, 256, 256), 6), ((512, 64, 64), 3), ((1024, 64, 32), 3),
+                                           ((256, 128, 256), 3)])
+def test_narrow_natural_chunking_rows_per_chunk_ge_3_vs_scalar_kernel(size, min_rows):
+    """The cost model's own chunking at bench-sized lattices (256^3: 37 chunks of 6-7 rows), against the scalar i32
+    kernel (LQFT_FLAG_FORCE_GENERIC): post-sweep fields, acceptance counts and in-run energies bit for bit."""
+    X, Y, T = size
+    beta, seed = 0.25, 0xB16 + T
+    v0 = seeded_field(X * Y * T, seed=T, lo=-3, hi=4)
+    out = []
+    for flags in (0, _lib.FLAG_FORCE_GENERIC):
+        with Engine(X, Y, T, flags=flags) as eng:
+            out.append(_engine_trajectory(eng, v0, beta, seed, (X // 3, T // 2)))
+            plan = eng.plan_info()
+            if flags == 0:
+                assert plan["path"] == "narrow" and plan["rows_per_chunk"] >= min_rows, plan
+                assert eng.narrow_segments() == 3
+            else:
+                assert plan["path"] == "generic", plan
+    assert out[0][1] == out[1][1]
+    assert (out[0][2] == out[1][2]).all()
+    assert (out[0][0] == out[1][0]).all(), f"{int((out[0][0] != out[1][0]).sum())} sites differ"
+
+
+def test_256cubed_narrow_rows_per_chunk_ge_3_vs_oracle():
+    """The headline shape itself, 256^3, through the kernel and chunking bench.py times, against the oracle."""
+    size = (256, 256, 256)
+    X, Y, T = size
+    beta, seed = 0.25, 20261019
+    v0 = seeded_field(X * Y * T, seed=256, lo=-2, hi=3)
+    lat = O.Lattice(list(size))
+    want = v0.copy()
+    wacc = sum(O.sweep(lat, want, beta, seed, s, order=1) for s in range(4))
+    we = O.energy_observable(lat, want, beta)
+    with Engine(X, Y, T) as eng:
+        eng.set_chain(0, beta, seed)
+        eng.upload(0, v0)
+        acc = eng.sweep(0, 4, want_accepted=True)[0]
+        plan = eng.plan_info()
+        assert plan["path"] == "narrow" and plan["rows_per_chunk"] >= 6, plan
+        assert eng.narrow_segments() == 1
+        got = eng.download(0)
+        e = eng.energy()[1][0]
+    assert acc == wacc and e == we
+    assert (got == want).all(), f"{int((got != want).sum())} sites differ"

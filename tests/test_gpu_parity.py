@@ -517,12 +517,13 @@ def test_256cubed_properties():
         # round trip of the layout conversion at full size
         eng.upload(0, v0)
         assert (eng.download(0) == v0).all()
-        acc = eng.sweep(0, 3, want_accepted=True)[0]
-        ref.sweep(0, 3)
+        acc = eng.sweep(0, 5, want_accepted=True)[0]
+        assert eng.narrow_segments() > 0              # >= 4 sweeps per call: the 16-bit kernel bench.py times
+        ref.sweep(0, 5)
         v = eng.download(0)
         assert (v == ref.download(0)).all()           # two independent kernels agree bit for bit
-        assert 0 < acc <= 3 * n
-        assert np.abs(v.astype(np.int64) - v0).max() <= 3  # +-1 per sweep
+        assert 0 < acc <= 5 * n
+        assert np.abs(v.astype(np.int64) - v0).max() <= 5  # +-1 per sweep
         # shift invariance of every observable (the action only sees differences)
         e0, s0 = int(eng.energy()[0][0]), int(eng.action()[0][0])
         s1, s2 = eng.slice_moments(0)
@@ -531,7 +532,7 @@ def test_256cubed_properties():
         assert int(eng.energy()[0][0]) == e0 and int(eng.action()[0][0]) == s0
         # RNG keyed by (seed, sweep, site): same sweep index twice from the same state == same result
         eng.upload(0, v0)
-        eng.sweep(0, 3)
+        eng.sweep(0, 5)
         assert (eng.download(0) == v).all()
 
 
