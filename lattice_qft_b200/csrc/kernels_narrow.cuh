@@ -107,9 +107,10 @@ __device__ __forceinline__ uint4 n16_wilson(uint32_t k0, uint32_t p, int sgn, ui
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// ---- the half-sweep: X = 256 (SEGS = 0), 512 (SEGS = 1), 1024 (SEGS = 2) ------------------------------------------
-// A warp is one 256-position segment of a row of ONE plane — for X = 256 two half-warps on two planes of the same
-// parity; with two segments the x-neighbour across the segment edge is one predicated 4-byte load.  Per step and
+// ---- the half-sweep: X = 16 ... 1024 (powers of two); XQ = X / 16 = uint4 per row of one colour ---------------------
+// A thread owns 8 same-colour sites of a row; LPR = min(XQ, 32) lanes cover a row (or a 512-site segment of it), so a
+// warp carries 32 / LPR planes of the same parity: 1 for X >= 512, 2 for X = 256, 8 for X = 64.  X = 1024 has two
+// segments per row; the x-neighbour across the segment edge is one predicated 4-byte load.  Per step and
 // thread: own row (read + write), the other colour's rows y+1 (y-1 and y stay in a rotating register window), t+1
 // and t-1: 4 LDG.128 + 1 STG.128, two Philox blocks, 8 decisions.
 //
@@ -121,20 +122,23 @@ __device__ __forceinline__ uint4 n16_wilson(uint32_t k0, uint32_t p, int sgn, ui
 // and plain shuffles only where it can prove convergence, and it does not know that threadIdx.x >> 5 is warp
 // uniform.  Hence (a) no guard around the body — surplus warps past the end of the plane range walk plane 0 with
 // their stores predicated off, (b) the branch on the x parity depends on blockIdx only: blocks 2m and 2m+1 share
-// P consecutive planes, the even ones in block 2m, the odd ones in 2m+1 (P = 16; 32 for X = 256, where a warp
-// carries two planes), (c) SINGLE: a lone chain's parameters arrive as a kernel argument, so that the key is a
+// P consecutive planes, the even ones in block 2m, the odd ones in 2m+1 (P = 2 * warps per block * planes per
+// warp), (c) SINGLE: a lone chain's parameters arrive as a kernel argument, so that the key is a
 // parameter-bank constant.  Without these the same source compiles to 1400 instead of 1024 instructions and runs
 // 18 % slower.
-// grid = (n_chunks * max(SEGS, 1), 2 * ceil(n_planes / P), n_chains).
-template <int SEGS, bool WILSON, bool COUNT, bool SINGLE>
+// grid = (n_chunks * max(SEGS, 1), 2 * ceil(n_planes / P), n_chains); block = 32 * warps, warps <= kN16Warps chosen by
+// narrow_warps so that small lattices do not carry idle warps.
+template <int XQ, bool WILSON, bool COUNT, bool SINGLE>
 __global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
 k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
             const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
             uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
             const ChainDev* __restrict__ chains, const ChainDev chain0, const uint32_t* __restrict__ thr_all,
             unsigned long long* __restrict__ acc, const uint32_t max_thr) {
-    constexpr uint32_t ROWQ = SEGS ? 32u * SEGS : 16u;  // uint4 per row of one colour
-    constexpr uint32_t LPR = SEGS ? 32u : 16u;           // lanes of a warp on one row
+    constexpr uint32_t ROWQ = XQ;                        // uint4 per row of one colour
+    constexpr uint32_t LPR = XQ < 32 ? XQ : 32;          // lanes of a warp on one row
+    constexpr uint32_t PPW = 32u / LPR;                  // planes per warp
+    constexpr int SEGS = XQ / 32;                        // 512-site row segments (0: a row is narrower than a warp)
     __shared__ unsigned int s_cnt;
     pdl_launch_dependents();
     const uint32_t chain = SINGLE ? 0u : blockIdx.z;
@@ -148,9 +152,8 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t seg = SEGS > 1 ? blockIdx.x % SEGS : 0u, chunk = SEGS > 1 ? blockIdx.x / SEGS : blockIdx.x;
     // all planes of a block have the parity of blockIdx.y (see above)
-    const uint32_t sub = SEGS ? 0u : lane >> 4;
-    const uint32_t slot = SEGS ? warp : 2u * warp + sub;  // plane slot within the block
-    const uint32_t pl_raw = (blockIdx.y >> 1) * (SEGS ? 2u * kN16Warps : 4u * kN16Warps) + 2u * slot + (blockIdx.y & 1u);
+    const uint32_t slot = PPW * warp + lane / LPR;   // plane slot within the block
+    const uint32_t pl_raw = (blockIdx.y >> 1) * (2u * PPW * (blockDim.x >> 5)) + 2u * slot + (blockIdx.y & 1u);
     const uint32_t y0 = chunk * g.Y / n_chunks, y1 = (chunk + 1u) * g.Y / n_chunks;
     int accepted = 0;
     const bool live = pl_raw < n_planes;              // surplus warps: plane 0 of the range, stores off
@@ -159,7 +162,7 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         const uint32_t tl = pl < n_first ? (uint32_t)tl_first + pl : (uint32_t)tl_second + (pl - n_first);
         const uint32_t tg = (g.t0 + g.T + tl) % g.T;
         const bool owned = live && tl < g.Tl;
-        const uint32_t kq = SEGS ? seg * 32u + lane : lane & 15u;  // uint4 column of this thread within the row
+        const uint32_t kq = SEGS ? seg * 32u + lane : lane & (LPR - 1u);  // uint4 column of this thread within the row
         const uint32_t planeq = g.Y * ROWQ;
         const uint32_t cq = chain * (uint32_t)(g.chain_stride / 8);
         const uint32_t r_own = cq + plane_self(g, tl) * planeq;  // row 0 of this plane
@@ -345,10 +348,12 @@ __global__ void k_narrow_begin(const int32_t* __restrict__ offset, int32_t* __re
 // ---- host side ----------------------------------------------------------------------------------------------
 struct NarrowPlan {
     bool enabled = false;
-    int segs = 0;          // row segments of 256 positions: 0 (X = 256, half a warp per row), 1 (X = 512), 2 (X = 1024)
-    int blocks_per_sm = 0;
+    int xq = 0;            // X / 16: uint4 per row of one colour (1 ... 64)
     int sm_count = 0;
     uint32_t forced_chunks = 0;  // LQFT_N16_CHUNKS (tests): y chunks per plane group instead of the cost model's choice
+    int occ[2][2][kN16Warps + 1];  // resident blocks per SM by (WILSON, COUNT, warps per block); 0 = not asked yet
+    int segs() const { return xq / 32; }                       // 512-site row segments
+    uint32_t ppw() const { return xq < 32 ? 32u / xq : 1u; }   // planes per warp
 };
 
 struct NarrowArgs {
@@ -373,8 +378,30 @@ struct NarrowArgs {
     bool pdl;
 };
 
+template <int XQ>
+inline const void* n16_variant(bool w, bool c, bool s) {
+    if (w) {
+        if (c) return s ? (const void*)k_sweep_n16<XQ, true, true, true> : (const void*)k_sweep_n16<XQ, true, true, false>;
+        return s ? (const void*)k_sweep_n16<XQ, true, false, true> : (const void*)k_sweep_n16<XQ, true, false, false>;
+    }
+    if (c) return s ? (const void*)k_sweep_n16<XQ, false, true, true> : (const void*)k_sweep_n16<XQ, false, true, false>;
+    return s ? (const void*)k_sweep_n16<XQ, false, false, true> : (const void*)k_sweep_n16<XQ, false, false, false>;
+}
+inline const void* n16_kernel(int xq, bool w, bool c, bool s) {
+    switch (xq) {
+        case 1: return n16_variant<1>(w, c, s);
+        case 2: return n16_variant<2>(w, c, s);
+        case 4: return n16_variant<4>(w, c, s);
+        case 8: return n16_variant<8>(w, c, s);
+        case 16: return n16_variant<16>(w, c, s);
+        case 32: return n16_variant<32>(w, c, s);
+        case 64: return n16_variant<64>(w, c, s);
+    }
+    return nullptr;
+}
+
 inline bool narrow_geometry_ok(const Geom& g, uint32_t max_thr, uint32_t n_chains) {
-    return (g.X == 256 || g.X == 512 || g.X == 1024) && g.Tl >= 2 && g.Tl % 2 == 0 &&
+    return g.X >= 16 && g.X <= 1024 && (g.X & (g.X - 1)) == 0 && g.Tl >= 2 && g.Tl % 2 == 0 &&
            max_thr <= (uint32_t)kN16KcMax + 1 &&
            (uint64_t)g.plane / 8 * (g.Tl + 2 * kN16GhostDepth) * n_chains < (1ull << 30) &&  // uint4 and word offsets in 32 bits
            (uint64_t)g.T * g.Y * (g.X / 8) < (1ull << 32);
@@ -384,30 +411,46 @@ inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, uint32_t n_chain
     p.enabled = false;
     if (force_off || !narrow_geometry_ok(g, max_thr, n_chains)) return cudaSuccess;
     p.sm_count = sm_count;
-    p.segs = g.X == 256 ? 0 : (int)(g.X / 512);
-    cudaError_t e;
-    if (p.segs == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<0, false, false, true>, kN16Threads, 0);
-    else if (p.segs == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<1, false, false, true>, kN16Threads, 0);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p.blocks_per_sm, k_sweep_n16<2, false, false, true>, kN16Threads, 0);
-    if (e != cudaSuccess) return e;
-    p.enabled = p.blocks_per_sm > 0;
+    p.xq = (int)(g.X / 16);
+    memset(p.occ, 0, sizeof p.occ);
+    p.enabled = true;
     p.forced_chunks = 0;
     if (const char* e = getenv("LQFT_N16_CHUNKS")) p.forced_chunks = (uint32_t)atoi(e);
     return cudaSuccess;
 }
 
-// grid.y: blocks along the planes: block pairs (even / odd planes) over 16 planes, or over 32 for X = 256 where a
-// warp carries two planes.
+// Warps per block: as many as the planes of one parity need, at most kN16Warps.
+inline uint32_t narrow_warps(const NarrowPlan& p, uint32_t n_planes) {
+    const uint32_t need = ((n_planes + 1) / 2 + p.ppw() - 1) / p.ppw();
+    return need < 1 ? 1 : (need > (uint32_t)kN16Warps ? (uint32_t)kN16Warps : need);
+}
+
+// Resident blocks per SM of the instantiation a launch will use (each has its own register count).
+inline int narrow_occupancy(NarrowPlan& p, bool wilson, bool count, uint32_t warps) {
+    int& o = p.occ[wilson][count][warps];
+    if (o == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, n16_kernel(p.xq, wilson, count, true), (int)(32 * warps), 0) != cudaSuccess) {
+            cudaGetLastError();
+            n = 1;
+        }
+        o = n > 0 ? n : 1;
+    }
+    return o;
+}
+
+// grid.y: blocks along the planes: block pairs (even / odd planes) over 2 * warps * planes-per-warp planes.
 inline uint32_t narrow_groups(const NarrowPlan& p, uint32_t n_planes) {
-    const uint32_t per_pair = p.segs ? 2 * kN16Warps : 4 * kN16Warps;
+    const uint32_t per_pair = 2 * narrow_warps(p, n_planes) * p.ppw();
     return 2 * ((n_planes + per_pair - 1) / per_pair);
 }
 
 // y chunks per plane group: one wave if possible, chunks as short as that allows (cost model of stream_chunks;
 // the per-chunk prologue is worth about two rows here).
-inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_planes, uint32_t n_chains) {
-    const uint64_t slots = (uint64_t)p.sm_count * p.blocks_per_sm;
-    const uint64_t base = narrow_groups(p, n_planes) * (uint64_t)(p.segs ? p.segs : 1) * n_chains;  // blocks per chunk
+inline uint32_t narrow_chunks(NarrowPlan& p, const Geom& g, uint32_t n_planes, uint32_t n_chains, bool wilson = false,
+                              bool count = false) {
+    const uint64_t slots = (uint64_t)p.sm_count * narrow_occupancy(p, wilson, count, narrow_warps(p, n_planes));
+    const uint64_t base = narrow_groups(p, n_planes) * (uint64_t)(p.segs() ? p.segs() : 1) * n_chains;  // blocks per chunk
     const uint32_t max_chunks = g.Y / 2 ? g.Y / 2 : 1;
     if (p.forced_chunks) return p.forced_chunks < g.Y ? p.forced_chunks : g.Y;
     uint32_t best = 1;
@@ -425,12 +468,12 @@ inline uint32_t narrow_chunks(const NarrowPlan& p, const Geom& g, uint32_t n_pla
     return best;
 }
 
-inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
+inline cudaError_t narrow_half(NarrowPlan& p, const NarrowArgs& a) {
     const uint32_t n_groups = narrow_groups(p, a.n_planes);
-    const uint32_t n_chunks = narrow_chunks(p, a.g, a.n_planes, a.n_chains);
+    uint32_t n_chunks = narrow_chunks(p, a.g, a.n_planes, a.n_chains, a.wilson, a.count);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_chunks * (p.segs ? p.segs : 1), n_groups, a.n_chains);
-    cfg.blockDim = dim3(kN16Threads);
+    cfg.gridDim = dim3(n_chunks * (p.segs() ? p.segs() : 1), n_groups, a.n_chains);
+    cfg.blockDim = dim3(32 * narrow_warps(p, a.n_planes));
     cfg.dynamicSmemBytes = 0;
     cfg.stream = a.stream;
     cudaLaunchAttribute attr[1];
@@ -438,29 +481,22 @@ inline cudaError_t narrow_half(const NarrowPlan& p, const NarrowArgs& a) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = a.pdl ? 1 : 0;
-#define LQFT_ARGS a.g, a.colour, a.sweep, a.ctr, a.tl_first, a.n_first, a.tl_second, a.n_planes, n_chunks, a.own, a.oth, a.chains, \
-                  a.chain0, a.thr, a.acc, a.max_thr
-#define LQFT_GO(W, C, S)                                                                         \
-    {                                                                                            \
-        if (p.segs == 0) return cudaLaunchKernelEx(&cfg, k_sweep_n16<0, W, C, S>, LQFT_ARGS);   \
-        if (p.segs == 1) return cudaLaunchKernelEx(&cfg, k_sweep_n16<1, W, C, S>, LQFT_ARGS);   \
-        return cudaLaunchKernelEx(&cfg, k_sweep_n16<2, W, C, S>, LQFT_ARGS);                    \
-    }
-    if (a.n_chains == 1) {
-        if (a.wilson) {
-            if (a.count) LQFT_GO(true, true, true) else LQFT_GO(true, false, true)
-        } else {
-            if (a.count) LQFT_GO(false, true, true) else LQFT_GO(false, false, true)
-        }
-    }
-    if (a.wilson) {
-        if (a.count) LQFT_GO(true, true, false) else LQFT_GO(true, false, false)
-    } else {
-        if (a.count) LQFT_GO(false, true, false) else LQFT_GO(false, false, false)
-    }
-#undef LQFT_GO
-#undef LQFT_ARGS
-    return cudaGetLastError();
+    // parameter order of k_sweep_n16
+    Geom g = a.g;
+    int colour = a.colour;
+    uint64_t sweep = a.sweep;
+    const uint64_t* ctr = a.ctr;
+    int32_t tl_first = a.tl_first, tl_second = a.tl_second;
+    uint32_t n_first = a.n_first, n_planes = a.n_planes, max_thr = a.max_thr;
+    uint16_t* own = a.own;
+    const uint16_t* oth = a.oth;
+    const ChainDev* chains = a.chains;
+    ChainDev chain0 = a.chain0;
+    const uint32_t* thr = a.thr;
+    unsigned long long* acc = a.acc;
+    void* args[] = {&g, &colour, &sweep, &ctr, &tl_first, &n_first, &tl_second, &n_planes, &n_chunks, &own, &oth, &chains,
+                    &chain0, &thr, &acc, &max_thr};
+    return cudaLaunchKernelExC(&cfg, n16_kernel(p.xq, a.wilson, a.count, a.n_chains == 1), args);
 }
 
 }  // namespace lqft

@@ -246,12 +246,12 @@ static lqft_status upload_params(lqft_handle* h) {
         CU(cudaFuncSetAttribute(k_run_resident<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     CU(narrow_prepare(h->narrowp, h->g, nc, h->sm_count, h->max_thr,
-                      !h->narrow[0] || h->resident_ok || !h->streamp.enabled || (h->g.ghost != 0 && !h->p2p)));
+                      !h->narrow[0] || h->resident_ok || (h->g.ghost != 0 && !h->p2p)));
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
     if (getenv("LQFT_DEBUG"))
         fprintf(stderr, "[lqft] %ux%ux%u chains=%u path=%s (stream: segs=%d blocks/SM=%d chunks=%u; march: g=%d rows=%d)\n",
-                h->g.X, h->g.Y, h->g.T, nc, h->narrowp.enabled ? "narrow+stream" : h->streamp.enabled ? "stream" : (h->tiled.enabled ? "march" : "v1"),
+                h->g.X, h->g.Y, h->g.T, nc, h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream" : (h->tiled.enabled ? "march" : "v1"),
                 h->streamp.segs, h->streamp.blocks_per_sm,
                 h->streamp.enabled ? stream_chunks(h->streamp, h->g, h->g.Tl, nc) : 0u, h->tiled.g, h->tiled.march);
     return LQFT_OK;
@@ -1690,13 +1690,15 @@ extern "C" lqft_status lqft_plan_info(lqft_handle* h, char* buf, size_t cap) {
     const char* path = h->is64 ? "f64" : h->resident_ok ? "resident" : h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream"
                        : h->tiled.enabled ? "march" : ((h->g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) ? "vec4" : "generic");
     uint32_t chunks = 0, rows = 0, groups = 0;
+    int occ = 0;
     if (h->narrowp.enabled) {
-        chunks = narrow_chunks(h->narrowp, h->gn, h->g.Tl, h->cfg.n_chains);
+        chunks = narrow_chunks(h->narrowp, h->gn, h->g.Tl, h->cfg.n_chains, h->any_wilson, false);
         rows = (h->g.Y + chunks - 1) / chunks;
         groups = narrow_groups(h->narrowp, h->g.Tl);
+        occ = narrow_occupancy(h->narrowp, h->any_wilson, false, narrow_warps(h->narrowp, h->g.Tl));
     }
     snprintf(buf, cap, "path=%s chunks=%u rows_per_chunk=%u plane_blocks=%u blocks_per_sm=%d ghost_depth=%u p2p=%d", path, chunks, rows,
-             groups, h->narrowp.enabled ? h->narrowp.blocks_per_sm : 0, h->narrowp.enabled ? h->gn.ghost : h->g.ghost, h->p2p ? 1 : 0);
+             groups, occ, h->narrowp.enabled ? h->gn.ghost : h->g.ghost, h->p2p ? 1 : 0);
     return LQFT_OK;
 }
 

@@ -36,7 +36,7 @@ def _engine_trajectory(eng, v0, beta, seed, wilson):
 
 @pytest.mark.parametrize("chunks", [1, 2, 3])
 @pytest.mark.parametrize("size,wilson", [
-    ((256, 14, 4), (0, 0)), ((256, 10, 6), (100, 5)), ((256, 22, 2), (0, 0)), ((256, 6, 34), (255, 20)),
+    ((256, 14, 4), (0, 0)), ((256, 10, 6), (100, 5)), ((256, 22, 2), (0, 0)), ((256, 10, 34), (255, 20)),
     ((512, 14, 4), (300, 3)), ((512, 10, 2), (0, 0)), ((1024, 10, 2), (0, 0)), ((1024, 14, 4), (513, 3)),
 ])
 def test_narrow_rows_per_chunk_ge_3_vs_oracle(size, wilson, chunks, monkeypatch):
@@ -60,7 +60,7 @@ def test_narrow_rows_per_chunk_ge_3_vs_oracle(size, wilson, chunks, monkeypatch)
 
 
 @pytest.mark.parametrize("chunks", [1, 3])
-@pytest.mark.parametrize("size,wilson", [((256, 10, 40), (77, 33)), ((512, 14, 24), (0, 0)), ((1024, 6, 20), (600, 9))])
+@pytest.mark.parametrize("size,wilson", [((256, 10, 40), (77, 33)), ((512, 14, 24), (0, 0)), ((1024, 10, 20), (600, 9))])
 def test_self_halo_rows_per_chunk_ge_3_vs_oracle(size, wilson, chunks, monkeypatch):
     """The slab path (deep halo, interior under the exchange, two-range wedge launches) with long chunks."""
     monkeypatch.setenv("LQFT_N16_CHUNKS", str(chunks))
@@ -77,7 +77,7 @@ def test_self_halo_rows_per_chunk_ge_3_vs_oracle(size, wilson, chunks, monkeypat
     assert (got == want).all(), f"{int((got != want).sum())} sites differ"
 
 
-@pytest.mark.parametrize("size,min_rows", [((256, 256, 128), 3), ((256, 256, 256), 6), ((512, 64, 64), 3), ((1024, 64, 32), 3),
+@pytest.mark.parametrize("size,min_rows", [((256, 256, 128), 3), ((256, 256, 256), 6), ((512, 256, 64), 4), ((1024, 256, 32), 4),
                                            ((256, 128, 256), 3)])
 def test_narrow_natural_chunking_rows_per_chunk_ge_3_vs_scalar_kernel(size, min_rows):
     """The cost model's own chunking at bench-sized lattices (256^3: 37 chunks of 6-7 rows), against the scalar i32
@@ -121,3 +121,57 @@ def test_256cubed_narrow_rows_per_chunk_ge_3_vs_oracle():
         e = eng.energy()[1][0]
     assert acc == wacc and e == we
     assert (got == want).all(), f"{int((got != want).sum())} sites differ"
+
+
+@pytest.mark.parametrize("chunks", [0, 1, 3])
+@pytest.mark.parametrize("size,wilson", [
+    ((16, 16, 16), (5, 16)), ((16, 10, 70), (0, 0)), ((32, 12, 8), (0, 0)), ((32, 10, 36), (21, 30)),
+    ((64, 64, 64), (21, 32)), ((64, 14, 18), (0, 0)), ((64, 10, 2), (64, 2)), ((128, 16, 12), (0, 0)),
+    ((128, 10, 34), (100, 20)), ((128, 128, 128), (0, 0)),
+])
+def test_narrow_rows_shorter_than_a_warp_vs_oracle(size, wilson, chunks, monkeypatch):
+    """X = 16 ... 128: a warp carries 32 / (X / 16) planes of one parity (kernels_narrow.cuh, PPW); the x-edge
+    neighbour comes from a shuffle within the lanes of one row (X = 16: the thread's own other-colour quad).
+    Plane counts that do not fill a warp or a block, forced long chunks, Wilson sheets, counts, graphs."""
+    if chunks:
+        monkeypatch.setenv("LQFT_N16_CHUNKS", str(chunks))
+    X, Y, T = size
+    beta, seed = 0.26, 0xFACE + X + T
+    v0 = seeded_field(X * Y * T, seed=X + Y + T)
+    want, wacc, we = _oracle_trajectory(size, v0, beta, seed, wilson)
+    for flags in (NORES, NORES | _lib.FLAG_NO_GRAPH):
+        with Engine(X, Y, T, flags=flags) as eng:
+            got, acc, e = _engine_trajectory(eng, v0, beta, seed, wilson)
+            plan = eng.plan_info()
+            assert plan["path"] == "narrow", plan
+            assert eng.narrow_segments() == 3
+        assert acc == wacc
+        assert (e == we).all()
+        assert (got == want).all(), f"{int((got != want).sum())} sites differ (chunks={chunks}, flags={flags})"
+
+
+def test_narrow_64cubed_many_chains_match_single_chain_runs():
+    """Config 2's shape (64^3 chains batched along blockIdx.z) on the 16-bit kernel: five chains with their own
+    couplings, seeds and Wilson sheets equal five single-chain runs on the scalar kernel."""
+    X = Y = T = 64
+    betas = [0.2, 0.23, 0.25, 0.28, 0.31]
+    v0 = [seeded_field(X * Y * T, seed=640 + c) for c in range(5)]
+    single = []
+    for c in range(5):
+        with Engine(X, Y, T, flags=_lib.FLAG_FORCE_GENERIC) as eng:
+            eng.set_chain(0, betas[c], 64000 + c, 10 * c, 13 * c)
+            eng.upload(0, v0[c])
+            acc = eng.sweep(0, 6, want_accepted=True)[0]
+            e, _, _ = eng.run(20, sweep_base=6, energy_every=5, normalize_every=10)
+            single.append((acc, e[0].copy(), eng.download(0)))
+    with Engine(X, Y, T, n_chains=5) as eng:
+        for c in range(5):
+            eng.set_chain(c, betas[c], 64000 + c, 10 * c, 13 * c)
+            eng.upload(c, v0[c])
+        acc = eng.sweep(0, 6, want_accepted=True)
+        e, _, _ = eng.run(20, sweep_base=6, energy_every=5, normalize_every=10)
+        assert eng.plan_info()["path"] == "narrow" and eng.narrow_segments() == 2
+        for c in range(5):
+            assert acc[c] == single[c][0]
+            assert (e[c] == single[c][1]).all()
+            assert (eng.download(c) == single[c][2]).all()
