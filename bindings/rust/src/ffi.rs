@@ -37,6 +37,20 @@ pub struct lqft_schedule {
     pub n_steps: u64,
     pub energy_every: u32,
     pub normalize_every: u32,
+    pub action_every: u32,
+    pub correlator_every: u32,
+    pub correlator_reps: u32,
+    pub difference_every: u32,
+}
+
+#[repr(C)]
+pub struct lqft_run_outputs {
+    pub e_obs: *mut f64,
+    pub e_int: *mut i64,
+    pub s_obs: *mut f64,
+    pub s_int: *mut i64,
+    pub corr: *mut f64,
+    pub accepted: *mut u64,
 }
 
 extern "C" {
@@ -62,6 +76,7 @@ extern "C" {
     pub fn lqft_difference_read(h: *mut lqft_handle, chain: u32, mean: *mut f64, count: *mut u64) -> i32;
     pub fn lqft_run_measurements(first_step: u64, n_steps: u64, every: u32) -> u64;
     pub fn lqft_run(h: *mut lqft_handle, s: *const lqft_schedule, e_obs: *mut f64, e_int: *mut i64, accepted: *mut u64) -> i32;
+    pub fn lqft_run_observables(h: *mut lqft_handle, s: *const lqft_schedule, out: *const lqft_run_outputs) -> i32;
     pub fn lqft_synchronize(h: *mut lqft_handle) -> i32;
     pub fn lqft_last_device_ms(h: *mut lqft_handle, ms: *mut f32) -> i32;
     pub fn lqft_kernel_launches(h: *mut lqft_handle, n: *mut u64) -> i32;

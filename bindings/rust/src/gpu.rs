@@ -40,12 +40,32 @@ impl Gpu {
     /// Loop body of Simulation::run for `n_steps` steps; returns the energies (chain-major).
     pub fn run(&self, sweep_base: u64, first_step: u64, n_steps: u64, energy_every: u32, normalize_every: u32)
         -> Result<Vec<f64>, Box<dyn Error>> {
-        let s = lqft_schedule { sweep_base, first_step, n_steps, energy_every, normalize_every };
+        let s = lqft_schedule { sweep_base, first_step, n_steps, energy_every, normalize_every, action_every: 0,
+                                correlator_every: 0, correlator_reps: 0, difference_every: 0 };
         let n = unsafe { lqft_run_measurements(first_step, n_steps, energy_every) } as usize;
         let mut e = vec![0f64; n * self.n_chains as usize];
         let p = if n > 0 { e.as_mut_ptr() } else { std::ptr::null_mut() };
         check(unsafe { lqft_run(self.raw, &s, p, std::ptr::null_mut(), std::ptr::null_mut()) })?;
         Ok(e)
+    }
+    /// The whole measurement loop of `Simulation::run` (computation.rs:247-270) in one call: every `OutputData`
+    /// kind on its own frequency, logged on the device.  Returns (energies, actions, correlator rows) of chain 0.
+    pub fn run_observables(&self, s: &lqft_schedule) -> Result<(Vec<f64>, Vec<f64>, Vec<Vec<f64>>), Box<dyn Error>> {
+        let nc = self.n_chains as usize;
+        let ne = unsafe { lqft_run_measurements(s.first_step, s.n_steps, s.energy_every) } as usize;
+        let na = unsafe { lqft_run_measurements(s.first_step, s.n_steps, s.action_every) } as usize;
+        let ncr = unsafe { lqft_run_measurements(s.first_step, s.n_steps, s.correlator_every) } as usize;
+        let (mut e, mut a, mut c) = (vec![0f64; ne * nc], vec![0f64; na * nc], vec![0f64; ncr * nc * self.t]);
+        let nullable = |v: &mut Vec<f64>| if v.is_empty() { std::ptr::null_mut() } else { v.as_mut_ptr() };
+        let out = lqft_run_outputs {
+            e_obs: nullable(&mut e), e_int: std::ptr::null_mut(), s_obs: nullable(&mut a), s_int: std::ptr::null_mut(),
+            corr: nullable(&mut c), accepted: std::ptr::null_mut(),
+        };
+        check(unsafe { lqft_run_observables(self.raw, s, &out) })?;
+        e.truncate(ne);
+        a.truncate(na);
+        let rows = c[..ncr * self.t].chunks(self.t).map(|r| r.to_vec()).collect();
+        Ok((e, a, rows))
     }
     pub fn sweep(&self, sweep: u64) -> Result<usize, Box<dyn Error>> {
         let mut acc = vec![0u64; self.n_chains as usize];

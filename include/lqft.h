@@ -35,7 +35,7 @@ extern "C" {
 #endif
 
 #define LQFT_VERSION_MAJOR 0
-#define LQFT_VERSION_MINOR 1
+#define LQFT_VERSION_MINOR 2
 
 typedef enum lqft_status {
     LQFT_OK = 0,
@@ -166,19 +166,42 @@ lqft_status lqft_difference_read(lqft_handle* h, uint32_t chain, double* mean, u
 /* ---- fused measurement schedule -------------------------------------------------- */
 /* The loop bodies of Simulation::run / WilsonSim::run (computation.rs:229-270, 313-340) for
  * steps [first_step, first_step + n_steps): per step one sweep (RNG counter sweep_base +
- * step), then if step % energy_every == 0 an energy measurement of every chain, then if
- * step % 10 == 0 normalize_random.  energy_every == 0 measures nothing.  e_obs receives
- * n_chains * ceil-count values, chain-major: e_obs[chain * n_meas + m]; n_meas =
- * lqft_run_measurements(first_step, n_steps, energy_every).  Everything runs on the device
- * without host round trips; results are copied back once at the end. */
+ * step), then every observable whose frequency divides the step (the OutputData filter of
+ * computation.rs:262-265, set_frequency outputdata.rs:99-107), then if step % normalize_every
+ * == 0 normalize_random (computation.rs:267-269).  A frequency of 0 switches that item off.
+ *   energy_every      EnergyObservable::update        (outputdata.rs:168-178)
+ *   action_every      ActionObservableNew::update     (outputdata.rs:202-212)
+ *   correlator_every  CorrelationPlotOutputData::update with `correlator_reps` reference sites
+ *                     (outputdata.rs:313-344); the sites of step s come from stream
+ *                     LQFT_STREAM_CORRELATOR at counter sweep_base + s, rep r (lqft_host_pick_site) —
+ *                     the same sites lqft_correlator(h, chain, NULL, reps, sweep_base + s, ..) draws
+ *   difference_every  DifferencePlotOutputData::update of every chain (outputdata.rs:241-256);
+ *                     read with lqft_difference_read
+ * Measurements are taken of every chain.  Everything runs on the device without host round
+ * trips (one CUDA graph per period of the schedule); the logs are copied back once at the end. */
 typedef struct lqft_schedule {
     uint64_t sweep_base;    /* RNG sweep counter of step 0 (burn-in offset)              */
     uint64_t first_step;
     uint64_t n_steps;
-    uint32_t energy_every;  /* OutputData::set_frequency (outputdata.rs:99-107); 0 = off  */
-    uint32_t normalize_every; /* 10 in the reference (computation.rs:242,267); 0 = off     */
+    uint32_t energy_every;
+    uint32_t normalize_every; /* 10 in the reference (computation.rs:242,267)            */
+    uint32_t action_every;
+    uint32_t correlator_every;
+    uint32_t correlator_reps; /* 100 in src/bin/sim.rs:78                                */
+    uint32_t difference_every;
 } lqft_schedule;
+/* Where lqft_run_observables puts its logs; every pointer is nullable.  n_x =
+ * lqft_run_measurements(first_step, n_steps, x_every); all arrays are chain-major:
+ * e_obs[chain * n_energy + m], corr[(chain * n_corr + m) * T + tau]. */
+typedef struct lqft_run_outputs {
+    double* e_obs;   int64_t* e_int;   /* energy_observable = beta * integer_energy (fields.rs:669-671) */
+    double* s_obs;   int64_t* s_int;   /* action_observable = beta * action (fields.rs:665-667)         */
+    double* corr;                      /* T values per measurement (one row of correlation_{i}.csv)     */
+    uint64_t* accepted;                /* [n_chains] accepted proposals over the call (this rank's slab) */
+} lqft_run_outputs;
 uint64_t lqft_run_measurements(uint64_t first_step, uint64_t n_steps, uint32_t every);
+lqft_status lqft_run_observables(lqft_handle* h, const lqft_schedule* s, const lqft_run_outputs* out);
+/* lqft_run_observables with the energy log and the acceptance counts only. */
 lqft_status lqft_run(lqft_handle* h, const lqft_schedule* s, double* e_obs /*nullable*/,
                      int64_t* e_int /*nullable*/, uint64_t* accepted /*nullable*/);
 

@@ -33,6 +33,16 @@ class Schedule(C.Structure):
     _fields_ = [
         ("sweep_base", C.c_uint64), ("first_step", C.c_uint64), ("n_steps", C.c_uint64),
         ("energy_every", C.c_uint32), ("normalize_every", C.c_uint32),
+        ("action_every", C.c_uint32), ("correlator_every", C.c_uint32), ("correlator_reps", C.c_uint32),
+        ("difference_every", C.c_uint32),
+    ]
+
+
+class RunOutputs(C.Structure):
+    _fields_ = [
+        ("e_obs", C.POINTER(C.c_double)), ("e_int", C.POINTER(C.c_int64)),
+        ("s_obs", C.POINTER(C.c_double)), ("s_int", C.POINTER(C.c_int64)),
+        ("corr", C.POINTER(C.c_double)), ("accepted", C.POINTER(C.c_uint64)),
     ]
 
 
@@ -62,6 +72,7 @@ SIGNATURES = {
     "lqft_difference_read": (C.c_int, [vp, u32, P(f64), P(u64)]),
     "lqft_run_measurements": (u64, [u64, u64, u32]),
     "lqft_run": (C.c_int, [vp, P(Schedule), P(f64), P(i64), P(u64)]),
+    "lqft_run_observables": (C.c_int, [vp, P(Schedule), P(RunOutputs)]),
     "lqft_synchronize": (C.c_int, [vp]),
     "lqft_last_device_ms": (C.c_int, [vp, P(C.c_float)]),
     "lqft_kernel_launches": (C.c_int, [vp, P(u64)]),

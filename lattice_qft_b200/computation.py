@@ -81,27 +81,39 @@ class Computation:
             accepted += acc[0]
         # WilsonSim ignores `frequency` (quirk Q4, :334-336) and measures the plain field (Q3, :335)
         freq = (lambda o: 1) if self.is_wilson else (lambda o: o.frequency)
-        energy_outs = [o for o in self.output if isinstance(o.data, EnergyObservable)]
-        fused = energy_outs[0] if energy_outs else None
-        others = [o for o in self.output if o is not fused]
+        # the first output of each kind is measured and logged on the device inside ONE lqft_run_observables call;
+        # a second output of the same kind (no reference driver has one) is updated from the host between calls
+        fused, others = {}, []
+        for o in self.output:
+            if type(o.data) not in fused:
+                fused[type(o.data)] = o
+            else:
+                others.append(o)
+        fe, fa = fused.get(EnergyObservable), fused.get(ActionObservableNew)
+        fc, fd = fused.get(CorrelationPlotOutputData), fused.get(DifferencePlotOutputData)
         rng = SweepRng(self.seed)
         step, end = 0, self.iterations
         while step < end:
-            # next step at which a host-side observable is due (they are shift invariant, so
-            # measuring after that step's normalize equals the reference's order)
             nxt = end - 1
             for o in others:
                 f = freq(o)
-                due = ((step + f - 1) // f) * f
-                nxt = min(nxt, due)
+                nxt = min(nxt, ((step + f - 1) // f) * f)
             n = nxt - step + 1
-            e_obs, _, acc = eng.run(n, first_step=step, sweep_base=self.burnin,
-                                    energy_every=freq(fused) if fused else 0,
-                                    normalize_every=NORMALIZE_EVERY, want_accepted=True)
-            accepted += acc[0]
+            res = eng.run_observables(
+                n, first_step=step, sweep_base=self.burnin,
+                energy_every=freq(fe) if fe else 0, action_every=freq(fa) if fa else 0,
+                correlator_every=freq(fc) if fc else 0, correlator_reps=fc.data.repetitions if fc else 0,
+                difference_every=freq(fd) if fd else 0, normalize_every=NORMALIZE_EVERY, want_accepted=True)
+            accepted += res["accepted"][0]
             field._device_changed()
-            if fused is not None:
-                fused.data.values.extend(e_obs[0].tolist())
+            if fe is not None:
+                fe.data.values.extend(res["e_obs"][0].tolist())
+            if fa is not None:
+                fa.data.values.extend(res["s_obs"][0].tolist())
+            if fc is not None:
+                fc.data.corr_fn.extend(res["corr"][0].tolist())
+            if fd is not None:
+                fd.data._field = field
             for o in others:
                 if nxt % freq(o) == 0:
                     o.update(field, rng)

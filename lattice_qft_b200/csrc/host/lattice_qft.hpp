@@ -271,34 +271,54 @@ struct Computation {  // enum Computation::{Simulation, WilsonSim} (computation.
         return s.str();
     }
 
-    // Compute::run (computation.rs:221-281, 304-350): the device handle lives for the whole run; every
-    // stretch between host-visible measurements is one lqft_run call (CUDA graph replay on the device).
+    // Compute::run (computation.rs:221-281, 304-350): the device handle lives for the whole run.  The burn-in is one
+    // lqft_run call; the measurement phase is ONE lqft_run_observables call in which the first output of each kind
+    // is measured and logged on the device at its own frequency (computation.rs:262-265).  Only a second output of
+    // the same kind (never used by the reference's drivers) falls back to a host loop between calls.
     Computation run() && {
         auto t0 = std::chrono::steady_clock::now();
         fields::Field field = fields::Field::random(*lattice, seed, device);
         lqft_handle* h = field.gpu->raw();
         check(lqft_set_chain(h, 0, temp, seed, wilson ? width : 0, wilson ? height : 0));
         lqft_schedule s{};
-        s.sweep_base = 0; s.first_step = 0; s.n_steps = burnin; s.energy_every = 0; s.normalize_every = 10;
+        s.sweep_base = 0; s.first_step = 0; s.n_steps = burnin; s.normalize_every = 10;
         if (burnin) check(lqft_run(h, &s, nullptr, nullptr, nullptr));
         auto freq = [&](const OutputData& o) { return wilson ? (uint64_t)1 : o.frequency; };  // quirk Q4
-        OutputData* fused = nullptr;
-        for (auto& o : output)
-            if (o.kind == Kind::EnergyObservable) { fused = &o; break; }
+        OutputData* fused[4] = {nullptr, nullptr, nullptr, nullptr};
+        std::vector<OutputData*> others;
+        for (auto& o : output) {
+            OutputData*& slot = fused[(int)o.kind];
+            if (!slot) slot = &o; else others.push_back(&o);
+        }
+        const uint32_t T = lattice->size[2];
         uint64_t step = 0;
         while (step < iterations) {
             uint64_t nxt = iterations - 1;
-            for (auto& o : output)
-                if (&o != fused) nxt = std::min(nxt, (step + freq(o) - 1) / freq(o) * freq(o));
+            for (auto* o : others) nxt = std::min(nxt, (step + freq(*o) - 1) / freq(*o) * freq(*o));
             const uint64_t n = nxt - step + 1;
-            s.sweep_base = burnin; s.first_step = step; s.n_steps = n;
-            s.energy_every = fused ? (uint32_t)freq(*fused) : 0;
-            const uint64_t n_meas = lqft_run_measurements(step, n, s.energy_every);
-            std::vector<double> e(n_meas ? n_meas : 1);
-            check(lqft_run(h, &s, n_meas ? e.data() : nullptr, nullptr, nullptr));
-            if (fused) fused->values.insert(fused->values.end(), e.begin(), e.begin() + n_meas);
-            for (auto& o : output)
-                if (&o != fused && nxt % freq(o) == 0) o.update(field, burnin + nxt);
+            s = lqft_schedule{};
+            s.sweep_base = burnin; s.first_step = step; s.n_steps = n; s.normalize_every = 10;
+            OutputData* fe = fused[(int)Kind::EnergyObservable];
+            OutputData* fa = fused[(int)Kind::ActionObservable];
+            OutputData* fc = fused[(int)Kind::CorrelationData];
+            OutputData* fd = fused[(int)Kind::DifferencePlot];
+            if (fe) s.energy_every = (uint32_t)freq(*fe);
+            if (fa) s.action_every = (uint32_t)freq(*fa);
+            if (fc) { s.correlator_every = (uint32_t)freq(*fc); s.correlator_reps = (uint32_t)fc->repetitions; }
+            if (fd) s.difference_every = (uint32_t)freq(*fd);
+            const uint64_t ne = lqft_run_measurements(step, n, s.energy_every), na = lqft_run_measurements(step, n, s.action_every),
+                           ncr = lqft_run_measurements(step, n, s.correlator_every);
+            std::vector<double> e(ne), a(na), c(ncr * T);
+            lqft_run_outputs out{};
+            out.e_obs = ne ? e.data() : nullptr;
+            out.s_obs = na ? a.data() : nullptr;
+            out.corr = ncr ? c.data() : nullptr;
+            check(lqft_run_observables(h, &s, &out));
+            if (fe) fe->values.insert(fe->values.end(), e.begin(), e.end());
+            if (fa) fa->values.insert(fa->values.end(), a.begin(), a.end());
+            for (uint64_t m = 0; m < ncr; ++m) fc->corr_fn.emplace_back(c.begin() + m * T, c.begin() + (m + 1) * T);
+            for (auto* o : others)
+                if (nxt % freq(*o) == 0) o->update(field, burnin + nxt);
             step = nxt + 1;
         }
         for (auto& o : output) o.finish(field);

@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/lqft.h"
@@ -21,6 +23,7 @@
 #include "kernels_resident.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_narrow.cuh"
+#include "kernels_observe.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_v1.cuh"
 #include "spec.cuh"
@@ -110,14 +113,13 @@ static lqft_status nccl_load() {
 // handle
 // ---------------------------------------------------------------------------------------------
 struct GraphKey {
-    uint32_t energy_every, normalize_every, cycle;
+    uint32_t energy_every, normalize_every, action_every, correlator_every, correlator_reps, difference_every, cycle;
     bool count, narrow;
     bool operator<(const GraphKey& o) const {
-        if (energy_every != o.energy_every) return energy_every < o.energy_every;
-        if (normalize_every != o.normalize_every) return normalize_every < o.normalize_every;
-        if (cycle != o.cycle) return cycle < o.cycle;
-        if (count != o.count) return count < o.count;
-        return narrow < o.narrow;
+        return std::tie(energy_every, normalize_every, action_every, correlator_every, correlator_reps, difference_every, cycle,
+                        count, narrow) <
+               std::tie(o.energy_every, o.normalize_every, o.action_every, o.correlator_every, o.correlator_reps,
+                        o.difference_every, o.cycle, o.count, o.narrow);
     }
 };
 struct GraphVal {
@@ -162,10 +164,20 @@ struct lqft_handle {
     int32_t* staging_d = nullptr;          // [n_slab] lexicographic
     uint64_t* sweep_ctr_d = nullptr;       // device sweep counter for graph replays
     uint32_t* n_meas_d = nullptr;
-    long long* elog_d = nullptr;
+    long long* elog_d = nullptr;           // [n_chains][elog_cap] energies logged by lqft_run
     uint32_t elog_cap = 0;
+    long long* alog_d = nullptr;           // [n_chains][alog_cap] actions
+    uint32_t alog_cap = 0;
+    double* clog_d = nullptr;              // [n_chains][clog_cap][T] correlators
+    uint32_t clog_cap = 0;
+    unsigned int* ticket_d = nullptr;      // arrival counter of the observe launch (kernels_observe.cuh)
+    long long* result_d = nullptr;         // [n_chains][2] E, S of a standalone measurement
+    double* cres_d = nullptr;              // [T] correlator of a standalone measurement
+    uint64_t* run_d = nullptr;             // {sweep_base, first_step} of the running schedule, read by the finalisers
+    ObsFin run_fin{};                      // where the running schedule logs its observables
     uint64_t* sites_d = nullptr;
     long long* gathered_d = nullptr;
+    size_t gathered_cap = 0;
     uint32_t sites_cap = 0;
     std::vector<double*> diff_sum, diff_comp;
     std::vector<uint64_t> diff_count;
@@ -496,6 +508,7 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
     cudaFree(h->chains_d); cudaFree(h->thr_d); cudaFree(h->acc_d); cudaFree(h->obs_d);
     cudaFree(h->mom_d); cudaFree(h->shift_d); cudaFree(h->offset_d); cudaFree(h->staging_d); cudaFree(h->sweep_ctr_d);
     cudaFree(h->n_meas_d); cudaFree(h->elog_d); cudaFree(h->sites_d); cudaFree(h->gathered_d);
+    cudaFree(h->alog_d); cudaFree(h->clog_d); cudaFree(h->ticket_d); cudaFree(h->result_d); cudaFree(h->cres_d); cudaFree(h->run_d);
     for (auto p : h->diff_sum) cudaFree(p);
     for (auto p : h->diff_comp) cudaFree(p);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -598,6 +611,13 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     CU(cudaMemsetAsync(h->obs_d, 0, sizeof(unsigned long long) * (size_t)nc * 2, h->stream));
     CU(cudaMemsetAsync(h->sweep_ctr_d, 0, sizeof(uint64_t), h->stream));
     CU(cudaMemsetAsync(h->n_meas_d, 0, sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->mom_d, 0, sizeof(unsigned long long) * (size_t)nc * T * 2, h->stream));
+    CU(cudaMalloc(&h->ticket_d, sizeof(unsigned int)));
+    CU(cudaMemsetAsync(h->ticket_d, 0, sizeof(unsigned int), h->stream));
+    CU(cudaMalloc(&h->result_d, sizeof(long long) * (size_t)nc * 2));
+    CU(cudaMalloc(&h->cres_d, sizeof(double) * T));
+    CU(cudaMalloc(&h->run_d, sizeof(uint64_t) * 2));
+    CU(cudaMemsetAsync(h->run_d, 0, sizeof(uint64_t) * 2, h->stream));
     h->chains_h.assign(nc, ChainDev{});
     h->beta.assign(nc, 0.0);
     h->configured.assign(nc, 0);
@@ -765,6 +785,9 @@ static lqft_status allreduce_i32(lqft_handle* h, void* buf, size_t n) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
+static lqft_status narrow_exchange_begin(lqft_handle* h);
+static lqft_status narrow_exchange_end(lqft_handle* h);
+
 static inline uint32_t block_for(uint32_t units) {
     uint32_t b = (units + 31u) & ~31u;
     return std::min(256u, std::max(32u, b));
@@ -843,8 +866,6 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
 }
 
 // One full red-black sweep.  `sweep` + (*ctr if ctr) is the RNG sweep counter.
-static lqft_status narrow_exchange_begin(lqft_handle* h);
-static lqft_status narrow_exchange_end(lqft_handle* h);
 
 static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* ctr) {
     const Geom& g = h->g;
@@ -900,47 +921,149 @@ static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* 
     return LQFT_OK;
 }
 
-static lqft_status launch_observe(lqft_handle* h, bool moments) {
+// f64 handles: compensated two-pass reduction, deterministic order
+static lqft_status launch_observe_f64(lqft_handle* h, bool moments) {
     const Geom& g = h->g;
-    if (h->is64) {  // compensated two-pass reduction, deterministic order
-        const uint32_t bd = 256, bx = (g.plane + bd - 1) / bd;
-        dim3 grid(bx, g.Tl, h->cfg.n_chains);
-        k_observe_f64<<<grid, bd, 0, h->stream>>>(g, h->field64[0], h->field64[1], h->part_d);
-        k_observe_fold_f64<<<h->cfg.n_chains, 128, 0, h->stream>>>(g, h->part_d, bx, h->obs64_d, moments ? h->mom64_d : nullptr);
-        CU(cudaGetLastError());
-        h->launches += 2;
-        return LQFT_OK;
+    const uint32_t bd = 256, bx = (g.plane + bd - 1) / bd;
+    dim3 grid(bx, g.Tl, h->cfg.n_chains);
+    k_observe_f64<<<grid, bd, 0, h->stream>>>(g, h->field64[0], h->field64[1], h->part_d);
+    k_observe_fold_f64<<<h->cfg.n_chains, 128, 0, h->stream>>>(g, h->part_d, bx, h->obs64_d, moments ? h->mom64_d : nullptr);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    return LQFT_OK;
+}
+
+// One measurement of chains [chain0, chain0 + n) of an i32 handle (kernels_observe.cuh): energy and action sums,
+// slice moments if asked, logged / folded on the device as `fin` and `due` say.
+struct Measure {
+    uint32_t due = 0;        // kObs* bits the finaliser logs
+    bool moments = false;    // accumulate the slice moments
+    bool fold = false;       // correlator epilogue (consumes the moments)
+    uint64_t sweep = 0;      // RNG counter of the step (relative to *ctr when ctr is given)
+    const uint64_t* ctr = nullptr;
+    uint32_t chain0 = 0, n = 0;
+    ObsFin fin{};
+};
+
+static lqft_status need_gathered(lqft_handle* h, uint32_t reps) {
+    const size_t want = (size_t)reps * h->cfg.n_chains;
+    if (want <= h->gathered_cap) return LQFT_OK;
+    cudaFree(h->gathered_d);
+    h->gathered_d = nullptr;
+    h->gathered_cap = 0;
+    CU(cudaMalloc(&h->gathered_d, sizeof(long long) * want));
+    h->gathered_cap = want;
+    return LQFT_OK;
+}
+
+template <typename H>
+static lqft_status launch_measure_t(lqft_handle* h, const Geom& g, const H* f0, const H* f1, Measure m) {
+    const uint32_t ws = h->cfg.world_size;
+    const bool vec = g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC);
+    m.fin.ticket = h->ticket_d;
+    m.fin.fused = (vec && ws == 1) ? 1u : 0u;
+    if (vec) {
+        // a few blocks per SM, each a run of rows of one plane: at least one quad per thread
+        const uint32_t Qx = g.Xh / 4;
+        const uint32_t per = g.Tl * m.n;
+        uint32_t ny = (8u * (uint32_t)h->sm_count + per - 1) / per;
+        ny = std::min(ny, std::max(1u, g.Y * Qx / 256u));
+        ny = std::max(1u, std::min(ny, g.Y));
+        dim3 grid(ny, g.Tl, m.n);
+        if (m.moments)
+            k_observe_rows<H, true><<<grid, 256, 0, h->stream>>>(g, f0, f1, m.chain0, h->obs_d, h->mom_d, m.fin, m.due, m.sweep, m.ctr,
+                                                                h->chains_d);
+        else
+            k_observe_rows<H, false><<<grid, 256, 0, h->stream>>>(g, f0, f1, m.chain0, h->obs_d, h->mom_d, m.fin, m.due, m.sweep, m.ctr,
+                                                                 h->chains_d);
+    } else if constexpr (std::is_same<H, int32_t>::value) {
+        const uint32_t bd = block_for(g.plane);
+        dim3 grid((g.plane + bd - 1) / bd, g.Tl, m.n);
+        k_observe<<<grid, bd, 0, h->stream>>>(g, f0 + (size_t)m.chain0 * g.chain_stride, f1 + (size_t)m.chain0 * g.chain_stride,
+                                              h->obs_d + (size_t)m.chain0 * 2,
+                                              m.moments ? h->mom_d + (size_t)m.chain0 * g.T * 2 : nullptr);
+    } else {
+        return fail(LQFT_ERR_STATE, "the 16-bit copy has no scalar observe kernel");
     }
+    CU(cudaGetLastError());
+    h->launches += 1;
+    if (m.fin.fused) return LQFT_OK;
+    ST(allreduce_i64(h, h->obs_d + (size_t)m.chain0 * 2, (size_t)m.n * 2));
+    if (m.moments) ST(allreduce_i64(h, h->mom_d + (size_t)m.chain0 * g.T * 2, (size_t)m.n * g.T * 2));
+    k_obs_finalize<<<1, 256, 0, h->stream>>>(m.fin, m.due, m.sweep, m.ctr, m.chain0, m.n, h->obs_d);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    if (m.fold) {
+        const long long* gathered = nullptr;
+        if (ws > 1 && m.fin.reps) {
+            if ((size_t)m.fin.reps * h->cfg.n_chains > h->gathered_cap) return fail(LQFT_ERR_STATE, "correlator scratch not allocated");
+            k_corr_gather<H><<<dim3((m.fin.reps + 127) / 128, m.n), 128, 0, h->stream>>>(g, f0, f1, m.fin, m.sweep, m.ctr, m.chain0,
+                                                                                        h->chains_d, h->gathered_d);
+            CU(cudaGetLastError());
+            h->launches += 1;
+            ST(allreduce_i64(h, h->gathered_d + (size_t)m.chain0 * m.fin.reps, (size_t)m.n * m.fin.reps));
+            gathered = h->gathered_d;
+        }
+        k_corr_fold<H><<<m.n, 128, 0, h->stream>>>(g, f0, f1, m.fin, m.sweep, m.ctr, m.chain0, h->chains_d, gathered, h->mom_d);
+        CU(cudaGetLastError());
+        h->launches += 1;
+    }
+    return LQFT_OK;
+}
+
+static lqft_status launch_measure(lqft_handle* h, const Measure& m) {
     if (h->narrow_active) {
-        if (moments) return fail(LQFT_ERR_STATE, "slice moments are not available on the narrow working copy");
         if (h->gn.ghost) {  // the last owned plane looks one plane up
             if (h->nvalid == 0) ST(narrow_exchange_begin(h));
             ST(narrow_exchange_end(h));
         }
-        const uint32_t units = g.plane / 4;
-        const uint32_t bd = block_for(units);
-        dim3 grid((units + bd - 1) / bd, g.Tl, h->cfg.n_chains);
-        k_observe_vec4<<<grid, bd, 0, h->stream>>>(h->gn, (const uint16_t*)h->narrow[0], (const uint16_t*)h->narrow[1], h->obs_d,
-                                                  (unsigned long long*)nullptr);
+        return launch_measure_t<uint16_t>(h, h->gn, h->narrow[0], h->narrow[1], m);
+    }
+    ST(ghost_op_begin(h));
+    ST(launch_measure_t<int32_t>(h, h->g, h->field[0], h->field[1], m));
+    return ghost_op_end(h);
+}
+
+// DifferencePlotOutputData::update of one chain on whichever copy is live (bond differences need no offset).
+static lqft_status launch_difference(lqft_handle* h, uint32_t chain) {
+    const Geom& g = h->g;
+    const uint32_t bd = block_for(g.plane);
+    dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
+    if (h->narrow_active) {
+        if (h->gn.ghost) {
+            if (h->nvalid == 0) ST(narrow_exchange_begin(h));
+            ST(narrow_exchange_end(h));
+        }
+        k_difference_update_h<uint16_t><<<grid, bd, 0, h->stream>>>(h->gn, h->narrow[0] + (size_t)chain * h->gn.chain_stride,
+                                                                   h->narrow[1] + (size_t)chain * h->gn.chain_stride,
+                                                                   h->diff_sum[chain], h->diff_comp[chain]);
         CU(cudaGetLastError());
         h->launches += 1;
         return LQFT_OK;
     }
     ST(ghost_op_begin(h));
-    if (g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) {
-        const uint32_t units = g.plane / 4;
-        const uint32_t bd = block_for(units);
-        dim3 grid((units + bd - 1) / bd, g.Tl, h->cfg.n_chains);
-        k_observe_vec4<<<grid, bd, 0, h->stream>>>(g, (const int32_t*)h->field[0], (const int32_t*)h->field[1], h->obs_d,
-                                                  moments ? h->mom_d : nullptr);
-    } else {
-        const uint32_t bd = block_for(g.plane);
-        dim3 grid((g.plane + bd - 1) / bd, g.Tl, h->cfg.n_chains);
-        k_observe<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->obs_d, moments ? h->mom_d : nullptr);
-    }
+    if (h->is64)
+        k_difference_update_f64<<<grid, bd, 0, h->stream>>>(g, h->field64[0] + (size_t)chain * g.chain_stride,
+                                                            h->field64[1] + (size_t)chain * g.chain_stride,
+                                                            h->diff_sum[chain], h->diff_comp[chain]);
+    else
+        k_difference_update_h<int32_t><<<grid, bd, 0, h->stream>>>(g, h->field[0] + (size_t)chain * g.chain_stride,
+                                                                  h->field[1] + (size_t)chain * g.chain_stride,
+                                                                  h->diff_sum[chain], h->diff_comp[chain]);
     CU(cudaGetLastError());
     h->launches += 1;
-    ST(ghost_op_end(h));
+    return ghost_op_end(h);
+}
+
+static lqft_status need_difference(lqft_handle* h, uint32_t chain) {
+    if (h->diff_sum[chain]) return LQFT_OK;
+    const size_t bytes = sizeof(double) * 3 * h->n_slab;
+    if (cudaMalloc(&h->diff_sum[chain], bytes) != cudaSuccess || cudaMalloc(&h->diff_comp[chain], bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LQFT_ERR_NOMEM, "cannot allocate %zu bytes for the difference plot", 2 * bytes);
+    }
+    CU(cudaMemsetAsync(h->diff_sum[chain], 0, bytes, h->stream));
+    CU(cudaMemsetAsync(h->diff_comp[chain], 0, bytes, h->stream));
     return LQFT_OK;
 }
 
@@ -1082,16 +1205,16 @@ static lqft_status read_accepted(lqft_handle* h, uint64_t* accepted) {
     return LQFT_OK;
 }
 
-static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_obs, int64_t* e_int, uint64_t* accepted);
+static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_run_outputs* out);
 
 extern "C" lqft_status lqft_sweep(lqft_handle* h, uint64_t first_sweep, uint32_t n_sweeps, uint64_t* accepted) {
     lqft_schedule s{};
     s.sweep_base = first_sweep;
     s.first_step = 0;
     s.n_steps = n_sweeps;
-    s.energy_every = 0;
-    s.normalize_every = 0;
-    return run_impl(h, &s, nullptr, nullptr, accepted);
+    lqft_run_outputs o{};
+    o.accepted = accepted;
+    return run_impl(h, &s, &o);
 }
 
 extern "C" lqft_status lqft_normalize(lqft_handle* h, uint64_t sweep_index) {
@@ -1126,23 +1249,23 @@ extern "C" lqft_status lqft_shift_values(lqft_handle* h, uint32_t chain, double 
 // ---------------------------------------------------------------------------------------------
 // observables
 // ---------------------------------------------------------------------------------------------
-static lqft_status measure(lqft_handle* h, bool moments, std::vector<long long>& obs) {
+// Energy and action sums of every chain: one launch, one copy, one synchronisation.
+static lqft_status measure_sums(lqft_handle* h, std::vector<long long>& obs) {
     const uint32_t nc = h->cfg.n_chains;
-    CU(cudaMemsetAsync(h->obs_d, 0, sizeof(unsigned long long) * (size_t)nc * 2, h->stream));
-    if (moments) CU(cudaMemsetAsync(h->mom_d, 0, sizeof(unsigned long long) * (size_t)nc * h->g.T * 2, h->stream));
-    ST(launch_observe(h, moments));
-    ST(allreduce_i64(h, h->obs_d, (size_t)nc * 2));
-    if (moments) ST(allreduce_i64(h, h->mom_d, (size_t)nc * h->g.T * 2));
+    Measure m;
+    m.n = nc;
+    m.fin.result = h->result_d;
+    ST(launch_measure(h, m));
     obs.resize((size_t)nc * 2);
-    CU(cudaMemcpyAsync(obs.data(), h->obs_d, sizeof(long long) * obs.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(obs.data(), h->result_d, sizeof(long long) * obs.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return check_halo_error(h);
+    return h->g.ghost ? check_halo_error(h) : LQFT_OK;
 }
 
 // f64 handles: energy / action (and moments) as doubles
 static lqft_status measure64(lqft_handle* h, bool moments, std::vector<double>& obs) {
     const uint32_t nc = h->cfg.n_chains;
-    ST(launch_observe(h, moments));
+    ST(launch_observe_f64(h, moments));
     obs.resize((size_t)nc * 2);
     CU(cudaMemcpyAsync(obs.data(), h->obs64_d, sizeof(double) * obs.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1161,7 +1284,7 @@ extern "C" lqft_status lqft_energy(lqft_handle* h, int64_t* e_int, double* e_obs
         return LQFT_OK;
     }
     std::vector<long long> obs;
-    ST(measure(h, false, obs));
+    ST(measure_sums(h, obs));
     for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
         if (e_int) e_int[c] = obs[(size_t)c * 2];
         if (e_obs) e_obs[c] = h->beta[c] * (double)obs[(size_t)c * 2];  // fields.rs:669-671
@@ -1181,7 +1304,7 @@ extern "C" lqft_status lqft_action(lqft_handle* h, int64_t* s_int, double* s_obs
         return LQFT_OK;
     }
     std::vector<long long> obs;
-    ST(measure(h, false, obs));
+    ST(measure_sums(h, obs));
     for (uint32_t c = 0; c < h->cfg.n_chains; ++c) {
         if (s_int) s_int[c] = obs[(size_t)c * 2 + 1];
         if (s_obs) s_obs[c] = h->beta[c] * (double)obs[(size_t)c * 2 + 1];  // fields.rs:665-667
@@ -1189,33 +1312,44 @@ extern "C" lqft_status lqft_action(lqft_handle* h, int64_t* s_int, double* s_obs
     return LQFT_OK;
 }
 
-static lqft_status fetch_moments(lqft_handle* h, uint32_t chain, std::vector<long long>& mom) {
-    std::vector<long long> obs;
-    ST(measure(h, true, obs));
-    const uint32_t T = h->g.T;
-    mom.resize((size_t)T * 2);
-    CU(cudaMemcpyAsync(mom.data(), h->mom_d + (size_t)chain * T * 2, sizeof(long long) * T * 2,
-                       cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return LQFT_OK;
-}
-
 extern "C" lqft_status lqft_slice_moments(lqft_handle* h, uint32_t chain, int64_t* s1, int64_t* s2) {
     ST(ready(h));
     if (h->is64) return fail(LQFT_ERR_INVALID, "integer slice moments are defined for LQFT_I32 fields");
     if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
-    std::vector<long long> mom;
-    ST(fetch_moments(h, chain, mom));
+    const uint32_t T = h->g.T;
+    Measure m;
+    m.moments = true;
+    m.chain0 = chain;
+    m.n = 1;
+    m.fin.result = h->result_d;
+    ST(launch_measure(h, m));
+    std::vector<long long> mom((size_t)T * 2);
     int32_t off = 0;
+    CU(cudaMemcpyAsync(mom.data(), h->mom_d + (size_t)chain * T * 2, sizeof(long long) * T * 2, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemsetAsync(h->mom_d + (size_t)chain * T * 2, 0, sizeof(long long) * T * 2, h->stream));  // moments are zero between uses
     CU(cudaMemcpyAsync(&off, h->offset_d + chain, sizeof off, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->g.ghost) ST(check_halo_error(h));
     // moments of the TRUE heights h = stored - off:  sum h = S1 - A off,  sum h^2 = S2 - 2 off S1 + A off^2
     const long long A = (long long)h->g.X * h->g.Y, o = off;
-    for (uint32_t t = 0; t < h->g.T; ++t) {
+    for (uint32_t t = 0; t < T; ++t) {
         const long long m1 = mom[(size_t)t * 2], m2 = mom[(size_t)t * 2 + 1];
         if (s1) s1[t] = m1 - A * o;
         if (s2) s2[t] = m2 - 2 * o * m1 + A * o * o;
     }
+    return LQFT_OK;
+}
+
+static lqft_status need_sites(lqft_handle* h, uint32_t reps) {
+    if (reps <= h->sites_cap) return LQFT_OK;
+    cudaFree(h->sites_d);
+    cudaFree(h->gathered64_d);
+    h->sites_d = nullptr;
+    h->gathered64_d = nullptr;
+    h->sites_cap = 0;
+    CU(cudaMalloc(&h->sites_d, sizeof(uint64_t) * reps));
+    if (h->is64) CU(cudaMalloc(&h->gathered64_d, sizeof(double) * reps));
+    h->sites_cap = reps;
     return LQFT_OK;
 }
 
@@ -1226,29 +1360,21 @@ extern "C" lqft_status lqft_correlator(lqft_handle* h, uint32_t chain, const uin
     if (!c_of_tau) return fail(LQFT_ERR_INVALID, "null output");
     const Geom& g = h->g;
     const uint32_t T = g.T;
-    std::vector<uint64_t> sites(reps);
-    const ChainDev& cd = h->chains_h[chain];
-    for (uint32_t r = 0; r < reps; ++r) {
-        sites[r] = ref_sites ? ref_sites[r]
-                             : pick_site(cd.k0, cd.k1, LQFT_STREAM_CORRELATOR, sweep_index, r, h->n_global);
-        if (sites[r] >= h->n_global)
-            return fail(LQFT_ERR_INVALID, "reference site %llu outside the lattice", (unsigned long long)sites[r]);
-    }
+    if (ref_sites)
+        for (uint32_t r = 0; r < reps; ++r)
+            if (ref_sites[r] >= h->n_global)
+                return fail(LQFT_ERR_INVALID, "reference site %llu outside the lattice", (unsigned long long)ref_sites[r]);
     if (h->is64) {
+        std::vector<uint64_t> sites(reps);
+        const ChainDev& cd = h->chains_h[chain];
+        for (uint32_t r = 0; r < reps; ++r)
+            sites[r] = ref_sites ? ref_sites[r] : pick_site(cd.k0, cd.k1, LQFT_STREAM_CORRELATOR, sweep_index, r, h->n_global);
         std::vector<double> o;
         ST(measure64(h, true, o));
         std::vector<double> m((size_t)T * 2), hv(reps, 0.0);
         CU(cudaMemcpyAsync(m.data(), h->mom64_d + (size_t)chain * T * 2, sizeof(double) * T * 2, cudaMemcpyDeviceToHost, h->stream));
         if (reps) {
-            if (reps > h->sites_cap) {
-                cudaFree(h->sites_d); cudaFree(h->gathered_d); cudaFree(h->gathered64_d);
-                h->sites_d = nullptr; h->gathered_d = nullptr; h->gathered64_d = nullptr; h->sites_cap = 0;
-                CU(cudaMalloc(&h->sites_d, sizeof(uint64_t) * reps));
-                CU(cudaMalloc(&h->gathered_d, sizeof(long long) * reps));
-                CU(cudaMalloc(&h->gathered64_d, sizeof(double) * reps));
-                h->sites_cap = reps;
-            }
-            if (!h->gathered64_d) CU(cudaMalloc(&h->gathered64_d, sizeof(double) * h->sites_cap));
+            ST(need_sites(h, reps));
             CU(cudaMemcpyAsync(h->sites_d, sites.data(), sizeof(uint64_t) * reps, cudaMemcpyHostToDevice, h->stream));
             k_gather_sites_f64<<<(reps + 127) / 128, 128, 0, h->stream>>>(g, h->field64[0] + (size_t)chain * g.chain_stride,
                                                                          h->field64[1] + (size_t)chain * g.chain_stride,
@@ -1271,69 +1397,32 @@ extern "C" lqft_status lqft_correlator(lqft_handle* h, uint32_t chain, const uin
         for (uint32_t tau = 0; tau < T; ++tau) c_of_tau[tau] = (double)c[tau];
         return LQFT_OK;
     }
-    std::vector<long long> mom;
-    ST(fetch_moments(h, chain, mom));
-    std::vector<long long> hx(reps, 0);
-    if (reps) {
-        if (reps > h->sites_cap) {
-            cudaFree(h->sites_d); cudaFree(h->gathered_d);
-            h->sites_d = nullptr; h->gathered_d = nullptr; h->sites_cap = 0;
-            CU(cudaMalloc(&h->sites_d, sizeof(uint64_t) * reps));
-            CU(cudaMalloc(&h->gathered_d, sizeof(long long) * reps));
-            h->sites_cap = reps;
-        }
-        CU(cudaMemcpyAsync(h->sites_d, sites.data(), sizeof(uint64_t) * reps, cudaMemcpyHostToDevice, h->stream));
-        k_gather_sites<<<(reps + 127) / 128, 128, 0, h->stream>>>(
-            g, h->field[0] + (size_t)chain * g.chain_stride, h->field[1] + (size_t)chain * g.chain_stride,
-            h->sites_d, reps, h->gathered_d);
-        CU(cudaGetLastError());
-        h->launches += 1;
-        ST(allreduce_i64(h, h->gathered_d, reps));
-        CU(cudaMemcpyAsync(hx.data(), h->gathered_d, sizeof(long long) * reps, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+    // i32: moments of this chain only, reference heights and the O(reps * T) epilogue on the device (kernels_observe.cuh)
+    Measure m;
+    m.due = kObsCorr;
+    m.moments = m.fold = true;
+    m.sweep = sweep_index;
+    m.chain0 = chain;
+    m.n = 1;
+    m.fin.clog = h->cres_d;
+    m.fin.reps = reps;
+    if (ref_sites && reps) {
+        ST(need_sites(h, reps));
+        CU(cudaMemcpyAsync(h->sites_d, ref_sites, sizeof(uint64_t) * reps, cudaMemcpyHostToDevice, h->stream));
+        m.fin.sites = h->sites_d;
     }
-    // C[tau] = sum_rep sum_{y in slice t_x+tau} (h_x - h_y)^2 = A h_x^2 - 2 h_x S1 + S2   (exact, int64)
-    const long long A = (long long)g.X * g.Y;
-    std::vector<long long> c(T, 0);
-    for (uint32_t r = 0; r < reps; ++r) {
-        const uint32_t tx = (uint32_t)(sites[r] / ((uint64_t)g.X * g.Y));
-        const long long v = hx[r];
-        for (uint32_t tau = 0; tau < T; ++tau) {
-            const uint32_t t = (tx + tau) % T;
-            c[tau] += A * v * v - 2 * v * mom[(size_t)t * 2] + mom[(size_t)t * 2 + 1];
-        }
-    }
-    for (uint32_t tau = 0; tau < T; ++tau) c_of_tau[tau] = (double)c[tau];
-    return LQFT_OK;
+    if (h->cfg.world_size > 1) ST(need_gathered(h, reps));
+    ST(launch_measure(h, m));
+    CU(cudaMemcpyAsync(c_of_tau, h->cres_d, sizeof(double) * T, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return h->g.ghost ? check_halo_error(h) : LQFT_OK;
 }
 
 extern "C" lqft_status lqft_difference_update(lqft_handle* h, uint32_t chain) {
     ST(ready(h));
     if (chain >= h->cfg.n_chains) return fail(LQFT_ERR_INVALID, "chain %u outside [0,%u)", chain, h->cfg.n_chains);
-    const Geom& g = h->g;
-    const size_t bytes = sizeof(double) * 3 * h->n_slab;
-    if (!h->diff_sum[chain]) {
-        if (cudaMalloc(&h->diff_sum[chain], bytes) != cudaSuccess || cudaMalloc(&h->diff_comp[chain], bytes) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(LQFT_ERR_NOMEM, "cannot allocate %zu bytes for the difference plot", 2 * bytes);
-        }
-        CU(cudaMemsetAsync(h->diff_sum[chain], 0, bytes, h->stream));
-        CU(cudaMemsetAsync(h->diff_comp[chain], 0, bytes, h->stream));
-    }
-    const uint32_t bd = block_for(g.plane);
-    dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
-    ST(ghost_op_begin(h));
-    if (h->is64)
-        k_difference_update_f64<<<grid, bd, 0, h->stream>>>(g, h->field64[0] + (size_t)chain * g.chain_stride,
-                                                            h->field64[1] + (size_t)chain * g.chain_stride,
-                                                            h->diff_sum[chain], h->diff_comp[chain]);
-    else
-    k_difference_update<<<grid, bd, 0, h->stream>>>(g, h->field[0] + (size_t)chain * g.chain_stride,
-                                                    h->field[1] + (size_t)chain * g.chain_stride,
-                                                    h->diff_sum[chain], h->diff_comp[chain]);
-    CU(cudaGetLastError());
-    h->launches += 1;
-    ST(ghost_op_end(h));
+    ST(need_difference(h, chain));
+    ST(launch_difference(h, chain));
     h->diff_count[chain] += 1;
     return LQFT_OK;
 }
@@ -1452,76 +1541,133 @@ static lqft_status narrow_exchange_end(lqft_handle* h) {
 // ---------------------------------------------------------------------------------------------
 // fused schedule (computation.rs:229-270, 313-340)
 // ---------------------------------------------------------------------------------------------
-static lqft_status launch_energy_log(lqft_handle* h) {
-    ST(launch_observe(h, false));
-    if (h->is64) {
-        k_energy_log_f64<<<1, 128, 0, h->stream>>>(h->obs64_d, h->elog64_d, h->elog_cap, h->cfg.n_chains, h->n_meas_d);
-        CU(cudaGetLastError());
-        h->launches += 1;
-        return LQFT_OK;
-    }
-    ST(allreduce_i64(h, h->obs_d, (size_t)h->cfg.n_chains * 2));
-    k_energy_log<<<1, 128, 0, h->stream>>>(h->obs_d, h->elog_d, h->elog_cap, h->cfg.n_chains, h->n_meas_d);
+static lqft_status launch_energy_log_f64(lqft_handle* h) {
+    ST(launch_observe_f64(h, false));
+    k_energy_log_f64<<<1, 128, 0, h->stream>>>(h->obs64_d, h->elog64_d, h->elog_cap, h->cfg.n_chains, h->n_meas_d);
     CU(cudaGetLastError());
     h->launches += 1;
     return LQFT_OK;
 }
 
-// One step of the schedule: sweep, then energy if due, then normalize if due.
+// One step of the schedule: sweep, then every observable that is due (computation.rs:262-265), then normalize if
+// due (computation.rs:267-269).
 static lqft_status launch_step(lqft_handle* h, const lqft_schedule* s, uint64_t step_arg,
                                uint64_t step_for_gating, const uint64_t* ctr) {
     ST(launch_sweep(h, s->sweep_base + step_arg, ctr));
-    if (s->energy_every && step_for_gating % s->energy_every == 0) ST(launch_energy_log(h));
+    uint32_t due = 0;
+    if (s->energy_every && step_for_gating % s->energy_every == 0) due |= kObsEnergy;
+    if (s->action_every && step_for_gating % s->action_every == 0) due |= kObsAction;
+    if (s->correlator_every && step_for_gating % s->correlator_every == 0) due |= kObsCorr;
+    if (h->is64) {
+        if (due & kObsEnergy) ST(launch_energy_log_f64(h));
+    } else if (due) {
+        Measure m;
+        m.due = due;
+        m.moments = m.fold = (due & kObsCorr) != 0;
+        m.sweep = s->sweep_base + step_arg;
+        m.ctr = ctr;
+        m.n = h->cfg.n_chains;
+        m.fin = h->run_fin;
+        ST(launch_measure(h, m));
+    }
+    if (s->difference_every && step_for_gating % s->difference_every == 0)
+        for (uint32_t c = 0; c < h->cfg.n_chains; ++c) ST(launch_difference(h, c));
     if (s->normalize_every && step_for_gating % s->normalize_every == 0)
         ST(launch_normalize(h, s->sweep_base + step_arg, ctr, -1, -1));
     return LQFT_OK;
 }
 
 static uint64_t gcd64(uint64_t a, uint64_t b) { return b ? gcd64(b, a % b) : a; }
+static uint64_t lcm64(uint64_t a, uint64_t b) { return a / gcd64(a, b) * b; }
 
 extern "C" lqft_status lqft_run(lqft_handle* h, const lqft_schedule* s, double* e_obs, int64_t* e_int,
                                 uint64_t* accepted) {
-    return run_impl(h, s, e_obs, e_int, accepted);
+    lqft_run_outputs o{};
+    o.e_obs = e_obs;
+    o.e_int = e_int;
+    o.accepted = accepted;
+    return run_impl(h, s, &o);
 }
 
-static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_obs, int64_t* e_int, uint64_t* accepted) {
+extern "C" lqft_status lqft_run_observables(lqft_handle* h, const lqft_schedule* s, const lqft_run_outputs* out) {
+    lqft_run_outputs none{};
+    return run_impl(h, s, out ? out : &none);
+}
+
+template <typename T>
+static lqft_status grow_log(lqft_handle* h, T*& log, uint32_t& cap, uint64_t n_meas, size_t per_meas, const char* what) {
+    if (n_meas <= cap) return LQFT_OK;
+    cudaFree(log);
+    log = nullptr;
+    cap = 0;
+    if (cudaMalloc(&log, sizeof(T) * (size_t)h->cfg.n_chains * n_meas * per_meas) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LQFT_ERR_NOMEM, "cannot allocate the %s log (%llu measurements)", what, (unsigned long long)n_meas);
+    }
+    cap = (uint32_t)n_meas;
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();  // graphs bake the log pointers and capacities
+    return LQFT_OK;
+}
+
+static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_run_outputs* out) {
     if (!s) return fail(LQFT_ERR_INVALID, "null schedule");
     ST(ready(h));
+    uint64_t* accepted = out->accepted;
     h->count_accepts = accepted != nullptr;
     const uint32_t nc = h->cfg.n_chains;
     const uint64_t n_meas = lqft_run_measurements(s->first_step, s->n_steps, s->energy_every);
-    if (n_meas > 0xffffffffull) return fail(LQFT_ERR_INVALID, "too many measurements in one run");
-    if (n_meas > h->elog_cap) {
-        cudaFree(h->elog_d);
-        h->elog_d = nullptr;
-        h->elog_cap = 0;
-        if (cudaMalloc(&h->elog_d, sizeof(long long) * (size_t)nc * n_meas) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(LQFT_ERR_NOMEM, "cannot allocate the energy log");
-        }
-        if (h->is64) {
-            cudaFree(h->elog64_d);
-            h->elog64_d = nullptr;
-            CU(cudaMalloc(&h->elog64_d, sizeof(double) * (size_t)nc * n_meas));
-        }
-        h->elog_cap = (uint32_t)n_meas;
-        for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
-        h->graphs.clear();  // graphs bake the log pointer and capacity
+    const uint64_t n_act = lqft_run_measurements(s->first_step, s->n_steps, s->action_every);
+    const uint64_t n_corr = lqft_run_measurements(s->first_step, s->n_steps, s->correlator_every);
+    const uint64_t n_diff = lqft_run_measurements(s->first_step, s->n_steps, s->difference_every);
+    if (n_meas > 0xffffffffull || n_act > 0xffffffffull || n_corr > 0xffffffffull)
+        return fail(LQFT_ERR_INVALID, "too many measurements in one run");
+    if (h->is64 && (s->action_every || s->correlator_every || s->difference_every))
+        return fail(LQFT_ERR_INVALID, "LQFT_F64 handles log the energy only inside lqft_run; use lqft_action / lqft_correlator / "
+                                      "lqft_difference_update between calls");
+    if (n_meas > h->elog_cap && h->is64) {
+        cudaFree(h->elog64_d);
+        h->elog64_d = nullptr;
+        CU(cudaMalloc(&h->elog64_d, sizeof(double) * (size_t)nc * n_meas));
+    }
+    ST(grow_log(h, h->elog_d, h->elog_cap, n_meas, 1, "energy"));
+    ST(grow_log(h, h->alog_d, h->alog_cap, n_act, 1, "action"));
+    ST(grow_log(h, h->clog_d, h->clog_cap, n_corr, h->g.T, "correlator"));
+    if (n_corr && h->cfg.world_size > 1) ST(need_gathered(h, s->correlator_reps));
+    if (n_diff)
+        for (uint32_t c = 0; c < nc; ++c) ST(need_difference(h, c));
+    {
+        ObsFin& f = h->run_fin;
+        f = ObsFin{};
+        f.elog = h->elog_d;
+        f.alog = h->alog_d;
+        f.clog = h->clog_d;
+        f.cap_e = h->elog_cap;
+        f.cap_a = h->alog_cap;
+        f.cap_c = h->clog_cap;
+        f.every_e = s->energy_every;
+        f.every_a = s->action_every;
+        f.every_c = s->correlator_every;
+        f.reps = s->correlator_reps;
+        f.run = h->run_d;
+        const uint64_t run[2] = {s->sweep_base, s->first_step};
+        CU(cudaMemcpyAsync(h->run_d, run, sizeof run, cudaMemcpyHostToDevice, h->stream));
     }
     CU(cudaMemsetAsync(h->n_meas_d, 0, sizeof(uint32_t), h->stream));
-    CU(cudaMemsetAsync(h->obs_d, 0, sizeof(unsigned long long) * (size_t)nc * 2, h->stream));
     if (accepted) CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * (size_t)nc * kAccSlots, h->stream));
 
-    const uint64_t ee = s->energy_every ? s->energy_every : 1, ne = s->normalize_every ? s->normalize_every : 1;
-    const uint64_t cycle = ee / gcd64(ee, ne) * ne;
+    uint64_t cycle = 1;
+    for (uint32_t f : {s->energy_every, s->normalize_every, s->action_every, s->correlator_every, s->difference_every})
+        if (f) cycle = std::min<uint64_t>(lcm64(cycle, f), 1u << 20);
     // one captured graph = `reps` cycles (about kGraphSteps sweeps); it is replayed while whole periods remain
     constexpr uint64_t kGraphSteps = 32;
     const bool graph_ok = !(h->cfg.flags & LQFT_FLAG_NO_GRAPH) && cycle <= 64 && s->n_steps >= 2 * cycle && s->n_steps >= 8;
+    const bool extra_obs = s->action_every || s->correlator_every || s->difference_every;
 
     CU(cudaEventRecord(h->ev_start, h->stream));
     uint64_t step = s->first_step;
     const uint64_t end = s->first_step + s->n_steps;
-    if (h->resident_ok && s->n_steps > 0) {
+    if (h->resident_ok && !extra_obs && s->n_steps > 0) {
         // small lattice: the whole schedule in one launch, one CTA per chain, field in shared memory
         ResidentArgs a{h->g, s->sweep_base, s->first_step, s->n_steps, s->energy_every, s->normalize_every,
                        h->elog_cap, h->count_accepts ? 1u : 0u};
@@ -1566,7 +1712,8 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
             const uint64_t period = reps * cycle;
             const uint64_t n_periods = (seg_end - step) / period;
             if (n_periods) {
-                GraphKey key{s->energy_every, s->normalize_every, (uint32_t)period, h->count_accepts, h->narrow_active};
+                GraphKey key{s->energy_every, s->normalize_every, s->action_every, s->correlator_every, s->correlator_reps,
+                             s->difference_every, (uint32_t)period, h->count_accepts, h->narrow_active};
                 auto it = h->graphs.find(key);
                 if (it == h->graphs.end()) {
                     // capture one period; every kernel reads the sweep counter from device memory.  On slabs a
@@ -1626,31 +1773,58 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, double* e_ob
     }
     CU(cudaEventRecord(h->ev_stop, h->stream));
     h->timed = true;
+    for (uint32_t c = 0; c < nc && n_diff; ++c) h->diff_count[c] += n_diff;
 
-    if (n_meas && (e_obs || e_int) && h->is64) {
+    // results: one copy per log at the end of the call
+    bool synced = false;
+    if (n_meas && (out->e_obs || out->e_int) && h->is64) {
         std::vector<double> log((size_t)nc * h->elog_cap);
         CU(cudaMemcpyAsync(log.data(), h->elog64_d, sizeof(double) * log.size(), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
+        synced = true;
         for (uint32_t c = 0; c < nc; ++c)
             for (uint64_t m = 0; m < n_meas; ++m) {
                 const double e = log[(size_t)c * h->elog_cap + m];
-                if (e_int) e_int[(size_t)c * n_meas + m] = (int64_t)e;
-                if (e_obs) e_obs[(size_t)c * n_meas + m] = h->beta[c] * e;
+                if (out->e_int) out->e_int[(size_t)c * n_meas + m] = (int64_t)e;
+                if (out->e_obs) out->e_obs[(size_t)c * n_meas + m] = h->beta[c] * e;
             }
-    } else if (n_meas && (e_obs || e_int)) {
-        std::vector<long long> log((size_t)nc * h->elog_cap);
-        CU(cudaMemcpyAsync(log.data(), h->elog_d, sizeof(long long) * log.size(), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        for (uint32_t c = 0; c < nc; ++c)
+    } else {
+        std::vector<long long> elog, alog;
+        if (n_meas && (out->e_obs || out->e_int)) {
+            elog.resize((size_t)nc * h->elog_cap);
+            CU(cudaMemcpyAsync(elog.data(), h->elog_d, sizeof(long long) * elog.size(), cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (n_act && (out->s_obs || out->s_int)) {
+            alog.resize((size_t)nc * h->alog_cap);
+            CU(cudaMemcpyAsync(alog.data(), h->alog_d, sizeof(long long) * alog.size(), cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (n_corr && out->corr)  // rows of T doubles, chain-major like the other logs
+            for (uint32_t c = 0; c < nc; ++c)
+                CU(cudaMemcpyAsync(out->corr + (size_t)c * n_corr * h->g.T, h->clog_d + (size_t)c * h->clog_cap * h->g.T,
+                                   sizeof(double) * n_corr * h->g.T, cudaMemcpyDeviceToHost, h->stream));
+        if (!elog.empty() || !alog.empty() || (n_corr && out->corr)) {
+            CU(cudaStreamSynchronize(h->stream));
+            synced = true;
+        }
+        for (uint32_t c = 0; c < nc && !elog.empty(); ++c)
             for (uint64_t m = 0; m < n_meas; ++m) {
-                const long long e = log[(size_t)c * h->elog_cap + m];
-                if (e_int) e_int[(size_t)c * n_meas + m] = e;
-                if (e_obs) e_obs[(size_t)c * n_meas + m] = h->beta[c] * (double)e;
+                const long long e = elog[(size_t)c * h->elog_cap + m];
+                if (out->e_int) out->e_int[(size_t)c * n_meas + m] = e;
+                if (out->e_obs) out->e_obs[(size_t)c * n_meas + m] = h->beta[c] * (double)e;  // fields.rs:669-671
+            }
+        for (uint32_t c = 0; c < nc && !alog.empty(); ++c)
+            for (uint64_t m = 0; m < n_act; ++m) {
+                const long long a = alog[(size_t)c * h->alog_cap + m];
+                if (out->s_int) out->s_int[(size_t)c * n_act + m] = a;
+                if (out->s_obs) out->s_obs[(size_t)c * n_act + m] = h->beta[c] * (double)a;  // fields.rs:665-667
             }
     }
-    if (accepted) ST(read_accepted(h, accepted));
+    if (accepted) {
+        ST(read_accepted(h, accepted));
+        synced = true;
+    }
     // slabs: a call that handed results back has synchronised; say so if a neighbour was lost on the way
-    if (h->g.ghost && (accepted || (n_meas && (e_obs || e_int)))) ST(check_halo_error(h));
+    if (h->g.ghost && synced) ST(check_halo_error(h));
     return LQFT_OK;
 }
 

@@ -10,7 +10,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import Config, Schedule, check, lib
+from ._lib import Config, RunOutputs, Schedule, check, lib
 
 
 def device_count() -> int:
@@ -178,7 +178,7 @@ class Engine:
             normalize_every: int = 10, want_accepted: bool = False):
         """Loop body of Simulation::run / WilsonSim::run (computation.rs:229-270, 313-340).
         Returns (e_obs[n_chains, n_meas], e_int[n_chains, n_meas], accepted or None)."""
-        s = Schedule(sweep_base, first_step, n_steps, energy_every, normalize_every)
+        s = Schedule(sweep_base, first_step, n_steps, energy_every, normalize_every, 0, 0, 0, 0)
         n_meas = run_measurements(first_step, n_steps, energy_every)
         e_obs = np.zeros((self.n_chains, n_meas), dtype=np.float64)
         e_int = np.zeros((self.n_chains, n_meas), dtype=np.int64)
@@ -187,6 +187,39 @@ class Engine:
                              e_obs.ctypes.data_as(C.POINTER(C.c_double)) if n_meas else None,
                              e_int.ctypes.data_as(C.POINTER(C.c_int64)) if n_meas else None, acc))
         return e_obs, e_int, ([int(a) for a in acc] if want_accepted else None)
+
+    def run_observables(self, n_steps: int, first_step: int = 0, sweep_base: int = 0, energy_every: int = 0,
+                        action_every: int = 0, correlator_every: int = 0, correlator_reps: int = 0,
+                        difference_every: int = 0, normalize_every: int = 10, want_accepted: bool = False) -> dict:
+        """The whole measurement loop of Simulation::run (computation.rs:247-270) as ONE lqft_run_observables call:
+        every OutputData kind on its own frequency, logged on the device.  Returns a dict with e_obs / e_int
+        [n_chains, n_energy], s_obs / s_int [n_chains, n_action], corr [n_chains, n_corr, T], accepted."""
+        s = Schedule(sweep_base, first_step, n_steps, energy_every, normalize_every, action_every, correlator_every,
+                     correlator_reps, difference_every)
+        n_e = run_measurements(first_step, n_steps, energy_every)
+        n_a = run_measurements(first_step, n_steps, action_every)
+        n_c = run_measurements(first_step, n_steps, correlator_every)
+        res = {
+            "e_obs": np.zeros((self.n_chains, n_e), dtype=np.float64), "e_int": np.zeros((self.n_chains, n_e), dtype=np.int64),
+            "s_obs": np.zeros((self.n_chains, n_a), dtype=np.float64), "s_int": np.zeros((self.n_chains, n_a), dtype=np.int64),
+            "corr": np.zeros((self.n_chains, n_c, self.t), dtype=np.float64), "accepted": None,
+        }
+        acc = (C.c_uint64 * self.n_chains)() if want_accepted else None
+        o = RunOutputs()
+        if n_e:
+            o.e_obs = res["e_obs"].ctypes.data_as(C.POINTER(C.c_double))
+            o.e_int = res["e_int"].ctypes.data_as(C.POINTER(C.c_int64))
+        if n_a:
+            o.s_obs = res["s_obs"].ctypes.data_as(C.POINTER(C.c_double))
+            o.s_int = res["s_int"].ctypes.data_as(C.POINTER(C.c_int64))
+        if n_c:
+            o.corr = res["corr"].ctypes.data_as(C.POINTER(C.c_double))
+        if acc is not None:
+            o.accepted = C.cast(acc, C.POINTER(C.c_uint64))
+        check(lib().lqft_run_observables(self._h, C.byref(s), C.byref(o)))
+        if acc is not None:
+            res["accepted"] = [int(a) for a in acc]
+        return res
 
     # -- misc -------------------------------------------------------------------------------
     def synchronize(self):

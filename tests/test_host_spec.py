@@ -29,7 +29,7 @@ def test_exports_every_declared_symbol():
 
 
 def test_version_and_error_string():
-    assert _lib.lib().lqft_version() == (0 << 16) | 1
+    assert _lib.lib().lqft_version() == (0 << 16) | 2
     assert isinstance(_lib.lib().lqft_last_error(), bytes)
 
 
