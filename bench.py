@@ -124,7 +124,7 @@ def run_reference(args, rank: int, world: int):
     # 256^3 would only add build time), all cores busy, like sim.rs's rayon pool.
     t_sample = CPU_SAMPLE_T
     lat = O.Lattice([X, Y, t_sample])
-    per_step = 4  # sweeps per step and core: amortises thread start-up and the hot start of each call
+    per_step = CPU_SAMPLE_SWEEPS  # sweeps per step and core; the clock covers the sweep loops only (orc_bench_chains)
     for _ in range(args.warmup):
         O.bench_chains(lat, BETA, SEED, per_step, 10, cores)
     t0 = time.time()
@@ -134,13 +134,19 @@ def run_reference(args, rank: int, world: int):
         secs += s
     updates = float(cores) * args.steps * per_step * lat.n_sites
     value = updates / secs
-    sample = (f"{cores} independent chains x {args.steps} steps of {per_step} lexicographic sweeps of {X}x{Y}x{t_sample} "
-              f"(neighbour-table i32 path of algorithm.rs:117-157), wall {time.time() - t0:.1f}s")
+    sample = (f"{cores} independent chains x {args.steps} steps of {per_step} lexicographic sweeps of {X}x{Y}x{t_sample} per core "
+              f"(neighbour-table i32 path of algorithm.rs:117-157; field and tables built outside the clock), "
+              f"wall {time.time() - t0:.1f}s")
+    cfg = workload_config(args.gpus)
+    cfg["workload"] = (f"reference arm: {X}x{Y}x{t_sample} periodic lattice per core, {cores} independent chains (sim.rs:90-93), "
+                       f"i32 heights, beta={BETA}, lexicographic Metropolis, {per_step} sweeps per step; a bounded sample of "
+                       f"the {X}x{Y}x{T_PER_GPU * args.gpus} workload of the b200 arm")
+    cfg["lattice_per_core"] = [X, Y, t_sample]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -189,16 +195,28 @@ def other_configs(device: int):
     out["wilson_scan_16x64^3"] = {"site_updates_per_s": len(shapes) * 64**3 * 100 / sec,
                                   "energy_measurements_per_s": len(shapes) * 100 / sec}
     eng.close()
-    # config 3: 128^3 correlator, 100 reference sites per measurement (reference work: 100 * N site visits each)
+    # config 3: 128^3 correlator, 100 reference sites per measurement (reference work: 100 * N site visits each):
+    # (a) one lqft_correlator call per measurement through the ABI, (b) sim.rs:78's workload — correlator every 10th
+    # sweep — as ONE lqft_run_observables call, (c) the same call measuring after EVERY sweep, whose extra time over a
+    # measurement-free run is the device cost per measurement
     eng = Engine(128, 128, 128, device=device)
     eng.set_chain(0, 0.25, 0xABCD)
     eng.init_hot()
     eng.run(100, energy_every=0)
-    sec = timed(eng, lambda: eng.correlator(0, reps=100, sweep_index=7), 20)
+    sec = timed(eng, lambda: eng.correlator(0, reps=100, sweep_index=7), 50)
     out["correlator_128^3_100_sites"] = {"measurements_per_s": 1.0 / sec,
-                                         "reference_equivalent_site_visits_per_s": 100 * 128**3 / sec}
-    sec = timed(eng, lambda: eng.run(100, sweep_base=100, energy_every=0), 3)
-    out["correlator_128^3_100_sites"]["site_updates_per_s"] = 128**3 * 100 / sec
+                                         "reference_equivalent_site_visits_per_s": 100 * 128**3 / sec,
+                                         "what": "lqft_correlator: one launch (moments + reference heights + O(R*T) epilogue "
+                                                 "on the device), one copy, one synchronisation"}
+    sec0 = timed(eng, lambda: eng.run(200, sweep_base=100, energy_every=0), 3)
+    out["correlator_128^3_100_sites"]["site_updates_per_s"] = 128**3 * 200 / sec0
+    sec10 = timed(eng, lambda: eng.run_observables(200, sweep_base=100, correlator_every=10, correlator_reps=100), 3)
+    sec1 = timed(eng, lambda: eng.run_observables(200, sweep_base=100, correlator_every=1, correlator_reps=100), 3)
+    out["correlator_128^3_100_sites"]["sim_rs_workload"] = {
+        "what": "sim.rs:78: sweep + correlator(100 reps) every 10th sweep + normalize every 10th, one lqft_run_observables call",
+        "site_updates_per_s": 128**3 * 200 / sec10, "measurements_per_s": 20 / sec10,
+        "in_run_measurements_per_s": 200 / max(sec1 - sec0, 1e-9),
+        "in_run_us_per_measurement": 1e6 * (sec1 - sec0) / 200}
     eng.close()
     # config 1: the reference's own run — 16^3, one chain per coupling of INVESTIGATE_ARY9 (lib.rs:50), energy every
     # 10th sweep; small enough to live in shared memory: the whole schedule is one launch (kernels_resident.cuh)
@@ -211,13 +229,147 @@ def other_configs(device: int):
         out[name] = {"site_updates_per_s": n_chains * 4096 * 4000 / sec, "energy_measurements_per_s": n_chains * 400 / sec,
                      "launches_per_call": 1}
         eng.close()
-    # energy / action measurement at the headline size
+    # energy / action measurement at the headline size: through the ABI (launch + copy + synchronise per call) and
+    # inside a run (device cost: a run measuring after every sweep minus a measurement-free run)
     eng = Engine(256, 256, 256, device=device)
     eng.set_chain(0, BETA, SEED)
     eng.init_hot()
-    sec = timed(eng, lambda: eng.energy(), 20)
+    eng.run(50, energy_every=0)
+    sec = timed(eng, lambda: eng.energy(), 50)
     out["energy_256^3"] = {"measurements_per_s": 1.0 / sec, "GB_per_s_of_4B_per_site": 4 * 256**3 / sec / 1e9}
+    sec0 = timed(eng, lambda: eng.run(100, sweep_base=50, energy_every=0), 3)
+    sec1 = timed(eng, lambda: eng.run(100, sweep_base=50, energy_every=1), 3)
+    per = max(sec1 - sec0, 1e-9) / 100
+    out["energy_256^3"]["in_run_measurements_per_s"] = 1.0 / per
+    out["energy_256^3"]["in_run_GB_per_s_of_4B_per_site"] = 4 * 256**3 / per / 1e9
     eng.close()
+    return out
+
+
+def fresh_nccl_id(world: int, rank: int):
+    """A new ncclUniqueId for one more slab-decomposed handle, broadcast from rank 0."""
+    import torch
+    import torch.distributed as dist
+    from lattice_qft_b200 import engine as E
+    if world == 1:
+        return None
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf.copy_(torch.tensor(list(E.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().tolist())
+
+
+def parity_check(world: int, rank: int, device: int):
+    """Before anything is timed: the slab-decomposed path of THIS launch (N ranks, peer-memory deep halo, graphs)
+    against one GPU holding the whole lattice — 256 x 64 x 16N, 7 sweeps with acceptance counts, a 12-step run with
+    energies and normalisation — post-sweep fields, counts and energies bit for bit on rank 0.  N = 1 checks the
+    same kernels with the rank as its own neighbour (LQFT_FLAG_SELF_HALO)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lattice_qft_b200 import Engine, _lib
+    x, y, t = 256, 64, 16 * world
+    beta, seed = 0.25, 0x5EED + world
+    flags = _lib.FLAG_SELF_HALO if world == 1 else 0
+    eng = Engine(x, y, t, device=device, world_size=world, rank=rank, nccl_id=fresh_nccl_id(world, rank), flags=flags)
+    eng.set_chain(0, beta, seed, 100, t // 2)
+    eng.init_hot()
+    acc = eng.sweep(0, 7, want_accepted=True)[0]
+    e_obs, e_int, _ = eng.run(12, sweep_base=7, energy_every=3, normalize_every=10)
+    mine = torch.from_numpy(eng.download(0)).cuda()
+    plan = eng.plan_info()
+    eng.close()
+    acc_t = torch.tensor([acc], dtype=torch.int64, device="cuda")
+    if world > 1:
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        dist.all_reduce(acc_t)
+    else:
+        parts = [mine]
+    ok, detail = True, ""
+    if rank == 0:
+        whole = torch.cat(parts).cpu().numpy()
+        ref = Engine(x, y, t, device=device, flags=_lib.FLAG_NO_NARROW)
+        ref.set_chain(0, beta, seed, 100, t // 2)
+        ref.init_hot()
+        racc = ref.sweep(0, 7, want_accepted=True)[0]
+        re_obs, re_int, _ = ref.run(12, sweep_base=7, energy_every=3, normalize_every=10)
+        want = ref.download(0)
+        ref.close()
+        bad = int((whole != want).sum())
+        ok = bad == 0 and int(acc_t.item()) == racc and bool((e_int == re_int).all()) and bool((e_obs == re_obs).all())
+        if not ok:
+            detail = f"{bad} sites differ, accepted {int(acc_t.item())} vs {racc}, energies {e_int.tolist()} vs {re_int.tolist()}"
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    if world > 1:
+        dist.broadcast(flag, 0)
+    res = {"ranks": world, "ok": bool(flag.item()), "lattice": [x, y, t], "path": plan.get("path"),
+           "ghost_depth": plan.get("ghost_depth"), "p2p": plan.get("p2p"),
+           "what": "N-rank slab run == 1-GPU i32 run of the whole lattice: field, acceptance counts, in-run energies"}
+    if detail:
+        res["detail"] = detail
+    return res
+
+
+def config5_leg(world: int, rank: int, device: int, barrier):
+    """BASELINE.json config 5 as a weak-scaling series: 1024 x 1024 x 128 planes per GPU (N = 8: 1024^3), 100 timed
+    sweeps on the 16-bit kernel after warm-up, energy summed over the ranks.  Beside it, on the same GPUs in the same
+    run, every rank sweeps a periodic 1024 x 1024 x 128 lattice of its own (no halo): the N = 1 rate the slab rate
+    is divided by."""
+    import torch
+    import torch.distributed as dist
+    from lattice_qft_b200 import Engine
+    x = y = 1024
+    tl, sweeps = 128, 100
+
+    def rate(eng, sites_per_rank):
+        stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", device))
+        eng.init_hot()
+        eng.sweep(0, 50)
+        eng.sweep(50, sweeps)  # same call shape as the timed one: graphs instantiated
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        eng.sweep(50 + sweeps, sweeps)
+        b.record(stream)
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        e = float(eng.energy()[1][0])
+        plan = eng.plan_info()
+        segs = eng.narrow_segments()
+        return sites_per_rank * sweeps / (float(ms.item()) * 1e-3), e, plan, segs
+
+    solo = Engine(x, y, tl, device=device)
+    solo.set_chain(0, BETA, SEED + rank)
+    solo_rate, _, _, _ = rate(solo, x * y * tl)
+    solo.close()
+    out = {"lattice": [x, y, tl * world], "planes_per_gpu": tl, "sweeps_timed": sweeps,
+           "single_gpu_periodic_slab_updates_per_s": solo_rate}
+    if world == 1:
+        out["site_updates_per_s"] = solo_rate
+        out["per_gpu_updates_per_s"] = solo_rate
+        out["efficiency_vs_single_gpu_slab"] = 1.0
+        peak, _ = measured_peak_gbs()
+        out["frac_hbm_roofline_8B_per_update"] = solo_rate * 8 / 1e9 / peak
+        out["frac_hbm_roofline_kernel_bytes_4B"] = solo_rate * 4 / 1e9 / peak
+        traffic, src = measured_traffic([x, y, tl], "k_sweep_n16")
+        out["dram_bytes_per_half_sweep_ncu"] = traffic
+        out["dram_bytes_source"] = src
+        out["algorithmic_bytes_per_half_sweep_4B"] = 4 * x * y * tl // 2
+        return out
+    eng = Engine(x, y, tl * world, device=device, world_size=world, rank=rank, nccl_id=fresh_nccl_id(world, rank))
+    eng.set_chain(0, BETA, SEED)
+    per_rank, e, plan, segs = rate(eng, x * y * tl)
+    eng.close()
+    out["site_updates_per_s"] = per_rank * world
+    out["per_gpu_updates_per_s"] = per_rank
+    out["efficiency_vs_single_gpu_slab"] = per_rank / solo_rate
+    out["energy_all_ranks"] = e
+    out["ghost_depth"] = plan.get("ghost_depth")
+    out["narrow_segments"] = segs
     return out
 
 
@@ -245,6 +397,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE.json configs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the slab-vs-single-GPU bit-exactness check (experiments)")
     ap.add_argument("--flags", type=int, default=0, help="LQFT_FLAG_* for experiments")
     ap.add_argument("--sweeps", type=int, default=None, help="sweeps per step override (experiments)")
     ap.add_argument("--lattice", default=None, help="X,Y,Tpergpu override for experiments (not the headline config)")
@@ -285,6 +438,15 @@ def main():
             buf.copy_(torch.tensor(list(E.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
         nccl_id = bytes(buf.cpu().tolist())
+
+    parity = None
+    if not args.lattice and not args.no_parity:
+        parity = parity_check(world, rank, local_rank)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "parity_n": parity, "error": "slab run differs from the "
+                                  "single-GPU run; nothing was timed"}), flush=True)
+            raise SystemExit(3)
 
     t_global = T_PER_GPU * world
     eng = Engine(X, Y, t_global, n_chains=1, device=local_rank, world_size=world, rank=rank, nccl_id=nccl_id,
@@ -363,9 +525,12 @@ def main():
     h2d = n_local * 4
     d2h = n_local * 4 + int(e_obs.size) * 8
 
+    eng.close()
     other = None
-    if world == 1 and not args.lattice and not args.no_configs:
-        other = other_configs(local_rank)
+    if not args.lattice and not args.no_configs:
+        c5 = config5_leg(world, rank, local_rank, barrier)
+        other = other_configs(local_rank) if world == 1 else {}
+        other["config5_1024x1024x128g"] = c5
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         n_sweep_launches = 2 * SWEEPS_PER_STEP * args.steps  # per rank, dominant kernel: half-sweep
@@ -398,6 +563,8 @@ def main():
                          "frac_kernel_bytes": moved / per_launch_s / 1e9 / peak,
                          "avg_launch_us": per_launch_s * 1e6},
         }
+        if parity is not None:
+            line["parity_n"] = parity
         if other:
             line["configs"] = other
         if not args.no_cpu_baseline:
@@ -409,7 +576,6 @@ def main():
                           f"({secs:.1f}s wall, {cores * secs:.0f} core-seconds); C restatement of the reference's "
                           "neighbour-table i32 path (oracle/lqft_oracle.c), hot start, energy every 10th sweep"}
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

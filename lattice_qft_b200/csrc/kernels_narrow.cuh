@@ -41,7 +41,9 @@ constexpr uint32_t kN16Segment = 1000;           // kN16Guard + kN16Segment < kN
 constexpr int kN16KcMax = 255;                   // threshold tables up to 256 entries (beta >= ~0.045)
 
 constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even); fewer for large planes
-constexpr uint32_t kN16ExchangeBlocks = 16;      // per (side, colour, chain)
+constexpr uint32_t kN16ExchangeBlocks = 4;       // per (side, colour, chain); few fat blocks: each one takes a slot from the
+                                                 // half-sweep running beside it (lqft.cu reserves them in its plan)
+constexpr uint32_t kN16ExchangeThreads = 512;
 constexpr uint32_t kN16Overlap = 1;              // half-sweeps whose interior runs underneath an exchange
 
 // Table entry (i << 1) | coin for d = i - kc: coin 1 proposes +1 (m = d), coin 0 proposes -1 (m = -d);
@@ -244,7 +246,7 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
 //   delivered = "your ghost planes hold my boundary planes" (sent by the last block, release chain as in
 //               k_sweep_stream); the same block then waits for both neighbours' deliveries, so the kernel
 //               completes only when this rank's ghost planes are valid.
-// grid = (kN16ExchangeBlocks, 4 = side * 2 + colour, n_chains), block = 256.
+// grid = (kN16ExchangeBlocks, 4 = side * 2 + colour, n_chains), block = kN16ExchangeThreads.
 struct ExchangeArgs {
     uint16_t* mine[2];       // my narrow arrays (colour 0, 1)
     uint16_t* lo[2];         // lower neighbour's narrow arrays, as mapped here
@@ -259,7 +261,7 @@ struct ExchangeArgs {
     unsigned long long* phase;  // device copy of the handle's phase counter: ready = *phase + 1, delivered = *phase + 2
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kN16ExchangeThreads)
 k_n16_exchange(const ExchangeArgs a) {
     // the phase lives in device memory so that a captured graph can be replayed; it is advanced by the last
     // block, after every block has passed the ticket and therefore read it
@@ -280,9 +282,20 @@ k_n16_exchange(const ExchangeArgs a) {
                               (size_t)(side ? a.tl_mine : a.depth) * a.plane;
         uint16_t* dst = side ? a.hi[colour] + (size_t)chain * a.stride_hi
                              : a.lo[colour] + (size_t)chain * a.stride_lo + (size_t)(a.depth + a.tl_lo) * a.plane;
-        // few, long-lived blocks: the kernel shares the GPU with a half-sweep that fills every SM
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-            reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+        // few, long-lived blocks: the kernel shares the GPU with a half-sweep that fills every other slot.  Four local
+        // loads in flight per thread, then four peer stores (fire and forget over NVLink).
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n; i += 4 * stride) {
+            const uint4 v0 = __ldcg(s4 + i), v1 = __ldcg(s4 + i + stride), v2 = __ldcg(s4 + i + 2 * stride), v3 = __ldcg(s4 + i + 3 * stride);
+            d4[i] = v0;
+            d4[i + stride] = v1;
+            d4[i + 2 * stride] = v2;
+            d4[i + 3 * stride] = v3;
+        }
+        for (; i < n; i += stride) d4[i] = __ldcg(s4 + i);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -376,6 +389,7 @@ struct NarrowArgs {
     bool wilson, count;
     cudaStream_t stream;
     bool pdl;
+    uint32_t reserve = 0;  // block slots left to a kernel running beside this launch (the halo exchange)
 };
 
 template <int XQ>
@@ -447,12 +461,19 @@ inline uint32_t narrow_groups(const NarrowPlan& p, uint32_t n_planes) {
 
 // y chunks per plane group: one wave if possible, chunks as short as that allows (cost model of stream_chunks;
 // the per-chunk prologue is worth about two rows here).
+// `reserve`: block slots (in 256-thread units) another kernel occupies beside this launch; *cost_out: the model's cost.
 inline uint32_t narrow_chunks(NarrowPlan& p, const Geom& g, uint32_t n_planes, uint32_t n_chains, bool wilson = false,
-                              bool count = false) {
-    const uint64_t slots = (uint64_t)p.sm_count * narrow_occupancy(p, wilson, count, narrow_warps(p, n_planes));
+                              bool count = false, uint32_t reserve = 0, double* cost_out = nullptr) {
+    const uint32_t warps = narrow_warps(p, n_planes);
+    uint64_t slots = (uint64_t)p.sm_count * narrow_occupancy(p, wilson, count, warps);
+    const uint64_t taken = (uint64_t)reserve * kN16Warps / warps;  // smaller blocks: more of them per displaced slot
+    slots = slots > taken + 1 ? slots - taken : 1;
     const uint64_t base = narrow_groups(p, n_planes) * (uint64_t)(p.segs() ? p.segs() : 1) * n_chains;  // blocks per chunk
     const uint32_t max_chunks = g.Y / 2 ? g.Y / 2 : 1;
-    if (p.forced_chunks) return p.forced_chunks < g.Y ? p.forced_chunks : g.Y;
+    if (p.forced_chunks) {
+        if (cost_out) *cost_out = 0.0;
+        return p.forced_chunks < g.Y ? p.forced_chunks : g.Y;
+    }
     uint32_t best = 1;
     double best_cost = 1e300;
     for (uint32_t nc = 1; nc <= max_chunks; ++nc) {
@@ -465,12 +486,13 @@ inline uint32_t narrow_chunks(NarrowPlan& p, const Geom& g, uint32_t n_planes, u
             best = nc;
         }
     }
+    if (cost_out) *cost_out = best_cost;
     return best;
 }
 
 inline cudaError_t narrow_half(NarrowPlan& p, const NarrowArgs& a) {
     const uint32_t n_groups = narrow_groups(p, a.n_planes);
-    uint32_t n_chunks = narrow_chunks(p, a.g, a.n_planes, a.n_chains, a.wilson, a.count);
+    uint32_t n_chunks = narrow_chunks(p, a.g, a.n_planes, a.n_chains, a.wilson, a.count, a.reserve);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_chunks * (p.segs() ? p.segs() : 1), n_groups, a.n_chains);
     cfg.blockDim = dim3(32 * narrow_warps(p, a.n_planes));

@@ -12,12 +12,15 @@
 // launch (two with the correlator on many chains) and no host round trip.  The slot of a measurement follows from
 // the step number alone (the number of due steps before it), so nothing is counted on the device.
 #pragma once
+#include <type_traits>
+
 #include "kernels_v1.cuh"
 
 namespace lqft {
 
 constexpr uint32_t kObsEnergy = 1u, kObsAction = 2u, kObsCorr = 4u;
 constexpr int kCorrTile = 256;
+constexpr int kCorrSmemT = 1024;
 
 struct ObsFin {
     unsigned int* ticket;   // blocks of the running launch that have flushed their sums (0 between launches)
@@ -81,8 +84,12 @@ __device__ void corr_fold_chain(const Geom& g, const H* __restrict__ c0, const H
                                 uint64_t counter, unsigned long long* __restrict__ mom, double* __restrict__ out) {
     __shared__ long long s_v[kCorrTile];
     __shared__ uint32_t s_t[kCorrTile];
+    __shared__ long long s_mom[2 * kCorrSmemT];  // the chain's moments, when they fit: the epilogue reads each 2 * reps times
     const uint64_t n_sites = (uint64_t)g.X * g.Y * g.T;
     const long long A = (long long)g.X * g.Y;
+    const bool staged = g.T <= (uint32_t)kCorrSmemT;
+    if (staged)
+        for (uint32_t t = threadIdx.x; t < 2 * g.T; t += blockDim.x) s_mom[t] = (long long)__ldcg(mom + t);
     for (uint32_t tau0 = 0; tau0 < g.T; tau0 += blockDim.x) {
         const uint32_t tau = tau0 + threadIdx.x;
         long long acc = 0;
@@ -103,7 +110,9 @@ __device__ void corr_fold_chain(const Geom& g, const H* __restrict__ c0, const H
                     uint32_t t = s_t[j] + tau;
                     if (t >= g.T) t -= g.T;
                     const long long v = s_v[j];
-                    acc += A * v * v - 2 * v * (long long)__ldcg(mom + (size_t)t * 2) + (long long)__ldcg(mom + (size_t)t * 2 + 1);
+                    const long long m1 = staged ? s_mom[2 * t] : (long long)__ldcg(mom + (size_t)t * 2);
+                    const long long m2 = staged ? s_mom[2 * t + 1] : (long long)__ldcg(mom + (size_t)t * 2 + 1);
+                    acc += A * v * v - 2 * v * m1 + m2;
                 }
             }
         }
@@ -139,7 +148,10 @@ k_observe_rows(const Geom g, const H* __restrict__ c0_base, const H* __restrict_
     const H* c1 = c1_base + (size_t)chain * g.chain_stride;
     const size_t ps = (size_t)plane_self(g, tl) * g.plane, pa = (size_t)plane_above(g, tl) * g.plane;
     long long q[4] = {0, 0, 0, 0};
-    auto sq = [](int u, int v) { const long long d = (long long)u - (long long)v; return d * d; };
+    // differences in i32 like the reference (fields.rs:728-737: `value - neighbour` in T), squares and sums in i64
+    // (one IMAD.WIDE with a 64-bit addend per term)
+    using W = long long;
+    auto sq = [](int u, int v) { const int d = u - v; return (long long)d * (long long)d; };
     for (uint32_t i = threadIdx.x; i < (y1 - y0) * Qx; i += blockDim.x) {
         const uint32_t yy = i / Qx, y = y0 + yy, k0 = (i - yy * Qx) << 2;
         const uint32_t p0 = (y + tg) & 1u;  // x parity of the colour-0 sites of this row
@@ -153,17 +165,17 @@ k_observe_rows(const Geom g, const H* __restrict__ c0_base, const H* __restrict_
         const int e = (int)(p0 ? c1 : c0)[row + kn];  // +x neighbour across the quad edge
         const int4 ax = p0 ? make_int4(b.y, b.z, b.w, e) : b;
         const int4 bx = p0 ? a : make_int4(a.y, a.z, a.w, e);
-        const long long dx = sq(a.x, ax.x) + sq(a.y, ax.y) + sq(a.z, ax.z) + sq(a.w, ax.w) +
-                             sq(b.x, bx.x) + sq(b.y, bx.y) + sq(b.z, bx.z) + sq(b.w, bx.w);
-        const long long dy = sq(a.x, ay.x) + sq(a.y, ay.y) + sq(a.z, ay.z) + sq(a.w, ay.w) +
-                             sq(b.x, by.x) + sq(b.y, by.y) + sq(b.z, by.z) + sq(b.w, by.w);
-        const long long dt = sq(a.x, at.x) + sq(a.y, at.y) + sq(a.z, at.z) + sq(a.w, at.w) +
-                             sq(b.x, bt.x) + sq(b.y, bt.y) + sq(b.z, bt.z) + sq(b.w, bt.w);
-        q[0] += dx + dy - dt;
-        q[1] += dx + dy + dt;
+        const W dx = sq(a.x, ax.x) + sq(a.y, ax.y) + sq(a.z, ax.z) + sq(a.w, ax.w) +
+                     sq(b.x, bx.x) + sq(b.y, bx.y) + sq(b.z, bx.z) + sq(b.w, bx.w);
+        const W dy = sq(a.x, ay.x) + sq(a.y, ay.y) + sq(a.z, ay.z) + sq(a.w, ay.w) +
+                     sq(b.x, by.x) + sq(b.y, by.y) + sq(b.z, by.z) + sq(b.w, by.w);
+        const W dt = sq(a.x, at.x) + sq(a.y, at.y) + sq(a.z, at.z) + sq(a.w, at.w) +
+                     sq(b.x, bt.x) + sq(b.y, bt.y) + sq(b.z, bt.z) + sq(b.w, bt.w);
+        q[0] += (long long)(dx + dy - dt);
+        q[1] += (long long)(dx + dy + dt);
         if (MOM) {
-            q[2] += (long long)a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
-            q[3] += sq(a.x, 0) + sq(a.y, 0) + sq(a.z, 0) + sq(a.w, 0) + sq(b.x, 0) + sq(b.y, 0) + sq(b.z, 0) + sq(b.w, 0);
+            q[2] += (long long)((W)a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w);
+            q[3] += (long long)(sq(a.x, 0) + sq(a.y, 0) + sq(a.z, 0) + sq(a.w, 0) + sq(b.x, 0) + sq(b.y, 0) + sq(b.z, 0) + sq(b.w, 0));
         }
     }
     unsigned long long* const dst[4] = {

@@ -171,8 +171,12 @@ struct lqft_handle {
     double* clog_d = nullptr;              // [n_chains][clog_cap][T] correlators
     uint32_t clog_cap = 0;
     unsigned int* ticket_d = nullptr;      // arrival counter of the observe launch (kernels_observe.cuh)
-    long long* result_d = nullptr;         // [n_chains][2] E, S of a standalone measurement
-    double* cres_d = nullptr;              // [T] correlator of a standalone measurement
+    // results of standalone measurements: pinned host memory mapped into the device, written by the finaliser itself
+    // (no copy after the launch, one synchronisation)
+    long long* result_h = nullptr;         // [n_chains][2] E, S
+    long long* result_d = nullptr;         //   its device address
+    double* cres_h = nullptr;              // [T] correlator
+    double* cres_d = nullptr;
     uint64_t* run_d = nullptr;             // {sweep_base, first_step} of the running schedule, read by the finalisers
     ObsFin run_fin{};                      // where the running schedule logs its observables
     uint64_t* sites_d = nullptr;
@@ -508,7 +512,7 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
     cudaFree(h->chains_d); cudaFree(h->thr_d); cudaFree(h->acc_d); cudaFree(h->obs_d);
     cudaFree(h->mom_d); cudaFree(h->shift_d); cudaFree(h->offset_d); cudaFree(h->staging_d); cudaFree(h->sweep_ctr_d);
     cudaFree(h->n_meas_d); cudaFree(h->elog_d); cudaFree(h->sites_d); cudaFree(h->gathered_d);
-    cudaFree(h->alog_d); cudaFree(h->clog_d); cudaFree(h->ticket_d); cudaFree(h->result_d); cudaFree(h->cres_d); cudaFree(h->run_d);
+    cudaFree(h->alog_d); cudaFree(h->clog_d); cudaFree(h->ticket_d); cudaFreeHost(h->result_h); cudaFreeHost(h->cres_h); cudaFree(h->run_d);
     for (auto p : h->diff_sum) cudaFree(p);
     for (auto p : h->diff_comp) cudaFree(p);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -614,8 +618,10 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     CU(cudaMemsetAsync(h->mom_d, 0, sizeof(unsigned long long) * (size_t)nc * T * 2, h->stream));
     CU(cudaMalloc(&h->ticket_d, sizeof(unsigned int)));
     CU(cudaMemsetAsync(h->ticket_d, 0, sizeof(unsigned int), h->stream));
-    CU(cudaMalloc(&h->result_d, sizeof(long long) * (size_t)nc * 2));
-    CU(cudaMalloc(&h->cres_d, sizeof(double) * T));
+    CU(cudaHostAlloc(&h->result_h, sizeof(long long) * (size_t)nc * 2, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer(&h->result_d, h->result_h, 0));
+    CU(cudaHostAlloc(&h->cres_h, sizeof(double) * T, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer(&h->cres_d, h->cres_h, 0));
     CU(cudaMalloc(&h->run_d, sizeof(uint64_t) * 2));
     CU(cudaMemsetAsync(h->run_d, 0, sizeof(uint64_t) * 2, h->stream));
     h->chains_h.assign(nc, ChainDev{});
@@ -796,10 +802,10 @@ static inline uint32_t block_for(uint32_t units) {
 // Narrow copy: one half-sweep of colour `colour` over local planes [first, first + n_first) and, if
 // n_second, [second, second + n_second).
 static lqft_status launch_half_narrow(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr, int32_t first,
-                                      uint32_t n_first, int32_t second, uint32_t n_second) {
+                                      uint32_t n_first, int32_t second, uint32_t n_second, uint32_t reserve = 0) {
     NarrowArgs a{h->gn, colour, sweep, ctr, first, n_first, second, n_first + n_second, h->cfg.n_chains, h->narrow[colour],
                  h->narrow[colour ^ 1], h->chains_d, h->chains_h[0], h->thr_d, h->acc_d, h->max_thr, h->any_wilson, h->count_accepts,
-                 h->stream, !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
+                 h->stream, !(h->cfg.flags & LQFT_FLAG_NO_PDL), reserve};
     CU(narrow_half(h->narrowp, a));
     h->launches += 1;
     return LQFT_OK;
@@ -884,9 +890,27 @@ static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* 
             static const uint32_t overlap = getenv("LQFT_N16_OVERLAP") ? (uint32_t)atoi(getenv("LQFT_N16_OVERLAP")) : kN16Overlap;
             if (h->exchange_inflight && h->wedges.size() < overlap && g.Tl >= 2 * (depth + overlap + 1)) {
                 // underneath the exchange: planes that need neither the ghost planes nor the planes being sent;
-                // k-th deferred half-sweep: interior [depth + k + 1, Tl - depth - k - 1), wedges of 2 * depth planes
-                const uint32_t k = (uint32_t)h->wedges.size(), a = depth + k + 1;
-                ST(launch_half_narrow(h, colour, sweep, ctr, (int32_t)a, g.Tl - 2 * a, 0, 0));
+                // k-th deferred half-sweep: interior [a, Tl - a), a >= depth + k + 1, the rest in two wedges.
+                // The exchange kernel's blocks take slots from this launch (the register file is full with the
+                // sweep's own blocks), so it is planned on the slots that remain, and `a` is the cut for which
+                // interior + wedge launches cost least: a thinner interior may need one block column less.
+                const uint32_t k = (uint32_t)h->wedges.size(), a_min = depth + k + 1;
+                const uint32_t reserve = kN16ExchangeBlocks * 4 * h->cfg.n_chains * (kN16ExchangeThreads / kN16Threads);
+                uint32_t a = a_min;
+                if (k == 0 && !h->narrowp.forced_chunks) {
+                    double best = 1e300;
+                    const uint32_t span = 2 * kN16Warps * h->narrowp.ppw();  // planes of a block column pair
+                    for (uint32_t c = a_min; c <= a_min + span && g.Tl >= 2 * c + 2; ++c) {
+                        double ci = 0.0, cw = 0.0;
+                        narrow_chunks(h->narrowp, h->gn, g.Tl - 2 * c, h->cfg.n_chains, h->any_wilson, h->count_accepts, reserve, &ci);
+                        narrow_chunks(h->narrowp, h->gn, 2 * (extra + c), h->cfg.n_chains, h->any_wilson, h->count_accepts, 0, &cw);
+                        if (ci + cw < best - 1e-9) {
+                            best = ci + cw;
+                            a = c;
+                        }
+                    }
+                }
+                ST(launch_half_narrow(h, colour, sweep, ctr, (int32_t)a, g.Tl - 2 * a, 0, 0, reserve));
                 h->wedges.push_back({colour, sweep, ctr, -(int32_t)extra, (int32_t)(g.Tl - a), extra + a});
                 continue;
             }
@@ -1256,9 +1280,8 @@ static lqft_status measure_sums(lqft_handle* h, std::vector<long long>& obs) {
     m.n = nc;
     m.fin.result = h->result_d;
     ST(launch_measure(h, m));
-    obs.resize((size_t)nc * 2);
-    CU(cudaMemcpyAsync(obs.data(), h->result_d, sizeof(long long) * obs.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    obs.assign(h->result_h, h->result_h + (size_t)nc * 2);
     return h->g.ghost ? check_halo_error(h) : LQFT_OK;
 }
 
@@ -1413,8 +1436,8 @@ extern "C" lqft_status lqft_correlator(lqft_handle* h, uint32_t chain, const uin
     }
     if (h->cfg.world_size > 1) ST(need_gathered(h, reps));
     ST(launch_measure(h, m));
-    CU(cudaMemcpyAsync(c_of_tau, h->cres_d, sizeof(double) * T, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    memcpy(c_of_tau, h->cres_h, sizeof(double) * T);
     return h->g.ghost ? check_halo_error(h) : LQFT_OK;
 }
 
@@ -1518,7 +1541,7 @@ static lqft_status narrow_exchange_begin(lqft_handle* h) {
     dim3 grid(kN16ExchangeBlocks, 4, h->cfg.n_chains);
     CU(cudaEventRecord(h->ev_bnd, h->stream));
     CU(cudaStreamWaitEvent(h->comm_stream, h->ev_bnd, 0));
-    k_n16_exchange<<<grid, 256, 0, h->comm_stream>>>(a);
+    k_n16_exchange<<<grid, kN16ExchangeThreads, 0, h->comm_stream>>>(a);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_comm, h->comm_stream));
     h->launches += 1;
