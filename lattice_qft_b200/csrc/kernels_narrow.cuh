@@ -16,14 +16,18 @@
 //   * the coin bit of the site's Philox word is funnel-shifted into the index, so one LDS.64 fetches
 //     {threshold | coin << 31, +-1} for the proposed direction.
 //
-// Slabs (world_size > 1): the narrow copy carries up to kN16GhostDepth ghost planes per side instead of one.
-// After an exchange (k_n16_exchange: peer stores over NVLink plus two flag phases) all of them are valid; each
-// half-sweep then also updates the ghost planes that still have valid t-neighbours — redundantly, with the same
-// Philox words as their owner, hence identically — and the valid depth shrinks by one.  One exchange per `depth`
-// half-sweeps replaces the per-half-sweep halo of the i32 path, and the sweep kernel itself carries no flags,
-// waits or peer stores at all.  The exchange runs on a second stream underneath the next kN16Overlap
-// half-sweeps, which update only the planes far enough from the boundaries; the wedges they leave out are caught
-// up, in order, once the ghost planes have arrived (lqft.cu: launch_sweep, narrow_exchange_begin / _end).
+// Slabs (world_size > 1): the narrow copy carries `depth` (up to kN16GhostDepth) ghost planes per side instead of
+// one, in TWO sets (Geom::gbuf selects the current one).  While a set is current, each half-sweep also updates the
+// ghost planes that still have valid t-neighbours — redundantly, with the same Philox words as their owner, hence
+// identically — and the valid depth shrinks by one; after `depth` half-sweeps it is used up.  Meanwhile the last two
+// half-sweeps of such a period (one per colour) store their first and last `depth` owned planes a second time:
+// straight into the OTHER ghost set of the two neighbours, over NVLink (PUSH instantiation, peer memory mapped
+// through CUDA IPC).  A period therefore ends with both sets complete and needs no copy kernel, no second stream
+// and no system-scope fence: the first half-sweep of the next period raises this rank's flag at the neighbours in
+// its prologue (its predecessor's completion has flushed the pushed rows), waits for theirs, and reads the other
+// set.  Writing into the set that is NOT current is race free: a neighbour can only be in the same period (it
+// cannot flip ahead without this rank's flag), where it reads and redundantly updates its current set only.
+// k_n16_fill copies the boundary planes for the first period after the copy was (re)built.
 //
 // Validity: a narrow segment starts only if every height is within kN16Guard of the centre and lasts at most
 // kN16Segment sweeps; a sweep moves a site by at most one, so no height can leave [0, 4096) (host logic in
@@ -41,10 +45,7 @@ constexpr uint32_t kN16Segment = 1000;           // kN16Guard + kN16Segment < kN
 constexpr int kN16KcMax = 255;                   // threshold tables up to 256 entries (beta >= ~0.045)
 
 constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even); fewer for large planes
-constexpr uint32_t kN16ExchangeBlocks = 4;       // per (side, colour, chain); few fat blocks: each one takes a slot from the
-                                                 // half-sweep running beside it (lqft.cu reserves them in its plan)
-constexpr uint32_t kN16ExchangeThreads = 512;
-constexpr uint32_t kN16Overlap = 1;              // half-sweeps whose interior runs underneath an exchange
+constexpr uint32_t kN16FillBlocks = 32;          // per (side, colour, chain)
 
 // Table entry (i << 1) | coin for d = i - kc: coin 1 proposes +1 (m = d), coin 0 proposes -1 (m = -d);
 // same contents as build_two_sided (kernels_tiled.cuh), interleaved so that the coin can be shifted in.
@@ -130,13 +131,67 @@ __device__ __forceinline__ uint4 n16_wilson(uint32_t k0, uint32_t p, int sgn, ui
 // 18 % slower.
 // grid = (n_chunks * max(SEGS, 1), 2 * ceil(n_planes / P), n_chains); block = 32 * warps, warps <= kN16Warps chosen by
 // narrow_warps so that small lattices do not carry idle warps.
-template <int XQ, bool WILSON, bool COUNT, bool SINGLE>
+// Slab launches: where the boundary planes go (PUSH) and the flip of the ghost sets in the prologue (sync).
+struct SlabArgs {
+    uint16_t* lo;            // lower neighbour's array of the colour being updated (chain 0), as mapped here
+    uint16_t* hi;            // upper neighbour's
+    uint32_t lo_stride8, hi_stride8;  // their uint4 per chain
+    uint32_t lo_plane, hi_plane;      // storage plane there of my local plane 0 / of my local plane Tl - depth
+    uint32_t depth;          // planes pushed per side
+    uint32_t sync;           // 1: raise my flag at both neighbours and wait for theirs before touching a ghost plane
+    HaloSync* mine;
+    HaloSync* lo_sync;
+    HaloSync* hi_sync;
+    const unsigned long long* seq_base;  // flag value = (seq_base ? *seq_base : 0) + seq_off: the number of this flip
+    unsigned long long seq_off;
+};
+
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void halo_wait_relaxed(const unsigned long long* flag, unsigned long long need, unsigned int* error) {
+    if (ld_relaxed_sys(flag) < need) {
+        const unsigned long long t0 = global_timer_ns();
+        const unsigned long long limit = *reinterpret_cast<volatile unsigned long long*>(&g_halo_timeout_ns);
+        while (ld_relaxed_sys(flag) < need) {
+            __nanosleep(32);
+            if (global_timer_ns() - t0 > limit) {
+                atomicExch(error, 1u);
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+}
+// Flip of the ghost sets, whole block: one thread of the launch tells both neighbours that this rank has finished the
+// period (its pushes were flushed when the previous kernel completed); every block then waits until both neighbours
+// have said the same, i.e. until the other ghost set holds their planes.
+__device__ __forceinline__ void slab_flip(const SlabArgs& sl, bool first_block) {
+    if (threadIdx.x == 0) {
+        const unsigned long long seq = (sl.seq_base ? *sl.seq_base : 0ull) + sl.seq_off;
+        if (first_block) {
+            st_relaxed_sys(&sl.lo_sync->from_hi, seq);
+            st_relaxed_sys(&sl.hi_sync->from_lo, seq);
+        }
+        halo_wait_relaxed(&sl.mine->from_lo, seq, &sl.mine->error);
+        halo_wait_relaxed(&sl.mine->from_hi, seq, &sl.mine->error);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+template <int XQ, bool WILSON, bool COUNT, bool SINGLE, bool SLAB>
 __global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
 k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
             const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
             uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
             const ChainDev* __restrict__ chains, const ChainDev chain0, const uint32_t* __restrict__ thr_all,
-            unsigned long long* __restrict__ acc, const uint32_t max_thr) {
+            unsigned long long* __restrict__ acc, const uint32_t max_thr, const SlabArgs sl) {
     constexpr uint32_t ROWQ = XQ;                        // uint4 per row of one colour
     constexpr uint32_t LPR = XQ < 32 ? XQ : 32;          // lanes of a warp on one row
     constexpr uint32_t PPW = 32u / LPR;                  // planes per warp
@@ -150,6 +205,9 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     const uint32_t c_off = (uint32_t)((kc - 24576) & 0xffff) * 0x10001u, c_max = (uint32_t)(2 * kc) * 0x10001u;
     pdl_wait();
     if (ctr) sweep += *ctr;
+    if (SLAB) {
+        if (sl.sync) slab_flip(sl, blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0);
+    }
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t seg = SEGS > 1 ? blockIdx.x % SEGS : 0u, chunk = SEGS > 1 ? blockIdx.x / SEGS : blockIdx.x;
@@ -172,6 +230,17 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         const uint32_t b_ta = cq + plane_above(g, tl) * planeq + kq, b_tb = cq + plane_below(g, tl) * planeq + kq;
         uint4* const q_own = reinterpret_cast<uint4*>(own_base);
         const uint4* const q_oth = reinterpret_cast<const uint4*>(oth_base);
+        // PUSH: this plane's rows also go to a neighbour's other ghost set (a thin slab may owe both neighbours)
+        uint4* q_lo = nullptr;
+        uint4* q_hi = nullptr;
+        if (SLAB) {
+            if (owned && sl.depth) {
+                if (tl < sl.depth && sl.lo)
+                    q_lo = reinterpret_cast<uint4*>(sl.lo) + (chain * sl.lo_stride8 + (sl.lo_plane + tl) * planeq + kq);
+                if (tl + sl.depth >= g.Tl && sl.hi)
+                    q_hi = reinterpret_cast<uint4*>(sl.hi) + (chain * sl.hi_stride8 + (sl.hi_plane + (tl + sl.depth - g.Tl)) * planeq + kq);
+            }
+        }
         const uint32_t* const w_oth = reinterpret_cast<const uint32_t*>(oth_base);
         // 32-bit word of the other-colour row that holds the x neighbour across the segment edge (SEGS > 1):
         // first word of the column to the right / last word of the column to the left, periodic in the row
@@ -222,6 +291,10 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         }                                                                                                                \
         if (COUNT) accepted += owned ? acc_row : 0;                                                                      \
         if (live) *po = w;                                                                                               \
+        if (SLAB) {                                                                                                      \
+            if (q_lo) q_lo[y * ROWQ] = w;                                                                                \
+            if (q_hi) q_hi[y * ROWQ] = w;                                                                                \
+        }                                                                                                                \
         y = yn;                                                                                                          \
         p ^= 1u;                                                                                                         \
     }
@@ -239,78 +312,36 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
 }
 
-// ---- deep halo exchange -------------------------------------------------------------------------------------
-// My first `depth` owned planes go to the lower neighbour's upper ghost planes, my last `depth` owned planes to
-// the upper neighbour's lower ghost planes; both colours, all chains.  Two flag phases on HaloSync (kernels_tiled.cuh):
-//   ready     = "my kernels that read my ghost planes are done: overwrite them" (sent first thing),
-//   delivered = "your ghost planes hold my boundary planes" (sent by the last block, release chain as in
-//               k_sweep_stream); the same block then waits for both neighbours' deliveries, so the kernel
-//               completes only when this rank's ghost planes are valid.
-// grid = (kN16ExchangeBlocks, 4 = side * 2 + colour, n_chains), block = kN16ExchangeThreads.
-struct ExchangeArgs {
+// ---- first fill of a ghost set ---------------------------------------------------------------------------------
+// My first `depth` owned planes go to the lower neighbour's upper ghost planes, my last `depth` owned planes to the
+// upper neighbour's lower ghost planes — of the set that is NOT current there; both colours, all chains.  No flags:
+// the flip that follows (slab_flip / k_n16_flip, after this kernel has completed) tells the neighbours.
+// grid = (kN16FillBlocks, 4 = side * 2 + colour, n_chains), block = 256.
+struct FillArgs {
     uint16_t* mine[2];       // my narrow arrays (colour 0, 1)
     uint16_t* lo[2];         // lower neighbour's narrow arrays, as mapped here
     uint16_t* hi[2];         // upper neighbour's
     uint64_t stride_mine, stride_lo, stride_hi;  // elements per chain
     uint32_t plane;          // elements per plane per colour
     uint32_t depth;          // planes to send per side == ghost planes per side
-    uint32_t tl_mine, tl_lo; // owned planes here and at the lower neighbour
-    HaloSync* sync_mine;
-    HaloSync* sync_lo;
-    HaloSync* sync_hi;
-    unsigned long long* phase;  // device copy of the handle's phase counter: ready = *phase + 1, delivered = *phase + 2
+    uint32_t tl_mine;        // owned planes here
+    uint32_t lo_plane, hi_plane;  // storage plane at the lower / upper neighbour where the first sent plane goes
 };
 
-__global__ void __launch_bounds__(kN16ExchangeThreads)
-k_n16_exchange(const ExchangeArgs a) {
-    // the phase lives in device memory so that a captured graph can be replayed; it is advanced by the last
-    // block, after every block has passed the ticket and therefore read it
-    const unsigned long long ready = *reinterpret_cast<const volatile unsigned long long*>(a.phase) + 1ull;
-    const unsigned long long delivered = ready + 1ull;
-    const bool first = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-    if (first && threadIdx.x == 0) {
-        st_release_sys(&a.sync_lo->from_hi, ready);
-        st_release_sys(&a.sync_hi->from_lo, ready);
-    }
+__global__ void __launch_bounds__(256)
+k_n16_fill(const FillArgs a) {
     const uint32_t side = blockIdx.y >> 1, colour = blockIdx.y & 1u, chain = blockIdx.z;
-    if (threadIdx.x == 0) halo_wait(side ? &a.sync_mine->from_hi : &a.sync_mine->from_lo, ready, &a.sync_mine->error);
-    __syncthreads();
     const uint64_t n = (uint64_t)a.depth * a.plane / 8;  // uint4 per (side, colour, chain)
-    {
-        // storage planes: [0, depth) lower ghosts, [depth, depth + Tl) owned, then the upper ghosts
-        const uint16_t* src = a.mine[colour] + (size_t)chain * a.stride_mine +
-                              (size_t)(side ? a.tl_mine : a.depth) * a.plane;
-        uint16_t* dst = side ? a.hi[colour] + (size_t)chain * a.stride_hi
-                             : a.lo[colour] + (size_t)chain * a.stride_lo + (size_t)(a.depth + a.tl_lo) * a.plane;
-        // few, long-lived blocks: the kernel shares the GPU with a half-sweep that fills every other slot.  Four local
-        // loads in flight per thread, then four peer stores (fire and forget over NVLink).
-        const uint4* s4 = reinterpret_cast<const uint4*>(src);
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
-        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        for (; i + 3 * stride < n; i += 4 * stride) {
-            const uint4 v0 = __ldcg(s4 + i), v1 = __ldcg(s4 + i + stride), v2 = __ldcg(s4 + i + 2 * stride), v3 = __ldcg(s4 + i + 3 * stride);
-            d4[i] = v0;
-            d4[i + stride] = v1;
-            d4[i + 2 * stride] = v2;
-            d4[i + 3 * stride] = v3;
-        }
-        for (; i < n; i += stride) d4[i] = __ldcg(s4 + i);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-        const unsigned int done = atom_add_acq_rel_gpu(&a.sync_mine->ticket, 1u);
-        if (done + 1u == total) {
-            st_relaxed_gpu(&a.sync_mine->ticket, 0u);
-            *a.phase = delivered;
-            st_release_sys(&a.sync_lo->from_hi, delivered);
-            st_release_sys(&a.sync_hi->from_lo, delivered);
-            halo_wait(&a.sync_mine->from_lo, delivered, &a.sync_mine->error);
-            halo_wait(&a.sync_mine->from_hi, delivered, &a.sync_mine->error);
-        }
-    }
+    // storage planes here: [0, depth) lower ghosts, [depth, depth + Tl) owned
+    const uint16_t* src = a.mine[colour] + (size_t)chain * a.stride_mine + (size_t)(side ? a.tl_mine : a.depth) * a.plane;
+    uint16_t* dst = side ? a.hi[colour] + (size_t)chain * a.stride_hi + (size_t)a.hi_plane * a.plane
+                         : a.lo[colour] + (size_t)chain * a.stride_lo + (size_t)a.lo_plane * a.plane;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4*>(dst)[i] = __ldcg(reinterpret_cast<const uint4*>(src) + i);
 }
+
+// The flip on its own (one thread), for operations other than a half-sweep that need the next ghost set.
+__global__ void k_n16_flip(const SlabArgs sl) { slab_flip(sl, true); }
 
 // ---- i32 <-> narrow ---------------------------------------------------------------------------------------
 // Owned planes of one colour, 4 heights per thread.  grid = (ceil(n/4/256), n_chains); n = Tl * plane elements per
@@ -364,7 +395,7 @@ struct NarrowPlan {
     int xq = 0;            // X / 16: uint4 per row of one colour (1 ... 64)
     int sm_count = 0;
     uint32_t forced_chunks = 0;  // LQFT_N16_CHUNKS (tests): y chunks per plane group instead of the cost model's choice
-    int occ[2][2][kN16Warps + 1];  // resident blocks per SM by (WILSON, COUNT, warps per block); 0 = not asked yet
+    int occ[2][2][2][kN16Warps + 1];  // resident blocks per SM by (WILSON, COUNT, SLAB, warps per block); 0 = not asked yet
     int segs() const { return xq / 32; }                       // 512-site row segments
     uint32_t ppw() const { return xq < 32 ? 32u / xq : 1u; }   // planes per warp
 };
@@ -389,27 +420,34 @@ struct NarrowArgs {
     bool wilson, count;
     cudaStream_t stream;
     bool pdl;
-    uint32_t reserve = 0;  // block slots left to a kernel running beside this launch (the halo exchange)
+    bool slab = false;     // SLAB instantiation: push boundary planes and / or flip the ghost sets (sl)
+    SlabArgs sl{};
 };
 
+// SLAB instantiations read the chain parameters from memory (SINGLE = false): they are 2 of the `depth` launches of
+// a period, not worth another 28 kernels.
 template <int XQ>
-inline const void* n16_variant(bool w, bool c, bool s) {
-    if (w) {
-        if (c) return s ? (const void*)k_sweep_n16<XQ, true, true, true> : (const void*)k_sweep_n16<XQ, true, true, false>;
-        return s ? (const void*)k_sweep_n16<XQ, true, false, true> : (const void*)k_sweep_n16<XQ, true, false, false>;
+inline const void* n16_variant(bool w, bool c, bool s, bool slab) {
+    if (slab) {
+        if (w) return c ? (const void*)k_sweep_n16<XQ, true, true, false, true> : (const void*)k_sweep_n16<XQ, true, false, false, true>;
+        return c ? (const void*)k_sweep_n16<XQ, false, true, false, true> : (const void*)k_sweep_n16<XQ, false, false, false, true>;
     }
-    if (c) return s ? (const void*)k_sweep_n16<XQ, false, true, true> : (const void*)k_sweep_n16<XQ, false, true, false>;
-    return s ? (const void*)k_sweep_n16<XQ, false, false, true> : (const void*)k_sweep_n16<XQ, false, false, false>;
+    if (w) {
+        if (c) return s ? (const void*)k_sweep_n16<XQ, true, true, true, false> : (const void*)k_sweep_n16<XQ, true, true, false, false>;
+        return s ? (const void*)k_sweep_n16<XQ, true, false, true, false> : (const void*)k_sweep_n16<XQ, true, false, false, false>;
+    }
+    if (c) return s ? (const void*)k_sweep_n16<XQ, false, true, true, false> : (const void*)k_sweep_n16<XQ, false, true, false, false>;
+    return s ? (const void*)k_sweep_n16<XQ, false, false, true, false> : (const void*)k_sweep_n16<XQ, false, false, false, false>;
 }
-inline const void* n16_kernel(int xq, bool w, bool c, bool s) {
+inline const void* n16_kernel(int xq, bool w, bool c, bool s, bool slab) {
     switch (xq) {
-        case 1: return n16_variant<1>(w, c, s);
-        case 2: return n16_variant<2>(w, c, s);
-        case 4: return n16_variant<4>(w, c, s);
-        case 8: return n16_variant<8>(w, c, s);
-        case 16: return n16_variant<16>(w, c, s);
-        case 32: return n16_variant<32>(w, c, s);
-        case 64: return n16_variant<64>(w, c, s);
+        case 1: return n16_variant<1>(w, c, s, slab);
+        case 2: return n16_variant<2>(w, c, s, slab);
+        case 4: return n16_variant<4>(w, c, s, slab);
+        case 8: return n16_variant<8>(w, c, s, slab);
+        case 16: return n16_variant<16>(w, c, s, slab);
+        case 32: return n16_variant<32>(w, c, s, slab);
+        case 64: return n16_variant<64>(w, c, s, slab);
     }
     return nullptr;
 }
@@ -417,7 +455,7 @@ inline const void* n16_kernel(int xq, bool w, bool c, bool s) {
 inline bool narrow_geometry_ok(const Geom& g, uint32_t max_thr, uint32_t n_chains) {
     return g.X >= 16 && g.X <= 1024 && (g.X & (g.X - 1)) == 0 && g.Tl >= 2 && g.Tl % 2 == 0 &&
            max_thr <= (uint32_t)kN16KcMax + 1 &&
-           (uint64_t)g.plane / 8 * (g.Tl + 2 * kN16GhostDepth) * n_chains < (1ull << 30) &&  // uint4 and word offsets in 32 bits
+           (uint64_t)g.plane / 8 * (g.Tl + 4 * kN16GhostDepth) * n_chains < (1ull << 30) &&  // uint4 and word offsets in 32 bits
            (uint64_t)g.T * g.Y * (g.X / 8) < (1ull << 32);
 }
 
@@ -440,11 +478,11 @@ inline uint32_t narrow_warps(const NarrowPlan& p, uint32_t n_planes) {
 }
 
 // Resident blocks per SM of the instantiation a launch will use (each has its own register count).
-inline int narrow_occupancy(NarrowPlan& p, bool wilson, bool count, uint32_t warps) {
-    int& o = p.occ[wilson][count][warps];
+inline int narrow_occupancy(NarrowPlan& p, bool wilson, bool count, bool slab, uint32_t warps) {
+    int& o = p.occ[wilson][count][slab][warps];
     if (o == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, n16_kernel(p.xq, wilson, count, true), (int)(32 * warps), 0) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, n16_kernel(p.xq, wilson, count, !slab, slab), (int)(32 * warps), 0) != cudaSuccess) {
             cudaGetLastError();
             n = 1;
         }
@@ -461,19 +499,12 @@ inline uint32_t narrow_groups(const NarrowPlan& p, uint32_t n_planes) {
 
 // y chunks per plane group: one wave if possible, chunks as short as that allows (cost model of stream_chunks;
 // the per-chunk prologue is worth about two rows here).
-// `reserve`: block slots (in 256-thread units) another kernel occupies beside this launch; *cost_out: the model's cost.
 inline uint32_t narrow_chunks(NarrowPlan& p, const Geom& g, uint32_t n_planes, uint32_t n_chains, bool wilson = false,
-                              bool count = false, uint32_t reserve = 0, double* cost_out = nullptr) {
-    const uint32_t warps = narrow_warps(p, n_planes);
-    uint64_t slots = (uint64_t)p.sm_count * narrow_occupancy(p, wilson, count, warps);
-    const uint64_t taken = (uint64_t)reserve * kN16Warps / warps;  // smaller blocks: more of them per displaced slot
-    slots = slots > taken + 1 ? slots - taken : 1;
+                              bool count = false, bool slab = false) {
+    const uint64_t slots = (uint64_t)p.sm_count * narrow_occupancy(p, wilson, count, slab, narrow_warps(p, n_planes));
     const uint64_t base = narrow_groups(p, n_planes) * (uint64_t)(p.segs() ? p.segs() : 1) * n_chains;  // blocks per chunk
     const uint32_t max_chunks = g.Y / 2 ? g.Y / 2 : 1;
-    if (p.forced_chunks) {
-        if (cost_out) *cost_out = 0.0;
-        return p.forced_chunks < g.Y ? p.forced_chunks : g.Y;
-    }
+    if (p.forced_chunks) return p.forced_chunks < g.Y ? p.forced_chunks : g.Y;
     uint32_t best = 1;
     double best_cost = 1e300;
     for (uint32_t nc = 1; nc <= max_chunks; ++nc) {
@@ -486,13 +517,12 @@ inline uint32_t narrow_chunks(NarrowPlan& p, const Geom& g, uint32_t n_planes, u
             best = nc;
         }
     }
-    if (cost_out) *cost_out = best_cost;
     return best;
 }
 
 inline cudaError_t narrow_half(NarrowPlan& p, const NarrowArgs& a) {
     const uint32_t n_groups = narrow_groups(p, a.n_planes);
-    uint32_t n_chunks = narrow_chunks(p, a.g, a.n_planes, a.n_chains, a.wilson, a.count, a.reserve);
+    uint32_t n_chunks = narrow_chunks(p, a.g, a.n_planes, a.n_chains, a.wilson, a.count, a.slab);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_chunks * (p.segs() ? p.segs() : 1), n_groups, a.n_chains);
     cfg.blockDim = dim3(32 * narrow_warps(p, a.n_planes));
@@ -516,9 +546,10 @@ inline cudaError_t narrow_half(NarrowPlan& p, const NarrowArgs& a) {
     ChainDev chain0 = a.chain0;
     const uint32_t* thr = a.thr;
     unsigned long long* acc = a.acc;
+    SlabArgs sl = a.sl;
     void* args[] = {&g, &colour, &sweep, &ctr, &tl_first, &n_first, &tl_second, &n_planes, &n_chunks, &own, &oth, &chains,
-                    &chain0, &thr, &acc, &max_thr};
-    return cudaLaunchKernelExC(&cfg, n16_kernel(p.xq, a.wilson, a.count, a.n_chains == 1), args);
+                    &chain0, &thr, &acc, &max_thr, &sl};
+    return cudaLaunchKernelExC(&cfg, n16_kernel(p.xq, a.wilson, a.count, a.n_chains == 1, a.slab), args);
 }
 
 }  // namespace lqft

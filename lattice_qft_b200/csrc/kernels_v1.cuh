@@ -20,7 +20,9 @@ struct Geom {
     uint32_t Tl, t0;        // owned planes, first owned global plane
     uint32_t ghost;         // ghost planes per side (0: periodic wrap by index; slabs: 1, or the deep halo of the narrow copy)
     uint32_t plane;         // Xh*Y elements per plane per colour
-    uint64_t chain_stride;  // plane * (Tl + 2*ghost) elements per chain per colour
+    uint32_t gbuf;          // 16-bit copy on slabs: which of its two sets of ghost planes is current (kernels_narrow.cuh)
+    uint32_t pad_;
+    uint64_t chain_stride;  // elements per chain per colour: plane * (Tl + 2*ghost); the 16-bit copy on slabs: Tl + 4*ghost
 };
 
 struct ChainDev {
@@ -33,13 +35,20 @@ struct ChainDev {
 constexpr uint32_t kThrStride = 2048;  // == LQFT_MAX_THRESHOLDS
 constexpr int kAccSlots = 64;          // spread of the acceptance counters per chain
 
+// Storage plane of local plane tl.  Negative numbers (wrapped) are the lower ghost planes, numbers >= Tl the upper
+// ones.  Layout per chain: [lower ghosts][owned][upper ghosts], and for the 16-bit copy on slabs a second set of
+// ghost planes behind it, [lower 1][upper 1]; gbuf says which set is current (the other one is being filled by the
+// neighbours, kernels_narrow.cuh).
+__device__ __forceinline__ uint32_t plane_self(const Geom& g, uint32_t tl) {
+    if (g.gbuf && tl >= g.Tl) return ((int32_t)tl < 0 ? g.Tl : 0u) + 3u * g.ghost + tl;
+    return tl + g.ghost;
+}
 __device__ __forceinline__ uint32_t plane_below(const Geom& g, uint32_t tl) {
-    return g.ghost ? tl + g.ghost - 1 : (tl == 0 ? g.Tl - 1 : tl - 1);  // storage plane index of t-1
+    return g.ghost ? plane_self(g, tl - 1u) : (tl == 0 ? g.Tl - 1 : tl - 1);  // storage plane index of t-1
 }
 __device__ __forceinline__ uint32_t plane_above(const Geom& g, uint32_t tl) {
-    return g.ghost ? tl + g.ghost + 1 : (tl + 1 == g.Tl ? 0 : tl + 1);  // storage plane index of t+1
+    return g.ghost ? plane_self(g, tl + 1u) : (tl + 1 == g.Tl ? 0 : tl + 1);  // storage plane index of t+1
 }
-__device__ __forceinline__ uint32_t plane_self(const Geom& g, uint32_t tl) { return tl + g.ghost; }
 
 // The Metropolis decision of metropolis_single (algorithm.rs:137-157) in integers:
 // proposal v -> v + s, s = +-1 from the coin; new - old = 6 + 2 s (6v - sum_n + off);
@@ -439,7 +448,10 @@ __global__ void k_energy_log(unsigned long long* __restrict__ obs, long long* __
 }
 
 // Advance the device-resident sweep counter at the end of a captured cycle.
-__global__ void k_tick(uint64_t* ctr, uint64_t by) { *ctr += by; }
+__global__ void k_tick(uint64_t* ctr, uint64_t by, unsigned long long* phase = nullptr, unsigned long long phases = 0) {
+    *ctr += by;
+    if (phase) *phase += phases;
+}
 
 // Heights of a list of global sites (0 where another rank owns the site).
 __global__ void k_gather_sites(Geom g, const int32_t* __restrict__ c0, const int32_t* __restrict__ c1,

@@ -115,11 +115,12 @@ static lqft_status nccl_load() {
 struct GraphKey {
     uint32_t energy_every, normalize_every, action_every, correlator_every, correlator_reps, difference_every, cycle;
     bool count, narrow;
+    uint32_t gbuf;  // slabs: the ghost set that is current when a replay begins (kernel arguments bake it)
     bool operator<(const GraphKey& o) const {
         return std::tie(energy_every, normalize_every, action_every, correlator_every, correlator_reps, difference_every, cycle,
-                        count, narrow) <
+                        count, narrow, gbuf) <
                std::tie(o.energy_every, o.normalize_every, o.action_every, o.correlator_every, o.correlator_reps,
-                        o.difference_every, o.cycle, o.count, o.narrow);
+                        o.difference_every, o.cycle, o.count, o.narrow, o.gbuf);
     }
 };
 struct GraphVal {
@@ -210,10 +211,10 @@ struct lqft_handle {
     NarrowPlan narrowp{};
     Geom gn{};                                  // geometry of the narrow arrays: slabs carry a deep halo (ghost > 1)
     uint32_t nvalid = 0;                        // ghost planes per side of the narrow copy that are valid right now
-    struct Wedge { int colour; uint64_t sweep; const uint64_t* ctr; int32_t lo_first, hi_first; uint32_t n_each; };
-    unsigned long long* phase_d = nullptr;      // device copy of `phase` while a narrow segment runs on a slab
-    std::vector<Wedge> wedges;                  // boundary parts of half-sweeps issued underneath an exchange
-    bool exchange_inflight = false;
+    unsigned long long* phase_d = nullptr;      // device copy of `phase` at the start of a graph replay (slabs, narrow copy)
+    bool next_ready = false;                    // the OTHER ghost set of the narrow copy holds this rank's pushed planes
+    bool capturing = false;                     // launches are being captured: flip numbers are relative to *phase_d
+    unsigned long long phase_capture0 = 0;      // `phase` when the capture began
     uint32_t tl_lo = 0, tl_hi = 0;              // owned planes of the lower / upper neighbour
     bool narrow_active = false;
     uint64_t narrow_segments = 0;
@@ -651,8 +652,8 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
             if (r == (cfg->rank + ws - 1) % ws) h->tl_lo = rnt;
             if (r == (cfg->rank + 1) % ws) h->tl_hi = rnt;
         }
-        h->gn.ghost = std::max(1u, depth & ~1u);
-        h->gn.chain_stride = (uint64_t)g.plane * (g.Tl + 2 * h->gn.ghost);
+        h->gn.ghost = std::max(2u, depth & ~1u);  // even: a period of `depth` half-sweeps starts with colour 0
+        h->gn.chain_stride = (uint64_t)g.plane * (g.Tl + 4 * h->gn.ghost);  // two sets of ghost planes (kernels_narrow.cuh)
     }
     if (!h->is64 && !(cfg->flags & no_narrow) && narrow_geometry_ok(g, 2, nc)) {
         // 16-bit working copy (+50 % field memory); without it the i32 kernels do all the work
@@ -791,21 +792,54 @@ static lqft_status allreduce_i32(lqft_handle* h, void* buf, size_t n) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
-static lqft_status narrow_exchange_begin(lqft_handle* h);
-static lqft_status narrow_exchange_end(lqft_handle* h);
+static lqft_status narrow_need_ghost(lqft_handle* h);
 
 static inline uint32_t block_for(uint32_t units) {
     uint32_t b = (units + 31u) & ~31u;
     return std::min(256u, std::max(32u, b));
 }
 
-// Narrow copy: one half-sweep of colour `colour` over local planes [first, first + n_first) and, if
-// n_second, [second, second + n_second).
+// Storage plane, in a neighbour's narrow array, of the first plane this rank sends into ghost set `set` there:
+// the lower neighbour's upper ghosts / the upper neighbour's lower ghosts (layout: kernels_v1.cuh, plane_self).
+static uint32_t peer_ghost_plane(const lqft_handle* h, int side, uint32_t set) {
+    const uint32_t d = h->gn.ghost;
+    if (side == 0) return set ? h->tl_lo + 3 * d : d + h->tl_lo;
+    return set ? h->tl_hi + 2 * d : 0u;
+}
+
+// Flag words and number of the flip that makes the other ghost set current (eager: the host's count; inside a
+// captured period: relative to the device copy the replay starts from).
+static void flip_args(lqft_handle* h, SlabArgs& sl) {
+    sl.sync = 1;
+    sl.mine = h->halo_d;
+    sl.lo_sync = (HaloSync*)h->peer_base[0][2];
+    sl.hi_sync = (HaloSync*)h->peer_base[1][2];
+    sl.seq_base = h->capturing ? h->phase_d : nullptr;
+    sl.seq_off = h->capturing ? h->phase - h->phase_capture0 : h->phase;
+}
+
+// Narrow copy: one half-sweep of colour `colour` over local planes [first, first + n_planes).  Slabs: `flip` opens a
+// period (the kernel's prologue swaps the ghost sets with the neighbours), `push` sends the boundary planes of this
+// colour into the neighbours' other set.
 static lqft_status launch_half_narrow(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr, int32_t first,
-                                      uint32_t n_first, int32_t second, uint32_t n_second, uint32_t reserve = 0) {
-    NarrowArgs a{h->gn, colour, sweep, ctr, first, n_first, second, n_first + n_second, h->cfg.n_chains, h->narrow[colour],
+                                      uint32_t n_planes, bool flip = false, bool push = false) {
+    NarrowArgs a{h->gn, colour, sweep, ctr, first, n_planes, 0, n_planes, h->cfg.n_chains, h->narrow[colour],
                  h->narrow[colour ^ 1], h->chains_d, h->chains_h[0], h->thr_d, h->acc_d, h->max_thr, h->any_wilson, h->count_accepts,
-                 h->stream, !(h->cfg.flags & LQFT_FLAG_NO_PDL), reserve};
+                 h->stream, !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
+    if (flip || push) {
+        a.slab = true;
+        if (flip) flip_args(h, a.sl);
+        if (push) {
+            const uint32_t d = h->gn.ghost, next = h->gn.gbuf ^ 1u;
+            a.sl.depth = d;
+            a.sl.lo = (uint16_t*)h->peer_base[0][3 + colour];
+            a.sl.hi = (uint16_t*)h->peer_base[1][3 + colour];
+            a.sl.lo_stride8 = (uint32_t)((uint64_t)h->gn.plane * (h->tl_lo + 4 * d) / 8);
+            a.sl.hi_stride8 = (uint32_t)((uint64_t)h->gn.plane * (h->tl_hi + 4 * d) / 8);
+            a.sl.lo_plane = peer_ghost_plane(h, 0, next);
+            a.sl.hi_plane = peer_ghost_plane(h, 1, next);
+        }
+    }
     CU(narrow_half(h->narrowp, a));
     h->launches += 1;
     return LQFT_OK;
@@ -873,49 +907,34 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
 
 // One full red-black sweep.  `sweep` + (*ctr if ctr) is the RNG sweep counter.
 
+static lqft_status narrow_fill(lqft_handle* h);
+
 static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* ctr) {
     const Geom& g = h->g;
     if (h->narrow_active) {
-        // narrow copy: on slabs every half-sweep also updates the ghost planes that still have valid neighbours,
-        // and the valid depth shrinks by one; an exchange restores it (kernels_narrow.cuh)
+        // narrow copy.  Slabs: a period of `depth` half-sweeps per ghost set; each half-sweep also updates the ghost
+        // planes that still have valid neighbours and the valid depth shrinks by one; the last two push this rank's
+        // boundary planes into the neighbours' other set, which the next period flips to (kernels_narrow.cuh)
         const uint32_t depth = h->gn.ghost;
         for (int colour = 0; colour < 2; ++colour) {
             if (depth == 0) {
-                ST(launch_half_narrow(h, colour, sweep, ctr, 0, g.Tl, 0, 0));
+                ST(launch_half_narrow(h, colour, sweep, ctr, 0, g.Tl));
                 continue;
             }
-            if (h->nvalid == 0) ST(narrow_exchange_begin(h));
+            bool flip = false;
+            if (h->nvalid == 0) {
+                if (!h->next_ready) ST(narrow_fill(h));
+                flip = true;
+                h->phase += 1;
+                h->gn.gbuf ^= 1u;
+                h->nvalid = depth;
+                h->next_ready = false;
+            }
             const uint32_t extra = h->nvalid - 1;  // ghost planes per side this half-sweep may still update
+            const bool push = h->nvalid <= 2;       // nvalid 2: colour 0 for the last time in this period, 1: colour 1
             h->nvalid -= 1;
-            static const uint32_t overlap = getenv("LQFT_N16_OVERLAP") ? (uint32_t)atoi(getenv("LQFT_N16_OVERLAP")) : kN16Overlap;
-            if (h->exchange_inflight && h->wedges.size() < overlap && g.Tl >= 2 * (depth + overlap + 1)) {
-                // underneath the exchange: planes that need neither the ghost planes nor the planes being sent;
-                // k-th deferred half-sweep: interior [a, Tl - a), a >= depth + k + 1, the rest in two wedges.
-                // The exchange kernel's blocks take slots from this launch (the register file is full with the
-                // sweep's own blocks), so it is planned on the slots that remain, and `a` is the cut for which
-                // interior + wedge launches cost least: a thinner interior may need one block column less.
-                const uint32_t k = (uint32_t)h->wedges.size(), a_min = depth + k + 1;
-                const uint32_t reserve = kN16ExchangeBlocks * 4 * h->cfg.n_chains * (kN16ExchangeThreads / kN16Threads);
-                uint32_t a = a_min;
-                if (k == 0 && !h->narrowp.forced_chunks) {
-                    double best = 1e300;
-                    const uint32_t span = 2 * kN16Warps * h->narrowp.ppw();  // planes of a block column pair
-                    for (uint32_t c = a_min; c <= a_min + span && g.Tl >= 2 * c + 2; ++c) {
-                        double ci = 0.0, cw = 0.0;
-                        narrow_chunks(h->narrowp, h->gn, g.Tl - 2 * c, h->cfg.n_chains, h->any_wilson, h->count_accepts, reserve, &ci);
-                        narrow_chunks(h->narrowp, h->gn, 2 * (extra + c), h->cfg.n_chains, h->any_wilson, h->count_accepts, 0, &cw);
-                        if (ci + cw < best - 1e-9) {
-                            best = ci + cw;
-                            a = c;
-                        }
-                    }
-                }
-                ST(launch_half_narrow(h, colour, sweep, ctr, (int32_t)a, g.Tl - 2 * a, 0, 0, reserve));
-                h->wedges.push_back({colour, sweep, ctr, -(int32_t)extra, (int32_t)(g.Tl - a), extra + a});
-                continue;
-            }
-            ST(narrow_exchange_end(h));
-            ST(launch_half_narrow(h, colour, sweep, ctr, -(int32_t)extra, g.Tl + 2 * extra, 0, 0));
+            ST(launch_half_narrow(h, colour, sweep, ctr, -(int32_t)extra, g.Tl + 2 * extra, flip, push));
+            if (h->nvalid == 0) h->next_ready = true;
         }
         return LQFT_OK;
     }
@@ -1037,10 +1056,7 @@ static lqft_status launch_measure_t(lqft_handle* h, const Geom& g, const H* f0, 
 
 static lqft_status launch_measure(lqft_handle* h, const Measure& m) {
     if (h->narrow_active) {
-        if (h->gn.ghost) {  // the last owned plane looks one plane up
-            if (h->nvalid == 0) ST(narrow_exchange_begin(h));
-            ST(narrow_exchange_end(h));
-        }
+        ST(narrow_need_ghost(h));  // the last owned plane looks one plane up
         return launch_measure_t<uint16_t>(h, h->gn, h->narrow[0], h->narrow[1], m);
     }
     ST(ghost_op_begin(h));
@@ -1054,10 +1070,7 @@ static lqft_status launch_difference(lqft_handle* h, uint32_t chain) {
     const uint32_t bd = block_for(g.plane);
     dim3 grid((g.plane + bd - 1) / bd, g.Tl, 1);
     if (h->narrow_active) {
-        if (h->gn.ghost) {
-            if (h->nvalid == 0) ST(narrow_exchange_begin(h));
-            ST(narrow_exchange_end(h));
-        }
+        ST(narrow_need_ghost(h));
         k_difference_update_h<uint16_t><<<grid, bd, 0, h->stream>>>(h->gn, h->narrow[0] + (size_t)chain * h->gn.chain_stride,
                                                                    h->narrow[1] + (size_t)chain * h->gn.chain_stride,
                                                                    h->diff_sum[chain], h->diff_comp[chain]);
@@ -1104,7 +1117,6 @@ static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint
         h->launches += 1;
         return LQFT_OK;
     }
-    if (h->narrow_active) ST(narrow_exchange_end(h));  // the picked site may lie in a wedge that is still behind
     if (h->narrow_active)
         k_pick_shift<<<(nc + 127) / 128, 128, 0, h->stream>>>(h->gn, (const uint16_t*)h->narrow[0], (const uint16_t*)h->narrow[1],
                                                              h->chains_d, nc, counter, ctr, explicit_site, only_chain, h->shift_d,
@@ -1492,16 +1504,14 @@ static lqft_status narrow_enter(lqft_handle* h, bool* ok) {
     CU(cudaStreamSynchronize(h->stream));
     *ok = worst == 0;
     h->narrow_active = *ok;
-    h->nvalid = 0;
-    if (*ok && g.ghost)
-        CU(cudaMemcpyAsync(h->phase_d, &h->phase, sizeof h->phase, cudaMemcpyHostToDevice, h->stream));
+    h->nvalid = 0;            // neither ghost set holds anything yet: the first half-sweep fills and flips
+    h->next_ready = false;
     if (*ok) h->narrow_segments += 1;
     return LQFT_OK;
 }
 
 static lqft_status narrow_exit(lqft_handle* h) {
     const Geom& g = h->g;
-    ST(narrow_exchange_end(h));
     const uint64_t count = (uint64_t)g.Tl * g.plane;
     dim3 grid((uint32_t)((count / 4 + 255) / 256), h->cfg.n_chains);
     for (int c = 0; c < 2; ++c)
@@ -1514,50 +1524,46 @@ static lqft_status narrow_exit(lqft_handle* h) {
     return LQFT_OK;
 }
 
-// Deep halo exchange of the narrow copy with both neighbours (k_n16_exchange, two phases of the flag protocol),
-// issued on the second stream: the caller may keep updating interior planes on the main stream until
-// narrow_exchange_end.
-static lqft_status narrow_exchange_begin(lqft_handle* h) {
+// First fill of the neighbours' other ghost set with this rank's boundary planes (k_n16_fill): after the copy was
+// built, or when a period is cut short.  The flip that follows tells the neighbours.
+static lqft_status narrow_fill(lqft_handle* h) {
     const Geom& gn = h->gn;
-    ST(narrow_exchange_end(h));
-    ExchangeArgs a{};
+    const uint32_t next = gn.gbuf ^ 1u;
+    FillArgs a{};
     for (int c = 0; c < 2; ++c) {
         a.mine[c] = h->narrow[c];
         a.lo[c] = (uint16_t*)h->peer_base[0][3 + c];
         a.hi[c] = (uint16_t*)h->peer_base[1][3 + c];
     }
     a.stride_mine = gn.chain_stride;
-    a.stride_lo = (uint64_t)gn.plane * (h->tl_lo + 2 * gn.ghost);
-    a.stride_hi = (uint64_t)gn.plane * (h->tl_hi + 2 * gn.ghost);
+    a.stride_lo = (uint64_t)gn.plane * (h->tl_lo + 4 * gn.ghost);
+    a.stride_hi = (uint64_t)gn.plane * (h->tl_hi + 4 * gn.ghost);
     a.plane = gn.plane;
     a.depth = gn.ghost;
     a.tl_mine = gn.Tl;
-    a.tl_lo = h->tl_lo;
-    a.sync_mine = h->halo_d;
-    a.sync_lo = (HaloSync*)h->peer_base[0][2];
-    a.sync_hi = (HaloSync*)h->peer_base[1][2];
-    a.phase = h->phase_d;
-    h->phase += 2;  // host mirror of what the kernel does to *phase_d
-    dim3 grid(kN16ExchangeBlocks, 4, h->cfg.n_chains);
-    CU(cudaEventRecord(h->ev_bnd, h->stream));
-    CU(cudaStreamWaitEvent(h->comm_stream, h->ev_bnd, 0));
-    k_n16_exchange<<<grid, kN16ExchangeThreads, 0, h->comm_stream>>>(a);
+    a.lo_plane = peer_ghost_plane(h, 0, next);
+    a.hi_plane = peer_ghost_plane(h, 1, next);
+    k_n16_fill<<<dim3(kN16FillBlocks, 4, h->cfg.n_chains), 256, 0, h->stream>>>(a);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(h->ev_comm, h->comm_stream));
     h->launches += 1;
-    h->nvalid = gn.ghost;
-    h->exchange_inflight = true;
+    h->next_ready = true;
     return LQFT_OK;
 }
 
-// Join the exchange and catch up, in order, the wedges of the half-sweeps that ran underneath it.
-static lqft_status narrow_exchange_end(lqft_handle* h) {
-    if (!h->exchange_inflight) return LQFT_OK;
-    CU(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
-    h->exchange_inflight = false;
-    for (const auto& w : h->wedges)
-        ST(launch_half_narrow(h, w.colour, w.sweep, w.ctr, w.lo_first, w.n_each, w.hi_first, w.n_each));
-    h->wedges.clear();
+// Operations other than a half-sweep that look at a ghost plane of the narrow copy (the observables: the last owned
+// plane looks one plane up): if the current set is used up, flip to the other one.
+static lqft_status narrow_need_ghost(lqft_handle* h) {
+    if (!h->narrow_active || h->gn.ghost == 0 || h->nvalid != 0) return LQFT_OK;
+    if (!h->next_ready) ST(narrow_fill(h));
+    h->phase += 1;
+    SlabArgs sl{};
+    flip_args(h, sl);
+    k_n16_flip<<<1, 32, 0, h->stream>>>(sl);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->gn.gbuf ^= 1u;
+    h->nvalid = h->gn.ghost;
+    h->next_ready = false;
     return LQFT_OK;
 }
 
@@ -1722,7 +1728,7 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_r
             else narrow = false;
         }
         if (!h->narrow_active) ST(refresh_ghosts(h));  // a narrow segment leaves the i32 ghost planes stale
-        // slabs replay graphs only on the narrow copy: its halo phases live in device memory (k_n16_exchange)
+        // slabs replay graphs only on the narrow copy: the numbers of its flips live in device memory
         const bool use_graph = graph_ok && (h->g.ghost == 0 || h->narrow_active);
         const bool deep = h->narrow_active && h->gn.ghost != 0;
         if (use_graph && step < seg_end) {
@@ -1731,41 +1737,51 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_r
                 ++step;
             }
             const uint64_t avail = (seg_end - step) / cycle;
-            const uint64_t reps = std::max<uint64_t>(1, std::min<uint64_t>(avail, std::max<uint64_t>(1, kGraphSteps / cycle)));
+            uint64_t reps = std::max<uint64_t>(1, std::min<uint64_t>(avail, std::max<uint64_t>(1, kGraphSteps / cycle)));
+            if (deep) {
+                // a replay must leave the ghost sets as it found them: whole periods of `depth` half-sweeps, and an
+                // even number of them (every period flips the set): the graph period is a multiple of `depth` sweeps
+                const uint64_t m = h->gn.ghost / gcd64(cycle, h->gn.ghost);
+                reps = std::max<uint64_t>(m, (reps + m - 1) / m * m);
+                if (reps > avail) reps = avail / m * m;
+            }
             const uint64_t period = reps * cycle;
-            const uint64_t n_periods = (seg_end - step) / period;
+            const uint64_t n_periods = period ? (seg_end - step) / period : 0;
             if (n_periods) {
+                if (deep && !(h->nvalid == 0 && h->next_ready)) {
+                    // entry state of a replay: the current set used up, the other one filled
+                    ST(narrow_fill(h));
+                    h->nvalid = 0;
+                }
                 GraphKey key{s->energy_every, s->normalize_every, s->action_every, s->correlator_every, s->correlator_reps,
-                             s->difference_every, (uint32_t)period, h->count_accepts, h->narrow_active};
+                             s->difference_every, (uint32_t)period, h->count_accepts, h->narrow_active, deep ? h->gn.gbuf : 0u};
                 auto it = h->graphs.find(key);
                 if (it == h->graphs.end()) {
-                    // capture one period; every kernel reads the sweep counter from device memory.  On slabs a
-                    // period starts with an exchange and ends with all wedges caught up, whatever came before.
-                    if (deep) {
-                        ST(narrow_exchange_end(h));
-                        h->nvalid = 0;
-                    }
+                    // capture one period; every kernel reads the sweep counter (and, on slabs, the number of the
+                    // flip it performs) from device memory
                     const unsigned long long phase_before = h->phase;
                     const uint64_t before = h->launches;
                     lqft_schedule rel = *s;
                     rel.sweep_base = 0;
                     cudaGraph_t graph = nullptr;
                     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                    h->capturing = true;
+                    h->phase_capture0 = phase_before;
                     lqft_status st = LQFT_OK;
                     for (uint64_t i = 0; i < period && st == LQFT_OK; ++i) st = launch_step(h, &rel, i, i, h->sweep_ctr_d);
-                    if (st == LQFT_OK && deep) st = narrow_exchange_end(h);  // joins the second stream
                     if (st == LQFT_OK) {
-                        k_tick<<<1, 1, 0, h->stream>>>(h->sweep_ctr_d, period);
+                        k_tick<<<1, 1, 0, h->stream>>>(h->sweep_ctr_d, period, h->phase_d, h->phase - phase_before);
                         h->launches += 1;
                     }
+                    h->capturing = false;
                     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-                    h->wedges.clear();
-                    h->exchange_inflight = false;
                     if (st != LQFT_OK) {
                         if (graph) cudaGraphDestroy(graph);
                         return st;
                     }
                     if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+                    if (deep && !(h->nvalid == 0 && h->next_ready && h->gn.gbuf == key.gbuf))
+                        return fail(LQFT_ERR_STATE, "internal: a captured period must end where it began (ghost sets)");
                     GraphVal val;
                     val.kernels = h->launches - before;
                     val.phases = h->phase - phase_before;
@@ -1776,12 +1792,9 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_r
                     if (ce != cudaSuccess) return fail(LQFT_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
                     it = h->graphs.emplace(key, val).first;
                 }
-                if (deep) {
-                    ST(narrow_exchange_end(h));
-                    h->nvalid = 0;  // what every replay ends with
-                }
                 const uint64_t base = s->sweep_base + step;
                 CU(cudaMemcpyAsync(h->sweep_ctr_d, &base, sizeof base, cudaMemcpyHostToDevice, h->stream));
+                if (deep) CU(cudaMemcpyAsync(h->phase_d, &h->phase, sizeof h->phase, cudaMemcpyHostToDevice, h->stream));
                 for (uint64_t c = 0; c < n_periods; ++c) CU(cudaGraphLaunch(it->second.exec, h->stream));
                 h->launches += it->second.kernels * n_periods;
                 h->phase += it->second.phases * n_periods;
@@ -1892,7 +1905,7 @@ extern "C" lqft_status lqft_plan_info(lqft_handle* h, char* buf, size_t cap) {
         chunks = narrow_chunks(h->narrowp, h->gn, h->g.Tl, h->cfg.n_chains, h->any_wilson, false);
         rows = (h->g.Y + chunks - 1) / chunks;
         groups = narrow_groups(h->narrowp, h->g.Tl);
-        occ = narrow_occupancy(h->narrowp, h->any_wilson, false, narrow_warps(h->narrowp, h->g.Tl));
+        occ = narrow_occupancy(h->narrowp, h->any_wilson, false, false, narrow_warps(h->narrowp, h->g.Tl));
     }
     snprintf(buf, cap, "path=%s chunks=%u rows_per_chunk=%u plane_blocks=%u blocks_per_sm=%d ghost_depth=%u p2p=%d", path, chunks, rows,
              groups, occ, h->narrowp.enabled ? h->gn.ghost : h->g.ghost, h->p2p ? 1 : 0);
