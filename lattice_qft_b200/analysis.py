@@ -1,6 +1,8 @@
 """Host-side statistics the validation harness needs: the second-moment correlation
 length of src/lib.rs:106-167, the symmetrisation of src/bin/correlation_data_analysis.rs:541-548, and
-chain-mean errors.  O(T) host arithmetic on measured observables — nothing here touches the field."""
+chain-mean errors, the error-propagated correlation length (lib.rs:122-159), the compounded binned bootstrap of the
+correlation functions (correlation_data_analysis.rs:371-473) and the cosh fit (:584-712).  O(T) host arithmetic on
+measured observables — nothing here touches the field."""
 from __future__ import annotations
 
 import cmath
@@ -115,3 +117,135 @@ def weighted_linear_fit(x: Sequence[float], y: Sequence[float], err: Sequence[fl
     a = np.stack([x, np.ones_like(x)], axis=1)
     sol = np.linalg.solve(a.T @ (w[:, None] * a), a.T @ (w * y))
     return float(sol[0]), float(sol[1])
+
+
+# ---- correlation length with errors (src/lib.rs:122-159) -------------------------------------------------------
+def calculate_correlation_length_errors(corr_fn: Sequence[float], corr_fn_err: Sequence[float], p1: float,
+                                        p2: float) -> Tuple[Tuple[float, float], Tuple[float, float]]:
+    """((Re m, Im m), (err Re m, 0)): linear error propagation of the per-point errors u_j of the correlation
+    function through m = acosh((g1 cos p1 - g2 cos p2) / (g1 - g2)), g_k = sum_j exp(i j p_k) c_j:
+        dm/dc_j = (g1 e^{i j p2} - e^{i j p1} g2)(cos p1 - cos p2) / ((g1 - g2)^2 sqrt(z - 1) sqrt(z + 1)),
+    err = sqrt(sum_j |dm/dc_j u_j|^2) — lib.rs:143-156, literally."""
+    g1 = discrete_fourier_transform(corr_fn, p1)
+    g2 = discrete_fourier_transform(corr_fn, p2)
+    cos1, cos2 = math.cos(p1), math.cos(p2)
+    y = g1 - g2
+    z = (g1 * cos1 - g2 * cos2) / y
+    ma = cmath.acosh(z)
+    total = 0.0
+    for pos, u in enumerate(corr_fn_err):
+        dg1, dg2 = cmath.exp(1j * pos * p1), cmath.exp(1j * pos * p2)
+        df = ((g1 * dg2 - dg1 * g2) * (cos1 - cos2)) / (y * y * cmath.sqrt(z - 1.0) * cmath.sqrt(z + 1.0))
+        total += abs(df * u) ** 2
+    return (ma.real, ma.imag), (math.sqrt(total), 0.0)
+
+
+class Welford:
+    """WelfordsAlgorithm64 (kahan.rs:78-138) on plain floats, vectorised over a trailing axis; keeps the crate's
+    quirk that get_standard_error returns var_unbiased / sqrt(n) (kahan.rs:135-137), not sqrt(var / n)."""
+
+    def __init__(self, shape=()):
+        self.sum = np.zeros(shape)
+        self.dss = np.zeros(shape)
+        self.n = 0
+
+    def update(self, value):
+        value = np.asarray(value, dtype=np.float64)
+        old = self.sum / self.n if self.n else np.zeros_like(self.sum)
+        self.sum = self.sum + value
+        self.n += 1
+        new = self.sum / self.n
+        self.dss = self.dss + (value - old) * (value - new)
+
+    def update_many(self, rows: np.ndarray):
+        """Same result as update() row by row up to rounding: mean and centred sum of squares of all rows."""
+        rows = np.asarray(rows, dtype=np.float64)
+        if self.n == 0:
+            self.n = rows.shape[0]
+            self.sum = rows.sum(axis=0)
+            self.dss = ((rows - rows.mean(axis=0)) ** 2).sum(axis=0)
+        else:
+            for r in rows:
+                self.update(r)
+
+    def get_mean(self):
+        return self.sum / self.n if self.n else np.zeros_like(self.sum)
+
+    def get_var_unbiased(self):
+        return self.dss / (self.n - 1) if self.n > 1 else np.zeros_like(self.dss)
+
+    def get_sd_unbiased(self):
+        return np.sqrt(self.get_var_unbiased())
+
+    def get_standard_error(self):
+        return self.get_var_unbiased() / math.sqrt(self.n) if self.n else np.zeros_like(self.dss)
+
+
+def compounded_binned_bootstrap(simulations: Sequence[np.ndarray], bin_size: int, ensembles: int = BOOTSTRAPPING_ENSEMBLES,
+                                seed0: int = 0, symmetrize: bool = True) -> dict:
+    """average_over_simulation_then_build_statistics (src/bin/correlation_data_analysis.rs:371-473).
+
+    `simulations`: one array [n_measurements, T] of correlation functions per simulation of the same parameters.
+    Each is symmetrised (:541-548) and cut into bins of `bin_size` consecutive measurements (chunks_exact).  Every
+    bootstrap ensemble redraws the simulations with replacement and, inside a simulation, as many bins as it has,
+    with replacement; over all redrawn measurements it forms per-tau mean and `get_standard_error` (the crate's
+    var/sqrt(n), see Welford), and from those xi_12 and its propagated error (calculate_correlation_length_errors,
+    p1 = 2 pi / T, p2 = 2 p1).  Returned: statistics over the ensembles — corr_fn mean / sd per tau, mass
+    m_12 = 1/xi_12 mean and sd, and the mean propagated error.  The reference seeds ensemble i with
+    StdRng::seed_from_u64(i); numpy's generator stands in (same recipe, different stream)."""
+    binned = []
+    for sim in simulations:
+        a = np.asarray(sim, dtype=np.float64)
+        if symmetrize:
+            a = np.stack([symmetrize_single_correlation_function(r) for r in a])
+        n = a.shape[0] // bin_size
+        if n:
+            binned.append(a[: n * bin_size].reshape(n, bin_size, a.shape[1]))
+    if not binned:
+        raise ValueError("no simulation holds a full bin")
+    t = binned[0].shape[2]
+    p1 = 2.0 * math.pi / t
+    fn_stats, m_stats, err_stats = Welford((t,)), Welford(), Welford()
+    for e in range(ensembles):
+        rng = np.random.default_rng(seed0 + e)
+        rows = []
+        for _ in binned:
+            b = binned[rng.integers(len(binned))]
+            rows.append(b[rng.integers(len(b), size=len(b))].reshape(-1, t))
+        w = Welford((t,))
+        w.update_many(np.concatenate(rows))
+        (m, _), (m_err, _) = calculate_correlation_length_errors(w.get_mean(), w.get_standard_error(), p1, 2.0 * p1)
+        fn_stats.update(w.get_mean())
+        m_stats.update(m)
+        err_stats.update(m_err)
+    return {"corr_fn": fn_stats.get_mean(), "corr_fn_sd": fn_stats.get_sd_unbiased(),
+            "m12": float(m_stats.get_mean()), "m12_sd": float(m_stats.get_sd_unbiased()),
+            "m12_propagated_err": float(err_stats.get_mean()), "xi12": 1.0 / float(m_stats.get_mean()),
+            "ensembles": ensembles, "bin_size": bin_size}
+
+
+def cosh_fit(corr_fn: Sequence[float], m0: float = 0.1) -> dict:
+    """nonlin_regression (src/bin/correlation_data_analysis.rs:635-712): y_j = max(c) - c_j is fitted by
+    c0 cosh(m (j - n/2)) + c1 with n = len(c); m by Levenberg-Marquardt from m0 = 0.1, the linear coefficients by
+    variable projection (the `varpro` crate's separable model: basis {cosh(m (x - n/2)), 1}).  Returns m, n, c0,
+    c1 — the columns of correlation_{i}_fits.csv."""
+    from scipy.optimize import least_squares
+    c = np.asarray(corr_fn, dtype=np.float64)
+    n = float(len(c))
+    y = c.max() - c
+    x = np.arange(len(c), dtype=np.float64)
+
+    def basis(m):
+        return np.stack([np.cosh(m * (x - n / 2.0)), np.ones_like(x)], axis=1)
+
+    def residual(p):
+        phi = basis(p[0])
+        coeff, *_ = np.linalg.lstsq(phi, y, rcond=None)
+        return phi @ coeff - y
+
+    sol = least_squares(residual, x0=[m0], method="lm", xtol=np.finfo(np.float64).eps)
+    if not sol.success:
+        raise RuntimeError("termination was not successful")
+    m = float(sol.x[0])
+    coeff, *_ = np.linalg.lstsq(basis(m), y, rcond=None)
+    return {"m": m, "n": n, "c0": float(coeff[0]), "c1": float(coeff[1])}
