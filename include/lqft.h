@@ -226,8 +226,9 @@ lqft_status lqft_stream(lqft_handle* h, void** stream);
 /* Philox4x32-10 (Salmon et al. 2011; constants of Random123).  key = seed lo/hi. */
 void lqft_host_philox4x32(uint64_t seed, const uint32_t ctr[4], uint32_t out[4]);
 /* The 32-bit word that drives site `idx` (global lexicographic) of colour stream
- * (x+y+t)&1 in sweep `sweep`: counter = (idx>>3, colour, sweep_lo, sweep_hi), word
- * (idx>>1)&3.  Bit 31 = coin (1 -> +1, 0 -> -1; algorithm.rs:138-143), low 31 bits u:
+ * (x+y+t)&1 in sweep `sweep`: with grp = idx>>3 (64 bits), counter =
+ * (grp & 0xffffffff, colour | (grp>>32)<<8, sweep_lo, sweep_hi), word (idx>>1)&3; the second
+ * word is just `colour` below 2^35 sites.  Bit 31 = coin (1 -> +1, 0 -> -1; algorithm.rs:138-143), low 31 bits u:
  * draw = u * 2^-31 (algorithm.rs:151). */
 uint32_t lqft_host_site_word(uint64_t seed, uint64_t idx, uint32_t colour, uint64_t sweep);
 /* Threshold table for `beta`: entry k serves m = k - 3 where the proposal changes the local

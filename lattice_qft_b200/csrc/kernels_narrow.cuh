@@ -37,7 +37,7 @@
 
 namespace lqft {
 
-constexpr int kN16Warps = 8;                     // per block: 8 planes of one parity (16 for X = 256)
+constexpr int kN16Warps = 8;                     // per block, at most (9 warps at 56 registers: 6 % slower, measured)
 constexpr int kN16Threads = kN16Warps * 32;
 constexpr int kN16Bias = 2048;
 constexpr int kN16Guard = 1023;
@@ -149,40 +149,25 @@ struct SlabArgs {
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void halo_wait_relaxed(const unsigned long long* flag, unsigned long long need, unsigned int* error) {
-    if (ld_relaxed_sys(flag) < need) {
-        const unsigned long long t0 = global_timer_ns();
-        const unsigned long long limit = *reinterpret_cast<volatile unsigned long long*>(&g_halo_timeout_ns);
-        while (ld_relaxed_sys(flag) < need) {
-            __nanosleep(32);
-            if (global_timer_ns() - t0 > limit) {
-                atomicExch(error, 1u);
-                __threadfence_system();
-                __trap();
-            }
-        }
-    }
-}
-// Flip of the ghost sets, whole block: one thread of the launch tells both neighbours that this rank has finished the
-// period (its pushes were flushed when the previous kernel completed); every block then waits until both neighbours
-// have said the same, i.e. until the other ghost set holds their planes.
-__device__ __forceinline__ void slab_flip(const SlabArgs& sl, bool first_block) {
-    if (threadIdx.x == 0) {
+// Flip of the ghost sets.  One thread of the launch tells both neighbours that this rank has finished the period (its
+// pushes were flushed when the previous kernel completed: the flag store needs no fence of its own).  A block that
+// is going to touch a ghost plane — `waits`: its planes include a ghost plane or a boundary plane, whose t
+// neighbour is one — spins with acquire loads until both neighbours have said the same, i.e. until the other ghost
+// set holds their planes; every other block goes straight on.  No fence: the acquire load orders the block's later
+// reads (bar.sync extends it to the other threads), and a system-scope fence per block costs microseconds.
+__device__ __forceinline__ void slab_flip(const SlabArgs& sl, bool first_block, bool waits) {
+    if (threadIdx.x == 0 && (first_block || waits)) {
         const unsigned long long seq = (sl.seq_base ? *sl.seq_base : 0ull) + sl.seq_off;
         if (first_block) {
             st_relaxed_sys(&sl.lo_sync->from_hi, seq);
             st_relaxed_sys(&sl.hi_sync->from_lo, seq);
         }
-        halo_wait_relaxed(&sl.mine->from_lo, seq, &sl.mine->error);
-        halo_wait_relaxed(&sl.mine->from_hi, seq, &sl.mine->error);
-        __threadfence_system();
+        if (waits) {
+            halo_wait(&sl.mine->from_lo, seq, &sl.mine->error);
+            halo_wait(&sl.mine->from_hi, seq, &sl.mine->error);
+        }
     }
-    __syncthreads();
+    __syncthreads();  // also where the compiler sees the block converge again: without it the sweep loop is compiled as divergent code
 }
 
 template <int XQ, bool WILSON, bool COUNT, bool SINGLE, bool SLAB>
@@ -205,8 +190,12 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     const uint32_t c_off = (uint32_t)((kc - 24576) & 0xffff) * 0x10001u, c_max = (uint32_t)(2 * kc) * 0x10001u;
     pdl_wait();
     if (ctr) sweep += *ctr;
+    // planes of this block's group: local numbers [grp_lo, grp_hi) of a launch with one range (every SLAB launch)
+    const int32_t grp_lo = tl_first + (int32_t)((blockIdx.y >> 1) * (2u * PPW * (blockDim.x >> 5)));
+    const int32_t grp_hi = grp_lo + (int32_t)(2u * PPW * (blockDim.x >> 5));
     if (SLAB) {
-        if (sl.sync) slab_flip(sl, blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0);
+        if (sl.sync)
+            slab_flip(sl, blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0, grp_lo <= 0 || grp_hi >= (int32_t)g.Tl);
     }
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -257,7 +246,7 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         const bool wil_plane = WILSON && tg < cd.wil_h;
         const uint32_t y_one = 1u % g.Y;
         uint32_t n = y1 - y0;
-#define LQFT_N16_STEP(OM, OC, ON)                                                                                       \
+#define LQFT_N16_STEP(OM, OC, ON, PUSH)                                                                                     \
     {                                                                                                                    \
         const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;                                                                  \
         uint4* const po = q_own + (b_own + y * ROWQ);                                                                    \
@@ -291,20 +280,33 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         }                                                                                                                \
         if (COUNT) accepted += owned ? acc_row : 0;                                                                      \
         if (live) *po = w;                                                                                               \
-        if (SLAB) {                                                                                                      \
+        if (PUSH) {                                                                                                      \
             if (q_lo) q_lo[y * ROWQ] = w;                                                                                \
             if (q_hi) q_hi[y * ROWQ] = w;                                                                                \
         }                                                                                                                \
         y = yn;                                                                                                          \
         p ^= 1u;                                                                                                         \
     }
-        for (;;) {
-            LQFT_N16_STEP(wa, wb, wc)
-            if (--n == 0) break;
-            LQFT_N16_STEP(wb, wc, wa)
-            if (--n == 0) break;
-            LQFT_N16_STEP(wc, wa, wb)
-            if (--n == 0) break;
+        // only the blocks whose group holds one of the first / last `depth` owned planes carry the push stores
+        if (SLAB && sl.depth != 0u && grp_hi > 0 && grp_lo < (int32_t)g.Tl &&
+            (grp_lo < (int32_t)sl.depth || grp_hi > (int32_t)(g.Tl - sl.depth))) {
+            for (;;) {
+                LQFT_N16_STEP(wa, wb, wc, true)
+                if (--n == 0) break;
+                LQFT_N16_STEP(wb, wc, wa, true)
+                if (--n == 0) break;
+                LQFT_N16_STEP(wc, wa, wb, true)
+                if (--n == 0) break;
+            }
+        } else {
+            for (;;) {
+                LQFT_N16_STEP(wa, wb, wc, false)
+                if (--n == 0) break;
+                LQFT_N16_STEP(wb, wc, wa, false)
+                if (--n == 0) break;
+                LQFT_N16_STEP(wc, wa, wb, false)
+                if (--n == 0) break;
+            }
         }
 #undef LQFT_N16_STEP
     }
@@ -341,7 +343,7 @@ k_n16_fill(const FillArgs a) {
 }
 
 // The flip on its own (one thread), for operations other than a half-sweep that need the next ghost set.
-__global__ void k_n16_flip(const SlabArgs sl) { slab_flip(sl, true); }
+__global__ void k_n16_flip(const SlabArgs sl) { slab_flip(sl, true, true); }
 
 // ---- i32 <-> narrow ---------------------------------------------------------------------------------------
 // Owned planes of one colour, 4 heights per thread.  grid = (ceil(n/4/256), n_chains); n = Tl * plane elements per
@@ -471,10 +473,20 @@ inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, uint32_t n_chain
     return cudaSuccess;
 }
 
-// Warps per block: as many as the planes of one parity need, at most kN16Warps.
+// Blocks along the planes come in pairs (even / odd planes).  As few pairs as kN16Warps warps per block allow, then
+// as few warps per block as those pairs need: 256 planes of X = 256 run 8 pairs of 8-warp blocks, and so do — with
+// 9 warps — the up to 288 planes of a slab whose ghost planes are being updated along (same grid, same y chunks,
+// same rows per warp as without ghost planes).
+inline uint32_t narrow_plane_warps(const NarrowPlan& p, uint32_t n_planes) {  // warps one parity needs
+    const uint32_t w = ((n_planes + 1) / 2 + p.ppw() - 1) / p.ppw();
+    return w < 1 ? 1 : w;
+}
+inline uint32_t narrow_pairs(const NarrowPlan& p, uint32_t n_planes) {
+    return (narrow_plane_warps(p, n_planes) + kN16Warps - 1) / kN16Warps;
+}
 inline uint32_t narrow_warps(const NarrowPlan& p, uint32_t n_planes) {
-    const uint32_t need = ((n_planes + 1) / 2 + p.ppw() - 1) / p.ppw();
-    return need < 1 ? 1 : (need > (uint32_t)kN16Warps ? (uint32_t)kN16Warps : need);
+    const uint32_t pairs = narrow_pairs(p, n_planes);
+    return (narrow_plane_warps(p, n_planes) + pairs - 1) / pairs;
 }
 
 // Resident blocks per SM of the instantiation a launch will use (each has its own register count).
@@ -491,11 +503,8 @@ inline int narrow_occupancy(NarrowPlan& p, bool wilson, bool count, bool slab, u
     return o;
 }
 
-// grid.y: blocks along the planes: block pairs (even / odd planes) over 2 * warps * planes-per-warp planes.
-inline uint32_t narrow_groups(const NarrowPlan& p, uint32_t n_planes) {
-    const uint32_t per_pair = 2 * narrow_warps(p, n_planes) * p.ppw();
-    return 2 * ((n_planes + per_pair - 1) / per_pair);
-}
+// grid.y
+inline uint32_t narrow_groups(const NarrowPlan& p, uint32_t n_planes) { return 2 * narrow_pairs(p, n_planes); }
 
 // y chunks per plane group: one wave if possible, chunks as short as that allows (cost model of stream_chunks;
 // the per-chunk prologue is worth about two rows here).
