@@ -128,7 +128,9 @@ lqft_status lqft_download(lqft_handle* h, uint32_t chain, void* values);
  * 165-174) — per-site logic of metropolis_single (algorithm.rs:127-158) unchanged, site
  * order red-black instead of lexicographic.  accepted[n_chains] (nullable) receives the
  * number of accepted proposals summed over the n_sweeps (the `usize` field_sweep returns),
- * for this rank's slab.  Asynchronous unless `accepted` is given. */
+ * for this rank's slab.  Asynchronous unless `accepted` is given — with one exception: where the 16-bit arrays store the
+ * field (powers of two 16 <= X <= 1024), the heights are measured against the band once the sweep budget of the last
+ * measurement is used up (at most once per 1024 sweeps), and that measurement is read by the host. */
 lqft_status lqft_sweep(lqft_handle* h, uint64_t first_sweep, uint32_t n_sweeps,
                        uint64_t* accepted);
 
@@ -211,9 +213,11 @@ lqft_status lqft_synchronize(lqft_handle* h);
 lqft_status lqft_last_device_ms(lqft_handle* h, float* ms);
 /* Number of kernels this handle has launched so far (graph replays count their nodes). */
 lqft_status lqft_kernel_launches(lqft_handle* h, uint64_t* n);
-/* Number of update segments this handle has run on the 16-bit working copy so far (0 = every sweep went
- * through the i32 kernels: other extents than X in {256, 512, 1024}, LQFT_FLAG_NO_NARROW, or heights outside the guard
- * band around the chain's normalisation offset). */
+/* How often this handle has taken the heights into its 16-bit storage or confirmed them there: a hot start, an upload
+ * that fits the band, a conversion from the i32 arrays, a re-centring when the sweep budget of the last measurement
+ * was used up.  0 = every sweep went through the i32 kernels (X not a power of two in [16, 1024], LQFT_FLAG_NO_NARROW,
+ * or heights outside the guard band around the chain's normalisation offset).  lqft_plan_info says which copy is
+ * live right now (storage=u16|i32). */
 lqft_status lqft_narrow_segments(lqft_handle* h, uint64_t* n);
 /* One line describing the launch plan the handle would use for its update kernels right now, e.g.
  * "path=narrow chunks=37 rows_per_chunk=7 plane_blocks=16 blocks_per_sm=4 ghost_depth=0 p2p=0" (for logs and for

@@ -205,7 +205,9 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     const uint32_t pl_raw = (blockIdx.y >> 1) * (2u * PPW * (blockDim.x >> 5)) + 2u * slot + (blockIdx.y & 1u);
     const uint32_t y0 = chunk * g.Y / n_chunks, y1 = (chunk + 1u) * g.Y / n_chunks;
     int accepted = 0;
-    const bool live = pl_raw < n_planes;              // surplus warps: plane 0 of the range, stores off
+    // (An early exit of warps without a live plane slot — `if (__all_sync(~0u, pl_raw >= n_planes)) return;` — compiles
+    // without divergence handling but moves the Philox keys out of the uniform registers: 3.6 % slower at 256^3.)
+    const bool live = pl_raw < n_planes;              // surplus plane slots: plane 0 of the range, stores off
     const uint32_t pl = live ? pl_raw : 0u;
     {
         const uint32_t tl = pl < n_first ? (uint32_t)tl_first + pl : (uint32_t)tl_second + (pl - n_first);
@@ -346,6 +348,18 @@ k_n16_fill(const FillArgs a) {
 __global__ void k_n16_flip(const SlabArgs sl) { slab_flip(sl, true, true); }
 
 // ---- i32 <-> narrow ---------------------------------------------------------------------------------------
+// Largest |height - centre| a conversion met, into *worst: one atomic per block, and none once the word is at
+// least as large (capped at 2^24).
+__device__ __forceinline__ void n16_report_worst(uint32_t far, uint32_t* __restrict__ worst) {
+    __shared__ uint32_t s_far;
+    if (threadIdx.x == 0) s_far = 0;
+    __syncthreads();
+    far = __reduce_max_sync(0xffffffffu, far);
+    if ((threadIdx.x & 31u) == 0u && far) atomicMax(&s_far, far);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_far > *reinterpret_cast<volatile uint32_t*>(worst)) atomicMax(worst, s_far);
+}
+
 // Owned planes of one colour, 4 heights per thread.  grid = (ceil(n/4/256), n_chains); n = Tl * plane elements per
 // chain, src/dst point at the first owned plane of chain 0.  worst = max |height - centre| over everything converted.
 __global__ void __launch_bounds__(256)
@@ -360,14 +374,13 @@ k_narrow(const int32_t* __restrict__ f, uint64_t f_stride, uint16_t* __restrict_
         // wide arithmetic: an uploaded field may hold any i32
         const long long dx = (long long)v.x - c, dy = (long long)v.y - c, dz = (long long)v.z - c, dw = (long long)v.w - c;
         const long long m = max(max(llabs(dx), llabs(dy)), max(llabs(dz), llabs(dw)));
-        far = (uint32_t)min(m, (long long)(1 << 24));  // capped: the word is summed over ranks
+        far = (uint32_t)min(m, (long long)(1 << 24));
         uint2 o;
         o.x = ((uint32_t)(dx + kN16Bias) & 0xffffu) | ((uint32_t)(dy + kN16Bias) << 16);
         o.y = ((uint32_t)(dz + kN16Bias) & 0xffffu) | ((uint32_t)(dw + kN16Bias) << 16);
         reinterpret_cast<uint2*>(n + (size_t)chain * n_stride)[i] = o;
     }
-    far = __reduce_max_sync(0xffffffffu, far);
-    if ((threadIdx.x & 31u) == 0u && far > (uint32_t)kN16Guard) atomicMax(worst, far);
+    n16_report_worst(far, worst);
 }
 
 __global__ void __launch_bounds__(256)
@@ -389,6 +402,49 @@ __global__ void k_narrow_begin(const int32_t* __restrict__ offset, int32_t* __re
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n_chains) centre[c] = offset[c];
     if (c == 0) *worst = 0;
+}
+
+// ---- the 16-bit copy as the storage between calls: re-centring -----------------------------------------------------
+// A sweep moves a height by at most one, so after a conversion that measured `worst` the copy is good for
+// kN16Bias - 1 - worst sweeps (host: narrow_budget).  When they are used up the heights are measured against the
+// chain's CURRENT normalisation offset (k_n16_worst) and, if they lie within kN16Guard of it, moved there in place
+// (k_n16_rebias; centre := offset afterwards, k_narrow_begin); otherwise the field goes back to i32 (k_widen).
+// Same grid as k_narrow.  centre = current centres, target = the offsets.
+__global__ void __launch_bounds__(256)
+k_n16_worst(const uint16_t* __restrict__ n, uint64_t n_stride, uint64_t count, const int32_t* __restrict__ centre,
+            const int32_t* __restrict__ target, uint32_t* __restrict__ worst) {
+    const uint32_t chain = blockIdx.y;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t far = 0;
+    if (i < count / 4) {
+        const long long d = (long long)centre[chain] - target[chain] - kN16Bias;
+        const uint2 v = reinterpret_cast<const uint2*>(n + (size_t)chain * n_stride)[i];
+        const long long a = llabs((long long)(v.x & 0xffffu) + d), b = llabs((long long)(v.x >> 16) + d);
+        const long long c = llabs((long long)(v.y & 0xffffu) + d), e = llabs((long long)(v.y >> 16) + d);
+        far = (uint32_t)min(max(max(a, b), max(c, e)), (long long)(1 << 24));
+    }
+    n16_report_worst(far, worst);
+}
+
+__global__ void __launch_bounds__(256)
+k_n16_rebias(uint16_t* __restrict__ n, uint64_t n_stride, uint64_t count, const int32_t* __restrict__ centre,
+             const int32_t* __restrict__ target) {
+    const uint32_t chain = blockIdx.y;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count / 4) return;
+    // |delta| <= 2 * kN16Guard + 2 (k_n16_worst has passed): the packed halves cannot carry into each other
+    const uint32_t d = (uint32_t)(centre[chain] - target[chain]) & 0xffffu;
+    uint2* q = reinterpret_cast<uint2*>(n + (size_t)chain * n_stride) + i;
+    uint2 v = *q;
+    v.x = ((v.x + d) & 0xffffu) | ((v.x + (d << 16)) & 0xffff0000u);
+    v.y = ((v.y + d) & 0xffffu) | ((v.y + (d << 16)) & 0xffff0000u);
+    *q = v;
+}
+
+// Every height of the 16-bit arrays := kN16Bias (a field of zeros around centre 0).  n = uint32 words.
+__global__ void k_n16_zero(uint32_t* __restrict__ words, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        words[i] = (uint32_t)kN16Bias * 0x10001u;
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -426,20 +482,18 @@ struct NarrowArgs {
     SlabArgs sl{};
 };
 
-// SLAB instantiations read the chain parameters from memory (SINGLE = false): they are 2 of the `depth` launches of
-// a period, not worth another 28 kernels.
+template <int XQ, bool SLAB>
+inline const void* n16_variant_s(bool w, bool c, bool s) {
+    if (w) {
+        if (c) return s ? (const void*)k_sweep_n16<XQ, true, true, true, SLAB> : (const void*)k_sweep_n16<XQ, true, true, false, SLAB>;
+        return s ? (const void*)k_sweep_n16<XQ, true, false, true, SLAB> : (const void*)k_sweep_n16<XQ, true, false, false, SLAB>;
+    }
+    if (c) return s ? (const void*)k_sweep_n16<XQ, false, true, true, SLAB> : (const void*)k_sweep_n16<XQ, false, true, false, SLAB>;
+    return s ? (const void*)k_sweep_n16<XQ, false, false, true, SLAB> : (const void*)k_sweep_n16<XQ, false, false, false, SLAB>;
+}
 template <int XQ>
 inline const void* n16_variant(bool w, bool c, bool s, bool slab) {
-    if (slab) {
-        if (w) return c ? (const void*)k_sweep_n16<XQ, true, true, false, true> : (const void*)k_sweep_n16<XQ, true, false, false, true>;
-        return c ? (const void*)k_sweep_n16<XQ, false, true, false, true> : (const void*)k_sweep_n16<XQ, false, false, false, true>;
-    }
-    if (w) {
-        if (c) return s ? (const void*)k_sweep_n16<XQ, true, true, true, false> : (const void*)k_sweep_n16<XQ, true, true, false, false>;
-        return s ? (const void*)k_sweep_n16<XQ, true, false, true, false> : (const void*)k_sweep_n16<XQ, true, false, false, false>;
-    }
-    if (c) return s ? (const void*)k_sweep_n16<XQ, false, true, true, false> : (const void*)k_sweep_n16<XQ, false, true, false, false>;
-    return s ? (const void*)k_sweep_n16<XQ, false, false, true, false> : (const void*)k_sweep_n16<XQ, false, false, false, false>;
+    return slab ? n16_variant_s<XQ, true>(w, c, s) : n16_variant_s<XQ, false>(w, c, s);
 }
 inline const void* n16_kernel(int xq, bool w, bool c, bool s, bool slab) {
     switch (xq) {
@@ -473,10 +527,10 @@ inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, uint32_t n_chain
     return cudaSuccess;
 }
 
-// Blocks along the planes come in pairs (even / odd planes).  As few pairs as kN16Warps warps per block allow, then
-// as few warps per block as those pairs need: 256 planes of X = 256 run 8 pairs of 8-warp blocks, and so do — with
-// 9 warps — the up to 288 planes of a slab whose ghost planes are being updated along (same grid, same y chunks,
-// same rows per warp as without ghost planes).
+// Blocks along the planes come in pairs (even / odd planes): as few pairs as kN16Warps warps per block allow, then as
+// few warps per block as those pairs need.  (Choosing the block size that leaves the fewest surplus warps — 17 pairs
+// of 4-warp blocks for the 270 planes of a slab with ghost planes in flight instead of 9 pairs of 8 — executes 5 %
+// fewer instructions and still runs 2 % slower: measured.)
 inline uint32_t narrow_plane_warps(const NarrowPlan& p, uint32_t n_planes) {  // warps one parity needs
     const uint32_t w = ((n_planes + 1) / 2 + p.ppw() - 1) / p.ppw();
     return w < 1 ? 1 : w;
@@ -494,7 +548,7 @@ inline int narrow_occupancy(NarrowPlan& p, bool wilson, bool count, bool slab, u
     int& o = p.occ[wilson][count][slab][warps];
     if (o == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, n16_kernel(p.xq, wilson, count, !slab, slab), (int)(32 * warps), 0) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, n16_kernel(p.xq, wilson, count, true, slab), (int)(32 * warps), 0) != cudaSuccess) {
             cudaGetLastError();
             n = 1;
         }

@@ -205,39 +205,59 @@ k_sweep_vec4(Geom g, int colour, uint64_t sweep, const uint64_t* __restrict__ ct
 
 // ---- layout conversion: lexicographic host order <-> colour split -------------------------
 // One thread per x-pair (x = 2k, 2k+1) of an owned plane.  grid = (ceil(plane/bd), Tl, 1).
-__global__ void k_split(Geom g, const int32_t* __restrict__ lex, int32_t* __restrict__ c0,
-                        int32_t* __restrict__ c1) {
+// H = int32_t: the i32 arrays.  H = uint16_t: the 16-bit arrays (kernels_narrow.cuh), stored = value - centre + bias
+// with *centre the chain's centre; k_split then also reports the largest |value - centre| it met (*worst, atomicMax;
+// capped at 2^24), from which the caller decides whether the 16-bit copy can hold the chain at all.
+template <typename H>
+__global__ void k_split(Geom g, const int32_t* __restrict__ lex, H* __restrict__ c0, H* __restrict__ c1,
+                        const int32_t* __restrict__ centre, int32_t bias, uint32_t* __restrict__ worst) {
     const uint32_t tl = blockIdx.y;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.plane) return;
-    const uint32_t y = i / g.Xh;
-    const uint32_t q = (y + g.t0 + tl) & 1u;  // colour of the even-x site of this pair
-    const size_t src = ((size_t)tl * g.plane + i);
-    const int2 v = reinterpret_cast<const int2*>(lex)[src];
-    const size_t dst = (size_t)plane_self(g, tl) * g.plane + i;
-    (q ? c1 : c0)[dst] = v.x;
-    (q ? c0 : c1)[dst] = v.y;
+    uint32_t far = 0;
+    if (i < g.plane) {
+        const uint32_t y = i / g.Xh;
+        const uint32_t q = (y + g.t0 + tl) & 1u;  // colour of the even-x site of this pair
+        const size_t src = ((size_t)tl * g.plane + i);
+        const int2 v = reinterpret_cast<const int2*>(lex)[src];
+        const size_t dst = (size_t)plane_self(g, tl) * g.plane + i;
+        if constexpr (sizeof(H) == 2) {
+            const long long dx = (long long)v.x - *centre, dy = (long long)v.y - *centre;
+            far = (uint32_t)min(max(llabs(dx), llabs(dy)), (long long)(1 << 24));
+            (q ? c1 : c0)[dst] = (H)(dx + bias);
+            (q ? c0 : c1)[dst] = (H)(dy + bias);
+        } else {
+            (q ? c1 : c0)[dst] = v.x;
+            (q ? c0 : c1)[dst] = v.y;
+        }
+    }
+    if constexpr (sizeof(H) == 2) {
+        far = __reduce_max_sync(0xffffffffu, far);
+        if ((threadIdx.x & 31u) == 0u && far) atomicMax(worst, far);
+    }
 }
 
-__global__ void k_merge(Geom g, int32_t* __restrict__ lex, const int32_t* __restrict__ c0,
-                        const int32_t* __restrict__ c1, const int32_t* __restrict__ offset) {
+template <typename H>
+__global__ void k_merge(Geom g, int32_t* __restrict__ lex, const H* __restrict__ c0, const H* __restrict__ c1,
+                        const int32_t* __restrict__ offset, const int32_t* __restrict__ centre, int32_t bias) {
     const uint32_t tl = blockIdx.y;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.plane) return;
     const uint32_t y = i / g.Xh;
     const uint32_t q = (y + g.t0 + tl) & 1u;
     const size_t src = (size_t)plane_self(g, tl) * g.plane + i;
-    const int32_t off = *offset;  // pending normalisation shift of this chain (see k_pick_shift)
+    // true height = stored - offset (pending normalisation shift of this chain, see k_pick_shift)
+    const int32_t off = *offset - (centre ? *centre - bias : 0);
     int2 v;
-    v.x = (q ? c1 : c0)[src] - off;
-    v.y = (q ? c0 : c1)[src] - off;
+    v.x = (int32_t)(q ? c1 : c0)[src] - off;
+    v.y = (int32_t)(q ? c0 : c1)[src] - off;
     reinterpret_cast<int2*>(lex)[(size_t)tl * g.plane + i] = v;
 }
 
-// Hot start (computation.rs:225-226): heights uniform in [-128,127], keyed by global index.
-// grid = (ceil(plane/bd), Tl, n_chains)
-__global__ void k_init_hot(Geom g, int32_t* __restrict__ c0_base, int32_t* __restrict__ c1_base,
-                           const ChainDev* __restrict__ chains) {
+// Hot start (computation.rs:225-226): heights uniform in [-128,127], keyed by global index; `bias` is added to what
+// is stored (the 16-bit arrays with centre 0).  grid = (ceil(plane/bd), Tl, n_chains)
+template <typename H>
+__global__ void k_init_hot(Geom g, H* __restrict__ c0_base, H* __restrict__ c1_base, const ChainDev* __restrict__ chains,
+                           int32_t bias) {
     const uint32_t chain = blockIdx.z, tl = blockIdx.y;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.plane) return;
@@ -247,11 +267,11 @@ __global__ void k_init_hot(Geom g, int32_t* __restrict__ c0_base, int32_t* __res
     const uint32_t q = (y + tg) & 1u;
     const uint64_t idx = 2 * ((uint64_t)tg * g.plane + i);  // global index of the even-x site
     const int v0 = hot_value(cd.k0, cd.k1, idx), v1 = hot_value(cd.k0, cd.k1, idx + 1);
-    int32_t* c0 = c0_base + (size_t)chain * g.chain_stride;
-    int32_t* c1 = c1_base + (size_t)chain * g.chain_stride;
+    H* c0 = c0_base + (size_t)chain * g.chain_stride;
+    H* c1 = c1_base + (size_t)chain * g.chain_stride;
     const size_t dst = (size_t)plane_self(g, tl) * g.plane + i;
-    (q ? c1 : c0)[dst] = v0;
-    (q ? c0 : c1)[dst] = v1;
+    (q ? c1 : c0)[dst] = (H)(v0 + bias);
+    (q ? c0 : c1)[dst] = (H)(v1 + bias);
 }
 
 // ---- normalize (fields.rs:616-633) ----------------------------------------------------------

@@ -204,7 +204,8 @@ struct lqft_handle {
     bool peer_same = false;                     // lo and hi are the same rank (world_size == 2)
     bool self_halo = false;                     // LQFT_FLAG_SELF_HALO: this rank is its own neighbour
     unsigned long long phase = 0;               // operations that touch ghost planes so far (same on every rank)
-    // 16-bit working copy of the field (kernels_narrow.cuh): live only inside lqft_run / lqft_sweep
+    // 16-bit copy of the field (kernels_narrow.cuh): the storage of admitted lattices, also between calls; the i32
+    // arrays are then allocated only if a field ever leaves the band (single GPU) or for the i32 halo path (slabs)
     uint16_t* narrow[2] = {nullptr, nullptr};
     int32_t* ncentre_d = nullptr;               // [n_chains] centre of the bias while a narrow segment runs
     uint32_t* nworst_d = nullptr;               // validity word of k_narrow
@@ -216,7 +217,9 @@ struct lqft_handle {
     bool capturing = false;                     // launches are being captured: flip numbers are relative to *phase_d
     unsigned long long phase_capture0 = 0;      // `phase` when the capture began
     uint32_t tl_lo = 0, tl_hi = 0;              // owned planes of the lower / upper neighbour
-    bool narrow_active = false;
+    bool narrow_active = false;                 // the live copy of the field is the 16-bit one (it stays so between calls)
+    uint32_t narrow_budget = 0;                 // sweeps the 16-bit copy may still take before it has to be re-measured
+    uint32_t narrow_retry = 0;                  // sweeps to stay on i32 before the band is tried again (after a refusal)
     uint64_t narrow_segments = 0;
 };
 
@@ -224,6 +227,9 @@ static lqft_status use_device(lqft_handle* h) {
     CU(cudaSetDevice(h->cfg.device));
     return LQFT_OK;
 }
+
+static lqft_status narrow_exit(lqft_handle* h);
+static lqft_status need_i32(lqft_handle* h);
 
 static lqft_status upload_params(lqft_handle* h) {
     if (!h->params_dirty) return LQFT_OK;
@@ -266,6 +272,7 @@ static lqft_status upload_params(lqft_handle* h) {
                       !h->narrow[0] || h->resident_ok || (h->g.ghost != 0 && !h->p2p)));
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
+    if (h->narrow_active && !h->narrowp.enabled) ST(narrow_exit(h));  // e.g. a coupling whose table the 16-bit kernel cannot hold
     if (getenv("LQFT_DEBUG"))
         fprintf(stderr, "[lqft] %ux%ux%u chains=%u path=%s (stream: segs=%d blocks/SM=%d chunks=%u; march: g=%d rows=%d)\n",
                 h->g.X, h->g.Y, h->g.T, nc, h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream" : (h->tiled.enabled ? "march" : "v1"),
@@ -526,6 +533,36 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
     return LQFT_OK;
 }
 
+// A field of zeros in the 16-bit arrays, centre 0, and these arrays the live copy.
+static lqft_status narrow_zero(lqft_handle* h) {
+    const uint32_t nc = h->cfg.n_chains;
+    for (int c = 0; c < 2; ++c)
+        k_n16_zero<<<1024, 256, 0, h->stream>>>((uint32_t*)h->narrow[c], h->gn.chain_stride * nc / 2);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(h->ncentre_d, 0, sizeof(int32_t) * nc, h->stream));
+    h->narrow_active = true;
+    h->narrow_budget = (uint32_t)kN16Bias - 1u;
+    h->nvalid = 0;
+    h->next_ready = false;
+    return LQFT_OK;
+}
+
+// The i32 arrays of the field (zero heights), allocated on first need.
+static lqft_status need_i32(lqft_handle* h) {
+    if (h->field[0]) return LQFT_OK;
+    const size_t fbytes = sizeof(int32_t) * h->g.chain_stride * h->cfg.n_chains;
+    for (int c = 0; c < 2; ++c) {
+        if (cudaMalloc(&h->field[c], fbytes) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(h->field[0]);
+            h->field[0] = h->field[1] = nullptr;
+            return fail(LQFT_ERR_NOMEM, "cannot allocate %zu bytes of device memory for the field", fbytes);
+        }
+        CU(cudaMemsetAsync(h->field[c], 0, fbytes, h->stream));
+    }
+    return LQFT_OK;
+}
+
 static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     h->cfg = *cfg;
     const uint32_t X = cfg->x, Y = cfg->y, T = cfg->t, ws = cfg->world_size ? cfg->world_size : 1;
@@ -584,14 +621,15 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     CU(cudaEventCreate(&h->ev_stop));
     CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
-    const size_t fbytes = (h->is64 ? sizeof(double) : sizeof(int32_t)) * g.chain_stride * nc;
-    for (int c = 0; c < 2; ++c) {
-        void** slot = h->is64 ? (void**)&h->field64[c] : (void**)&h->field[c];
-        if (cudaMalloc(slot, fbytes) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(LQFT_ERR_NOMEM, "cannot allocate %zu bytes of device memory for the field", fbytes);
+    if (h->is64) {
+        const size_t fbytes = sizeof(double) * g.chain_stride * nc;
+        for (int c = 0; c < 2; ++c) {
+            if (cudaMalloc(&h->field64[c], fbytes) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(LQFT_ERR_NOMEM, "cannot allocate %zu bytes of device memory for the field", fbytes);
+            }
+            CU(cudaMemsetAsync(h->field64[c], 0, fbytes, h->stream));
         }
-        CU(cudaMemsetAsync(*slot, 0, fbytes, h->stream));
     }
     if (h->is64) {
         CU(cudaMalloc(&h->beta_d, sizeof(double) * nc));
@@ -668,6 +706,10 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
             CU(cudaMalloc(&h->phase_d, sizeof(unsigned long long)));
         }
     }
+    // i32 arrays: always on slabs (their boundary planes are mapped by the neighbours for the i32 halo path); on one
+    // GPU only where the 16-bit copy cannot be the storage — otherwise need_i32 allocates them if a field ever
+    // leaves the band
+    if (!h->is64 && (g.ghost != 0 || !h->narrow[0])) ST(need_i32(h));
     if (ws > 1) {
         ST(nccl_load());
         ncclUniqueId id;
@@ -693,6 +735,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         h->p2p = true;
     }
     CU(tiled_prepare(h->tiled, g, nc, h->sm_count, h->is64 || (cfg->flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1)) != 0));
+    if (!h->is64 && !h->field[0]) ST(narrow_zero(h));  // the field of zeros lives in the 16-bit arrays from the start
     CU(cudaStreamSynchronize(h->stream));
     return LQFT_OK;
 }
@@ -1134,11 +1177,12 @@ static lqft_status launch_normalize(lqft_handle* h, uint64_t counter, const uint
 
 static lqft_status ready(lqft_handle* h) {
     if (!h) return fail(LQFT_ERR_INVALID, "null handle");
-    if (h->narrow_active)  // only possible after a device error in the middle of lqft_run: the i32 field is stale
-        return fail(LQFT_ERR_STATE, "an earlier call failed inside a narrow segment; the field is undefined, upload it again");
     ST(use_device(h));
     ST(upload_params(h));
-    ST(refresh_ghosts(h));
+    if (!h->narrow_active && !h->is64) {
+        ST(need_i32(h));
+        ST(refresh_ghosts(h));
+    }
     return LQFT_OK;
 }
 
@@ -1156,12 +1200,23 @@ extern "C" lqft_status lqft_init_hot(lqft_handle* h) {
     if (h->is64) {
         CU(cudaMemsetAsync(h->offset64_d, 0, sizeof(double) * h->cfg.n_chains, h->stream));
         k_init_hot_f64<<<grid, bd, 0, h->stream>>>(g, h->field64[0], h->field64[1], h->chains_d);
-    } else
-    k_init_hot<<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d);
+    } else if (h->narrowp.enabled) {
+        // straight into the 16-bit arrays: hot-start heights lie in [-128, 127], centre 0, no measurement needed
+        CU(cudaMemsetAsync(h->ncentre_d, 0, sizeof(int32_t) * h->cfg.n_chains, h->stream));
+        k_init_hot<uint16_t><<<grid, bd, 0, h->stream>>>(h->gn, h->narrow[0], h->narrow[1], h->chains_d, (int32_t)kN16Bias);
+        h->narrow_active = true;
+        h->narrow_budget = (uint32_t)kN16Bias - 1u - 128u;
+        h->nvalid = 0;
+        h->next_ready = false;
+        h->narrow_segments += 1;
+    } else {
+        ST(need_i32(h));
+        k_init_hot<int32_t><<<grid, bd, 0, h->stream>>>(g, h->field[0], h->field[1], h->chains_d, 0);
+        h->narrow_active = false;
+    }
     CU(cudaGetLastError());
     h->launches += 1;
     h->ghosts_valid = false;
-    h->narrow_active = false;
     return LQFT_OK;
 }
 
@@ -1191,13 +1246,46 @@ extern "C" lqft_status lqft_upload(lqft_handle* h, uint32_t chain, const void* v
         CU(cudaMemsetAsync(h->offset64_d + chain, 0, sizeof(double), h->stream));
         k_split_f64<<<grid, bd, 0, h->stream>>>(g, (const double*)h->staging_d, h->field64[0] + (size_t)chain * g.chain_stride,
                                                 h->field64[1] + (size_t)chain * g.chain_stride);
-    } else
-    k_split<<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
-                                        h->field[1] + (size_t)chain * g.chain_stride);
-    CU(cudaGetLastError());
-    h->launches += 1;
-    h->ghosts_valid = false;
-    h->narrow_active = false;  // (after a failed run: every chain has to be uploaded again, the caller's business)
+    } else {
+        bool to_i32 = !h->narrow_active;
+        if (h->narrow_active && g.ghost != 0) {
+            // slabs: measuring the band is a collective; an upload is not one.  Back to i32; the next run re-enters.
+            ST(narrow_exit(h));
+            to_i32 = true;
+        }
+        if (!to_i32) {
+            // straight into the 16-bit arrays around centre 0, if the chain fits the band
+            CU(cudaMemsetAsync(h->ncentre_d + chain, 0, sizeof(int32_t), h->stream));
+            CU(cudaMemsetAsync(h->nworst_d, 0, sizeof(uint32_t), h->stream));
+            k_split<uint16_t><<<grid, bd, 0, h->stream>>>(h->gn, h->staging_d, h->narrow[0] + (size_t)chain * h->gn.chain_stride,
+                                                         h->narrow[1] + (size_t)chain * h->gn.chain_stride, h->ncentre_d + chain,
+                                                         (int32_t)kN16Bias, h->nworst_d);
+            CU(cudaGetLastError());
+            h->launches += 1;
+            uint32_t worst = 0;
+            CU(cudaMemcpyAsync(&worst, h->nworst_d, sizeof worst, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            if (worst > (uint32_t)kN16Guard) {
+                ST(narrow_exit(h));  // every chain back to i32 (this one's 16-bit image is meaningless and is replaced below)
+                to_i32 = true;
+            } else {
+                h->narrow_budget = std::min(h->narrow_budget, (uint32_t)kN16Bias - 1u - worst);
+                h->narrow_segments += 1;
+            }
+        }
+        if (to_i32) {
+            ST(need_i32(h));
+            k_split<int32_t><<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
+                                                        h->field[1] + (size_t)chain * g.chain_stride, nullptr, 0, nullptr);
+            CU(cudaGetLastError());
+            h->launches += 1;
+            h->ghosts_valid = false;
+        }
+    }
+    if (h->is64) {
+        CU(cudaGetLastError());
+        h->launches += 1;
+    }
     CU(cudaStreamSynchronize(h->stream));  // the host buffer may be reused on return
     return LQFT_OK;
 }
@@ -1213,9 +1301,15 @@ extern "C" lqft_status lqft_download(lqft_handle* h, uint32_t chain, void* value
     if (h->is64)
         k_merge_f64<<<grid, bd, 0, h->stream>>>(g, (double*)h->staging_d, h->field64[0] + (size_t)chain * g.chain_stride,
                                                 h->field64[1] + (size_t)chain * g.chain_stride, h->offset64_d + chain);
-    else
-    k_merge<<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
-                                        h->field[1] + (size_t)chain * g.chain_stride, h->offset_d + chain);
+    else if (h->narrow_active)
+        k_merge<uint16_t><<<grid, bd, 0, h->stream>>>(h->gn, h->staging_d, h->narrow[0] + (size_t)chain * h->gn.chain_stride,
+                                                     h->narrow[1] + (size_t)chain * h->gn.chain_stride, h->offset_d + chain,
+                                                     h->ncentre_d + chain, (int32_t)kN16Bias);
+    else {
+        ST(need_i32(h));
+        k_merge<int32_t><<<grid, bd, 0, h->stream>>>(g, h->staging_d, h->field[0] + (size_t)chain * g.chain_stride,
+                                                    h->field[1] + (size_t)chain * g.chain_stride, h->offset_d + chain, nullptr, 0);
+    }
     CU(cudaGetLastError());
     h->launches += 1;
     CU(cudaMemcpyAsync(values, h->staging_d, (h->is64 ? sizeof(double) : sizeof(int32_t)) * h->n_slab, cudaMemcpyDeviceToHost, h->stream));
@@ -1363,7 +1457,10 @@ extern "C" lqft_status lqft_slice_moments(lqft_handle* h, uint32_t chain, int64_
     CU(cudaMemcpyAsync(mom.data(), h->mom_d + (size_t)chain * T * 2, sizeof(long long) * T * 2, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemsetAsync(h->mom_d + (size_t)chain * T * 2, 0, sizeof(long long) * T * 2, h->stream));  // moments are zero between uses
     CU(cudaMemcpyAsync(&off, h->offset_d + chain, sizeof off, cudaMemcpyDeviceToHost, h->stream));
+    int32_t centre = 0;
+    if (h->narrow_active) CU(cudaMemcpyAsync(&centre, h->ncentre_d + chain, sizeof centre, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->narrow_active) off -= centre - (int32_t)kN16Bias;  // 16-bit copy: stored = height - centre + bias
     if (h->g.ghost) ST(check_halo_error(h));
     // moments of the TRUE heights h = stored - off:  sum h = S1 - A off,  sum h^2 = S2 - 2 off S1 + A off^2
     const long long A = (long long)h->g.X * h->g.Y, o = off;
@@ -1483,14 +1580,32 @@ extern "C" lqft_status lqft_difference_read(lqft_handle* h, uint32_t chain, doub
 // ---------------------------------------------------------------------------------------------
 // narrow working copy (kernels_narrow.cuh)
 // ---------------------------------------------------------------------------------------------
-// i32 field -> u16 copy biased around each chain's normalisation offset; *ok = every height of every rank lies
-// within kN16Guard of its centre.  A ghost operation: the neighbours push into the narrow ghost planes next.
+// The 16-bit arrays are the storage of the field wherever they can be (also between calls); the i32 arrays take over
+// only while some height lies outside the band.  Bookkeeping: a sweep moves a height by at most one, so after a
+// conversion that measured `worst` = max |height - centre| the copy is good for kN16Bias - 1 - worst sweeps
+// (narrow_budget) without anyone looking at it; when they are used up the band is measured again (narrow_recheck) —
+// the only host synchronisation of the update path, once per > 1000 sweeps.
+static lqft_status allreduce_max_u32(lqft_handle* h, void* buf, size_t n) {
+    if (h->cfg.world_size <= 1) return LQFT_OK;
+    NC(g_nccl.AllReduce(buf, buf, n, ncclUint32, ncclMax, h->comm, h->stream));
+    return LQFT_OK;
+}
+
+static lqft_status read_worst(lqft_handle* h, uint32_t* worst) {
+    ST(allreduce_max_u32(h, h->nworst_d, 1));
+    CU(cudaMemcpyAsync(worst, h->nworst_d, sizeof *worst, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LQFT_OK;
+}
+
+// i32 field -> 16-bit copy biased around each chain's normalisation offset; *ok = every height of every rank lies
+// within kN16Guard of its centre.
 static lqft_status narrow_enter(lqft_handle* h, bool* ok) {
     const Geom& g = h->g;
     const uint32_t nc = h->cfg.n_chains;
     *ok = false;
     k_narrow_begin<<<(nc + 127) / 128, 128, 0, h->stream>>>(h->offset_d, h->ncentre_d, nc, h->nworst_d);
-    const uint64_t count = (uint64_t)g.Tl * g.plane;  // owned planes; ghost planes are filled by the first exchange
+    const uint64_t count = (uint64_t)g.Tl * g.plane;  // owned planes; ghost planes are filled by the first period
     dim3 grid((uint32_t)((count / 4 + 255) / 256), nc);
     for (int c = 0; c < 2; ++c)
         k_narrow<<<grid, 256, 0, h->stream>>>(h->field[c] + (size_t)g.ghost * g.plane, g.chain_stride,
@@ -1498,20 +1613,25 @@ static lqft_status narrow_enter(lqft_handle* h, bool* ok) {
                                               h->ncentre_d, h->nworst_d);
     CU(cudaGetLastError());
     h->launches += 3;
-    ST(allreduce_i32(h, h->nworst_d, 1));  // k_narrow caps the word at 2^24: the sum over ranks cannot wrap
     uint32_t worst = 0;
-    CU(cudaMemcpyAsync(&worst, h->nworst_d, sizeof worst, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    *ok = worst == 0;
+    ST(read_worst(h, &worst));
+    *ok = worst <= (uint32_t)kN16Guard;
     h->narrow_active = *ok;
     h->nvalid = 0;            // neither ghost set holds anything yet: the first half-sweep fills and flips
     h->next_ready = false;
-    if (*ok) h->narrow_segments += 1;
+    if (*ok) {
+        h->narrow_budget = (uint32_t)kN16Bias - 1u - worst;
+        h->narrow_segments += 1;
+    } else {
+        h->narrow_retry = kN16Segment;
+    }
     return LQFT_OK;
 }
 
+// 16-bit copy -> i32 arrays, which become the live copy.
 static lqft_status narrow_exit(lqft_handle* h) {
     const Geom& g = h->g;
+    ST(need_i32(h));
     const uint64_t count = (uint64_t)g.Tl * g.plane;
     dim3 grid((uint32_t)((count / 4 + 255) / 256), h->cfg.n_chains);
     for (int c = 0; c < 2; ++c)
@@ -1521,6 +1641,38 @@ static lqft_status narrow_exit(lqft_handle* h) {
     h->launches += 2;
     h->narrow_active = false;
     if (g.ghost) h->ghosts_valid = false;  // the i32 ghost planes were not maintained meanwhile
+    return LQFT_OK;
+}
+
+// The budget is used up: measure the heights against the chains' current offsets; within the guard band they are
+// re-centred there in place and the copy lives on, otherwise the field moves to the i32 arrays.
+static lqft_status narrow_recheck(lqft_handle* h) {
+    const Geom& g = h->g;
+    const uint32_t nc = h->cfg.n_chains;
+    const uint64_t count = (uint64_t)g.Tl * g.plane;
+    dim3 grid((uint32_t)((count / 4 + 255) / 256), nc);
+    CU(cudaMemsetAsync(h->nworst_d, 0, sizeof(uint32_t), h->stream));
+    for (int c = 0; c < 2; ++c)
+        k_n16_worst<<<grid, 256, 0, h->stream>>>(h->narrow[c] + (size_t)h->gn.ghost * g.plane, h->gn.chain_stride, count,
+                                                 h->ncentre_d, h->offset_d, h->nworst_d);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    uint32_t worst = 0;
+    ST(read_worst(h, &worst));
+    if (worst > (uint32_t)kN16Guard) {
+        h->narrow_retry = kN16Segment;
+        return narrow_exit(h);
+    }
+    for (int c = 0; c < 2; ++c)
+        k_n16_rebias<<<grid, 256, 0, h->stream>>>(h->narrow[c] + (size_t)h->gn.ghost * g.plane, h->gn.chain_stride, count,
+                                                  h->ncentre_d, h->offset_d);
+    k_narrow_begin<<<(nc + 127) / 128, 128, 0, h->stream>>>(h->offset_d, h->ncentre_d, nc, h->nworst_d);
+    CU(cudaGetLastError());
+    h->launches += 3;
+    h->narrow_budget = (uint32_t)kN16Bias - 1u - worst;
+    h->nvalid = 0;  // the ghost planes were not moved along: fill and flip
+    h->next_ready = false;
+    h->narrow_segments += 1;
     return LQFT_OK;
 }
 
@@ -1715,19 +1867,23 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_r
         h->launches += 1;
         step = end;
     }
-    // Steps left for the update kernels.  With a narrow plan they run in segments of at most kN16Segment sweeps
-    // on the 16-bit working copy, each entered only if the field is within the guard band (else this call
-    // finishes on the i32 kernels).
-    bool narrow = h->narrowp.enabled && end - step >= 4;
+    // Steps left for the update kernels.  Where the 16-bit arrays are admitted they are (or become) the live copy;
+    // a segment lasts as long as their budget does, then the band is measured again.  Outside the band the call
+    // goes on with the i32 kernels.
     while (step < end) {
         uint64_t seg_end = end;
-        if (narrow) {
+        if (h->narrowp.enabled && !h->narrow_active && h->narrow_retry == 0) {
             bool ok = false;
             ST(narrow_enter(h, &ok));
-            if (ok) seg_end = std::min<uint64_t>(end, step + kN16Segment);
-            else narrow = false;
         }
-        if (!h->narrow_active) ST(refresh_ghosts(h));  // a narrow segment leaves the i32 ghost planes stale
+        if (h->narrow_active && h->narrow_budget == 0) ST(narrow_recheck(h));
+        if (h->narrow_active) {
+            seg_end = std::min<uint64_t>(end, step + h->narrow_budget);
+        } else {
+            if (h->narrowp.enabled) seg_end = std::min<uint64_t>(end, step + h->narrow_retry);
+            ST(refresh_ghosts(h));  // leaving the 16-bit copy leaves the i32 ghost planes stale
+        }
+        const uint64_t seg_begin = step;
         // slabs replay graphs only on the narrow copy: the numbers of its flips live in device memory
         const bool use_graph = graph_ok && (h->g.ghost == 0 || h->narrow_active);
         const bool deep = h->narrow_active && h->gn.ghost != 0;
@@ -1805,7 +1961,8 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_r
             ST(launch_step(h, s, step, step, nullptr));
             ++step;
         }
-        if (h->narrow_active) ST(narrow_exit(h));
+        if (h->narrow_active) h->narrow_budget -= (uint32_t)(step - seg_begin);
+        else if (h->narrowp.enabled) h->narrow_retry -= (uint32_t)std::min<uint64_t>(h->narrow_retry, step - seg_begin);
     }
     CU(cudaEventRecord(h->ev_stop, h->stream));
     h->timed = true;
@@ -1907,8 +2064,10 @@ extern "C" lqft_status lqft_plan_info(lqft_handle* h, char* buf, size_t cap) {
         groups = narrow_groups(h->narrowp, h->g.Tl);
         occ = narrow_occupancy(h->narrowp, h->any_wilson, false, false, narrow_warps(h->narrowp, h->g.Tl));
     }
-    snprintf(buf, cap, "path=%s chunks=%u rows_per_chunk=%u plane_blocks=%u blocks_per_sm=%d ghost_depth=%u p2p=%d", path, chunks, rows,
-             groups, occ, h->narrowp.enabled ? h->gn.ghost : h->g.ghost, h->p2p ? 1 : 0);
+    snprintf(buf, cap, "path=%s chunks=%u rows_per_chunk=%u plane_blocks=%u blocks_per_sm=%d ghost_depth=%u p2p=%d storage=%s "
+             "i32_allocated=%d budget=%u", path, chunks, rows, groups, occ, h->narrowp.enabled ? h->gn.ghost : h->g.ghost,
+             h->p2p ? 1 : 0, h->is64 ? "f64" : h->narrow_active ? "u16" : "i32", h->field[0] ? 1 : 0,
+             h->narrow_active ? h->narrow_budget : 0u);
     return LQFT_OK;
 }
 

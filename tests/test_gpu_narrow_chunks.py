@@ -53,7 +53,7 @@ def test_narrow_rows_per_chunk_ge_3_vs_oracle(size, wilson, chunks, monkeypatch)
             got, acc, e = _engine_trajectory(eng, v0, beta, seed, wilson)
             plan = eng.plan_info()
             assert plan["path"] == "narrow" and plan["chunks"] == chunks and plan["rows_per_chunk"] >= 3, plan
-            assert eng.narrow_segments() == 3
+            assert eng.narrow_segments() == 1 and plan["storage"] == "u16" and plan["i32_allocated"] == 0, plan
         assert acc == wacc
         assert (e == we).all()
         assert (got == want).all(), f"{int((got != want).sum())} sites differ (chunks={chunks}, flags={flags})"
@@ -92,7 +92,7 @@ def test_narrow_natural_chunking_rows_per_chunk_ge_3_vs_scalar_kernel(size, min_
             plan = eng.plan_info()
             if flags == 0:
                 assert plan["path"] == "narrow" and plan["rows_per_chunk"] >= min_rows, plan
-                assert eng.narrow_segments() == 3
+                assert eng.narrow_segments() == 1 and plan["storage"] == "u16" and plan["i32_allocated"] == 0, plan
             else:
                 assert plan["path"] == "generic", plan
     assert out[0][1] == out[1][1]
@@ -144,7 +144,7 @@ def test_narrow_rows_shorter_than_a_warp_vs_oracle(size, wilson, chunks, monkeyp
             got, acc, e = _engine_trajectory(eng, v0, beta, seed, wilson)
             plan = eng.plan_info()
             assert plan["path"] == "narrow", plan
-            assert eng.narrow_segments() == 3
+            assert eng.narrow_segments() == 1 and plan["storage"] == "u16" and plan["i32_allocated"] == 0, plan
         assert acc == wacc
         assert (e == we).all()
         assert (got == want).all(), f"{int((got != want).sum())} sites differ (chunks={chunks}, flags={flags})"
@@ -170,8 +170,41 @@ def test_narrow_64cubed_many_chains_match_single_chain_runs():
             eng.upload(c, v0[c])
         acc = eng.sweep(0, 6, want_accepted=True)
         e, _, _ = eng.run(20, sweep_base=6, energy_every=5, normalize_every=10)
-        assert eng.plan_info()["path"] == "narrow" and eng.narrow_segments() == 2
+        assert eng.plan_info()["path"] == "narrow" and eng.narrow_segments() == 5 and eng.plan_info()["storage"] == "u16"
         for c in range(5):
             assert acc[c] == single[c][0]
             assert (e[c] == single[c][1]).all()
             assert (eng.download(c) == single[c][2]).all()
+
+
+def test_one_sweep_per_call_and_standalone_observables_stay_on_the_16_bit_arrays():
+    """The Algorithm::field_sweep drop-in: one sweep per lqft_sweep call, with every standalone operation in between
+    (energy, action, normalize at a site, slice moments, correlator, shift, download) served from the 16-bit arrays —
+    no i32 arrays are ever allocated, and everything equals the oracle."""
+    X, Y, T = 64, 12, 6
+    beta, seed = 0.27, 0x51E
+    lat = O.Lattice([X, Y, T])
+    v0 = seeded_field(X * Y * T, seed=99)
+    want = v0.copy()
+    sites = [int(O.pick_site(seed, 4, 3, r, lat.n_sites)) for r in range(6)]
+    with Engine(X, Y, T, flags=NORES) as eng:
+        eng.set_chain(0, beta, seed)
+        eng.upload(0, v0)
+        for s in range(7):
+            acc = eng.sweep(s, 1, want_accepted=True)[0]
+            assert acc == O.sweep(lat, want, beta, seed, s, order=1)
+            assert int(eng.energy()[0][0]) == O.integer_energy(lat, want)[0]
+            assert float(eng.action()[0][0]) == O.float_action(lat, want)
+            if s == 2:
+                eng.normalize_site(0, 1234)
+                O.shift_values(want, int(want[1234]))
+            if s == 4:
+                eng.shift_values(0, -7)
+                O.shift_values(want, -7)
+            s1, s2 = eng.slice_moments(0)
+            f = want.reshape(T, Y * X).astype(np.int64)
+            assert (s1 == f.sum(axis=1)).all() and (s2 == (f * f).sum(axis=1)).all()
+            assert (eng.correlator(0, ref_sites=sites) == O.correlator(lat, want, sites)).all()
+            assert (eng.download(0) == want).all(), s
+        plan = eng.plan_info()
+        assert plan["path"] == "narrow" and plan["storage"] == "u16" and plan["i32_allocated"] == 0, plan

@@ -127,28 +127,37 @@ def test_narrow_working_copy_bit_exact_vs_oracle(size, beta, wilson):
             eng.sweep(15, 6)
             e_obs, _, _ = eng.run(24, sweep_base=21, energy_every=4, normalize_every=10)
             got = eng.download(0)
-            segs = eng.narrow_segments()
+            segs, plan = eng.narrow_segments(), eng.plan_info()
         assert acc == wacc, flags
         assert (e_obs[0] == we).all(), flags
         assert (got == want).all(), f"{int((got != want).sum())} sites differ (flags={flags})"
-        assert segs == (0 if flags & _lib.FLAG_NO_NARROW else 3), (flags, segs)
+        # the 16-bit arrays are the storage from the upload on: one conversion, no i32 arrays at all
+        if flags & _lib.FLAG_NO_NARROW:
+            assert segs == 0 and plan["storage"] == "i32", (flags, segs, plan)
+        else:
+            assert segs == 1 and plan["storage"] == "u16" and plan["i32_allocated"] == 0, (flags, segs, plan)
 
 
-def test_narrow_segments_and_guard_band():
-    """More than kN16Segment sweeps in one call are split into re-validated segments; a field outside the guard
-    band around the normalisation offset stays on the i32 kernels.  Same trajectory either way."""
+def test_narrow_budget_recentring_and_guard_band():
+    """The 16-bit arrays store the field between calls.  A conversion that measured `worst` is good for 2047 - worst
+    sweeps; then the heights are measured against the chain's current offset and re-centred in place.  A field outside
+    the guard band lives in the i32 arrays.  Same trajectory either way."""
     X, Y, T = 256, 2, 2
     beta, seed = 0.3, 77
     lat = O.Lattice([X, Y, T])
     v0 = seeded_field(X * Y * T, seed=5)
     want = v0.copy()
-    we, _ = O.run(lat, want, beta, seed, 0, 0, 1100, 100, 10, order=1)
+    we, _ = O.run(lat, want, beta, seed, 0, 0, 2500, 100, 10, order=1)
     with Engine(X, Y, T, flags=_lib.FLAG_NO_RESIDENT) as eng:
         eng.set_chain(0, beta, seed)
         eng.upload(0, v0)
-        e_obs, _, _ = eng.run(1100, energy_every=100, normalize_every=10)
+        budget0 = eng.plan_info()["budget"]
+        assert 1900 <= budget0 <= 2047
+        e_obs, _, _ = eng.run(2500, energy_every=100, normalize_every=10)
         got = eng.download(0)
-        assert eng.narrow_segments() == 2
+        plan = eng.plan_info()
+        assert eng.narrow_segments() == 2 and plan["storage"] == "u16" and plan["i32_allocated"] == 0, plan
+        assert plan["budget"] > 1024
     assert (e_obs[0] == we).all() and (got == want).all()
     far = v0.copy()
     far[::7] += 5000
@@ -160,8 +169,41 @@ def test_narrow_segments_and_guard_band():
         eng.upload(0, far)
         eng.sweep(0, 6)
         got = eng.download(0)
-        assert eng.narrow_segments() == 0
+        plan = eng.plan_info()
+        assert eng.narrow_segments() == 0 and plan["storage"] == "i32" and plan["i32_allocated"] == 1, plan
     assert (got == want).all()
+
+
+def test_leaving_the_band_mid_call_falls_back_to_i32_bit_exactly():
+    """The band is measured around the chain's normalisation offset.  A shift of 5000 moves the offset away from the
+    heights; the running sweep budget stays valid (nothing was rewritten), but when it runs out in the middle of the
+    next call the re-measurement fails and the call finishes on the i32 arrays — same results as the oracle.  After
+    the shift is taken back, the retry interval (1000 sweeps) brings the field into the 16-bit arrays again."""
+    X, Y, T = 256, 4, 8
+    beta, seed = 0.3, 4242
+    lat = O.Lattice([X, Y, T])
+    v0 = seeded_field(X * Y * T, seed=9, lo=-2, hi=3)
+    want = v0.copy()
+    with Engine(X, Y, T, flags=_lib.FLAG_NO_RESIDENT) as eng:
+        eng.set_chain(0, beta, seed)
+        eng.upload(0, v0)
+        budget = eng.plan_info()["budget"]
+        assert eng.plan_info()["storage"] == "u16" and 2040 <= budget <= 2047
+        eng.shift_values(0, 5000)
+        O.shift_values(want, 5000)
+        e_obs, _, _ = eng.run(2200, energy_every=100, normalize_every=0)   # a normalize would pull the offset back
+        we, _ = O.run(lat, want, beta, seed, 0, 0, 2200, 100, 0, order=1)
+        got = eng.download(0)
+        plan = eng.plan_info()
+        assert plan["storage"] == "i32" and plan["i32_allocated"] == 1, plan
+        assert (e_obs[0] == we).all() and (got == want).all()
+        eng.shift_values(0, -5000)
+        O.shift_values(want, -5000)
+        eng.sweep(2200, 1100)
+        for s in range(2200, 3300):
+            O.sweep(lat, want, beta, seed, s, order=1)
+        assert eng.plan_info()["storage"] == "u16"
+        assert (eng.download(0) == want).all()
 
 
 def test_narrow_many_chains_match_single_chain_runs():
@@ -180,7 +222,7 @@ def test_narrow_many_chains_match_single_chain_runs():
             eng.set_chain(c, betas[c], 900 + c, 17 * c, c)
             eng.upload(c, v0[c])
         e, _, _ = eng.run(20, energy_every=5, normalize_every=10)
-        assert eng.narrow_segments() == 1
+        assert eng.narrow_segments() == 3 and eng.plan_info()["storage"] == "u16"   # one conversion per uploaded chain
         for c in range(3):
             assert (e[c] == single[c][0]).all()
             assert (eng.download(c) == single[c][1]).all()
@@ -211,7 +253,9 @@ def test_self_halo_slab_path_on_one_gpu(size, wilson):
         e_int = int(eng.energy()[0][0])
         s_int = int(eng.action()[0][0])
         eng.synchronize()
-        assert eng.narrow_segments() == (2 if X in (16, 32, 64, 128, 256, 512, 1024) else 0)
+        # slabs: the upload goes to the i32 arrays, the first sweep call takes the field into the 16-bit ones for good
+        assert eng.narrow_segments() == (1 if X in (16, 32, 64, 128, 256, 512, 1024) else 0)
+        assert eng.plan_info()["storage"] == ("u16" if X in (16, 32, 64, 128, 256, 512, 1024) else "i32")
         # a schedule short-cycled enough for graph replay (on slabs: narrow copy only, exchanges inside the graph)
         want3 = want.copy()
         we3, _ = O.run(lat, want3, beta, seed, 16, 0, 40, 2, 4, order=1, wilson=wil)
@@ -249,7 +293,7 @@ def test_self_halo_other_ghost_depths(size, depth, monkeypatch):
         acc = eng.sweep(0, 7, want_accepted=True)[0]
         e_obs, _, _ = eng.run(30, sweep_base=7, energy_every=3, normalize_every=10)
         got = eng.download(0)
-        assert eng.narrow_segments() == 2
+        assert eng.narrow_segments() == 1 and eng.plan_info()["storage"] == "u16"
         eng.synchronize()
     assert acc == wacc and (e_obs[0] == we).all()
     assert (got == want).all(), f"{int((got != want).sum())} sites differ (depth {depth})"
@@ -275,7 +319,7 @@ def test_self_halo_many_chains_deep_halo():
             eng.upload(c, v0[c])
         acc = eng.sweep(0, 6, want_accepted=True)
         e, _, _ = eng.run(20, sweep_base=6, energy_every=5, normalize_every=10)
-        assert eng.narrow_segments() == 2
+        assert eng.narrow_segments() == 1 and eng.plan_info()["storage"] == "u16"
         for c in range(3):
             assert acc[c] == single[c][0]
             assert (e[c] == single[c][1]).all()
