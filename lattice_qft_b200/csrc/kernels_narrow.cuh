@@ -247,7 +247,9 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         const uint32_t grp_base = tg * g.Y * (2u * ROWQ) + kq * 2u;
         const bool wil_plane = WILSON && tg < cd.wil_h;
         const uint32_t y_one = 1u % g.Y;
-        uint32_t n = y1 - y0;
+        // a warp without a live plane slot leaves after one row (the vote keeps the trip count warp uniform for the
+        // compiler; an outright early exit costs the uniform registers, see above)
+        uint32_t n = __all_sync(0xffffffffu, pl_raw >= n_planes) ? 1u : y1 - y0;
 #define LQFT_N16_STEP(OM, OC, ON, PUSH)                                                                                     \
     {                                                                                                                    \
         const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;                                                                  \
