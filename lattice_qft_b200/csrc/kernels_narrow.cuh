@@ -63,19 +63,12 @@ __device__ __forceinline__ int build_interleaved(uint2* s_tab, const uint32_t* _
 
 __shared__ uint2 s_n16_tab[2 * (2 * kN16KcMax + 1)];
 
-// Sums and decisions of one row of 8 sites per thread.  P = x parity of the row's sites (warp uniform).
-template <int P, bool WILSON, bool COUNT>
-__device__ __forceinline__ uint4 n16_row_update(const uint4 v, const uint4 om, const uint4 oc, const uint4 on, const uint4 to,
-                                                const uint4 ti, const uint32_t edge, const u32x4 r0, const u32x4 r1,
+// Sums and decisions of one row of 8 sites per thread.  sh = the other x neighbour of site j (position j+1 or j-1 of
+// the other colour's row, by the row's x parity).
+template <bool WILSON, bool COUNT>
+__device__ __forceinline__ uint4 n16_row_decide(const uint4 v, const uint4 om, const uint4 oc, const uint4 on, const uint4 to,
+                                                const uint4 ti, const uint4 sh, const u32x4 r0, const u32x4 r1,
                                                 const uint32_t c_off, const uint32_t c_max, const uint4 woff, int& accepted) {
-    uint4 sh;  // the other x neighbour of site j: position j+1 (P) or j-1 (!P)
-    if (P) {
-        sh.x = __byte_perm(oc.x, oc.y, 0x5432); sh.y = __byte_perm(oc.y, oc.z, 0x5432);
-        sh.z = __byte_perm(oc.z, oc.w, 0x5432); sh.w = __byte_perm(oc.w, edge, 0x5432);
-    } else {
-        sh.x = __byte_perm(edge, oc.x, 0x5432); sh.y = __byte_perm(oc.x, oc.y, 0x5432);
-        sh.z = __byte_perm(oc.y, oc.z, 0x5432); sh.w = __byte_perm(oc.z, oc.w, 0x5432);
-    }
     constexpr uint32_t C = 0x60006000u;
     uint4 w;
 #define LQFT_N16_PAIR(F, RA, RB)                                                                      \
@@ -96,6 +89,22 @@ __device__ __forceinline__ uint4 n16_row_update(const uint4 v, const uint4 om, c
     LQFT_N16_PAIR(w, r1.z, r1.w)
 #undef LQFT_N16_PAIR
     return w;
+}
+
+// The same with the x parity P of the row's sites known at compile time (warp uniform in k_sweep_n16).
+template <int P, bool WILSON, bool COUNT>
+__device__ __forceinline__ uint4 n16_row_update(const uint4 v, const uint4 om, const uint4 oc, const uint4 on, const uint4 to,
+                                                const uint4 ti, const uint32_t edge, const u32x4 r0, const u32x4 r1,
+                                                const uint32_t c_off, const uint32_t c_max, const uint4 woff, int& accepted) {
+    uint4 sh;
+    if (P) {
+        sh.x = __byte_perm(oc.x, oc.y, 0x5432); sh.y = __byte_perm(oc.y, oc.z, 0x5432);
+        sh.z = __byte_perm(oc.z, oc.w, 0x5432); sh.w = __byte_perm(oc.w, edge, 0x5432);
+    } else {
+        sh.x = __byte_perm(edge, oc.x, 0x5432); sh.y = __byte_perm(oc.x, oc.y, 0x5432);
+        sh.z = __byte_perm(oc.y, oc.z, 0x5432); sh.w = __byte_perm(oc.z, oc.w, 0x5432);
+    }
+    return n16_row_decide<WILSON, COUNT>(v, om, oc, on, to, ti, sh, r0, r1, c_off, c_max, woff, accepted);
 }
 
 // Packed Wilson offsets of the 8 sites x = 2 (k0 + j) + p of a row next to the sheet (spec.cuh, wilson_offset).
@@ -575,7 +584,9 @@ inline uint32_t narrow_chunks(NarrowPlan& p, const Geom& g, uint32_t n_planes, u
     for (uint32_t nc = 1; nc <= max_chunks; ++nc) {
         const uint64_t blocks = base * nc;
         const uint64_t waves = (blocks + slots - 1) / slots;
-        const double rows = (double)((g.Y + nc - 1) / nc);
+        // an SM is throughput bound over its resident warps rather than waiting for the slowest one: chunks of 7 and 8
+        // rows cost about their mean, the longest one counts only half
+        const double rows = 0.5 * ((double)g.Y / nc + (double)((g.Y + nc - 1) / nc));
         const double cost = (double)waves * (rows + 2.0);
         if (cost < best_cost - 1e-9) {
             best_cost = cost;

@@ -148,10 +148,13 @@ k_observe_rows(const Geom g, const H* __restrict__ c0_base, const H* __restrict_
     const H* c1 = c1_base + (size_t)chain * g.chain_stride;
     const size_t ps = (size_t)plane_self(g, tl) * g.plane, pa = (size_t)plane_above(g, tl) * g.plane;
     long long q[4] = {0, 0, 0, 0};
-    // differences in i32 like the reference (fields.rs:728-737: `value - neighbour` in T), squares and sums in i64
-    // (one IMAD.WIDE with a 64-bit addend per term)
-    using W = long long;
-    auto sq = [](int u, int v) { const int d = u - v; return (long long)d * (long long)d; };
+    // differences in i32 like the reference (fields.rs:728-737: `value - neighbour` in T).  i32 storage: squares and
+    // sums in i64 (one IMAD.WIDE with a 64-bit addend per term).  16-bit storage: heights lie in [0, 4096), a square
+    // is below 2^24 and the 24 terms of one iteration stay below 2^31, so they are summed in 32 bits (one IMAD per
+    // term) and only the iteration's totals are widened.
+    constexpr bool NARROW = sizeof(H) == 2;
+    using W = typename std::conditional<NARROW, int, long long>::type;
+    auto sq = [](int u, int v) { const int d = u - v; return (W)d * (W)d; };
     for (uint32_t i = threadIdx.x; i < (y1 - y0) * Qx; i += blockDim.x) {
         const uint32_t yy = i / Qx, y = y0 + yy, k0 = (i - yy * Qx) << 2;
         const uint32_t p0 = (y + tg) & 1u;  // x parity of the colour-0 sites of this row

@@ -60,11 +60,12 @@ __device__ __forceinline__ u32x4 philox4x32_rk(uint32_t c0, uint32_t c1, uint32_
                                                const RoundKeys& rk) {
 #pragma unroll
     for (int r = 0; r < kPhiloxRounds; ++r) {
-        const uint32_t lo0 = kPhiloxM0 * c0, hi0 = __umulhi(kPhiloxM0, c0);
-        const uint32_t lo1 = kPhiloxM1 * c2, hi1 = __umulhi(kPhiloxM1, c2);
-        const uint32_t n0 = hi1 ^ c1 ^ rk.k[r][0];
-        const uint32_t n2 = hi0 ^ c3 ^ rk.k[r][1];
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        // one 32 x 32 -> 64 multiply per product (IMAD.WIDE); written as separate low / high halves the compiler
+        // splits them into IMAD + IMAD.HI when registers are tight
+        const unsigned long long p0 = (unsigned long long)kPhiloxM0 * c0, p1 = (unsigned long long)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk.k[r][0];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk.k[r][1];
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
     }
     return u32x4{c0, c1, c2, c3};
 }

@@ -404,54 +404,6 @@ __device__ __forceinline__ int4 load_h4(const uint16_t* p) {
     return make_int4((int)(v.x & 0xffffu), (int)(v.x >> 16), (int)(v.y & 0xffffu), (int)(v.y >> 16));
 }
 
-template <typename H>
-__global__ void __launch_bounds__(256)
-k_observe_vec4(Geom g, const H* __restrict__ c0_base, const H* __restrict__ c1_base,
-               unsigned long long* __restrict__ obs, unsigned long long* __restrict__ mom) {
-    const uint32_t chain = blockIdx.z, tl = blockIdx.y;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    long long q[4] = {0, 0, 0, 0};
-    const uint32_t tg = g.t0 + tl;
-    const uint32_t Qx = g.Xh >> 2;
-    if (i < (g.plane >> 2)) {
-        const H* c0 = c0_base + (size_t)chain * g.chain_stride;
-        const H* c1 = c1_base + (size_t)chain * g.chain_stride;
-        const uint32_t y = i / Qx, k0 = (i - y * Qx) << 2;
-        const uint32_t p0 = (y + tg) & 1u;  // x parity of the colour-0 sites of this row
-        const size_t ps = (size_t)plane_self(g, tl) * g.plane;
-        const size_t row = ps + (size_t)y * g.Xh;
-        const uint32_t yp = (y + 1 == g.Y) ? 0 : y + 1;
-        const uint32_t kn = (k0 + 4 == g.Xh) ? 0 : k0 + 4;
-        const size_t up = (size_t)plane_above(g, tl) * g.plane + (size_t)y * g.Xh + k0;
-        const size_t yr = ps + (size_t)yp * g.Xh + k0;
-        const int4 a = load_h4(c0 + row + k0);
-        const int4 b = load_h4(c1 + row + k0);
-        const int4 ay = load_h4(c1 + yr), by = load_h4(c0 + yr);
-        const int4 at = load_h4(c1 + up), bt = load_h4(c0 + up);
-        // +x neighbour: the odd-x colour looks one position to the right in the other colour's row
-        const int e = (int)(p0 ? c1 : c0)[row + kn];
-        const int4 ax = p0 ? make_int4(b.y, b.z, b.w, e) : b;
-        const int4 bx = p0 ? a : make_int4(a.y, a.z, a.w, e);
-        auto sq = [](int u, int v) { const long long d = (long long)u - (long long)v; return d * d; };
-        const long long dx = sq(a.x, ax.x) + sq(a.y, ax.y) + sq(a.z, ax.z) + sq(a.w, ax.w) +
-                             sq(b.x, bx.x) + sq(b.y, bx.y) + sq(b.z, bx.z) + sq(b.w, bx.w);
-        const long long dy = sq(a.x, ay.x) + sq(a.y, ay.y) + sq(a.z, ay.z) + sq(a.w, ay.w) +
-                             sq(b.x, by.x) + sq(b.y, by.y) + sq(b.z, by.z) + sq(b.w, by.w);
-        const long long dt = sq(a.x, at.x) + sq(a.y, at.y) + sq(a.z, at.z) + sq(a.w, at.w) +
-                             sq(b.x, bt.x) + sq(b.y, bt.y) + sq(b.z, bt.z) + sq(b.w, bt.w);
-        q[0] = dx + dy - dt;
-        q[1] = dx + dy + dt;
-        if (mom) {
-            q[2] = (long long)a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
-            q[3] = sq(a.x, 0) + sq(a.y, 0) + sq(a.z, 0) + sq(a.w, 0) + sq(b.x, 0) + sq(b.y, 0) + sq(b.z, 0) + sq(b.w, 0);
-        }
-    }
-    unsigned long long* const dst[4] = {
-        obs + (size_t)chain * 2, obs + (size_t)chain * 2 + 1,
-        mom ? mom + ((size_t)chain * g.T + tg) * 2 : nullptr,
-        mom ? mom + ((size_t)chain * g.T + tg) * 2 + 1 : nullptr};
-    block_sum_flush<4>(q, dst);
-}
 
 // Append the accumulated energy of every chain to its log and clear the accumulators.
 // log[chain * cap + *n_meas] = E ; one thread per chain; thread 0 bumps *n_meas afterwards.

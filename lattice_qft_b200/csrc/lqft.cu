@@ -23,6 +23,7 @@
 #include "kernels_resident.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_narrow.cuh"
+#include "kernels_cluster.cuh"
 #include "kernels_observe.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_v1.cuh"
@@ -210,6 +211,7 @@ struct lqft_handle {
     int32_t* ncentre_d = nullptr;               // [n_chains] centre of the bias while a narrow segment runs
     uint32_t* nworst_d = nullptr;               // validity word of k_narrow
     NarrowPlan narrowp{};
+    ClusterPlan clusterp{};                     // chains resident in the shared memory of a cluster (kernels_cluster.cuh)
     Geom gn{};                                  // geometry of the narrow arrays: slabs carry a deep halo (ghost > 1)
     uint32_t nvalid = 0;                        // ghost planes per side of the narrow copy that are valid right now
     unsigned long long* phase_d = nullptr;      // device copy of `phase` at the start of a graph replay (slabs, narrow copy)
@@ -270,6 +272,8 @@ static lqft_status upload_params(lqft_handle* h) {
     }
     CU(narrow_prepare(h->narrowp, h->g, nc, h->sm_count, h->max_thr,
                       !h->narrow[0] || h->resident_ok || (h->g.ghost != 0 && !h->p2p)));
+    CU(cluster_prepare(h->clusterp, h->g, nc, h->sm_count, h->max_thr, h->smem_optin,
+                       !h->narrowp.enabled || (h->cfg.flags & LQFT_FLAG_NO_RESIDENT) != 0));
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
     if (h->narrow_active && !h->narrowp.enabled) ST(narrow_exit(h));  // e.g. a coupling whose table the 16-bit kernel cannot hold
@@ -1836,6 +1840,10 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_r
     }
     CU(cudaMemsetAsync(h->n_meas_d, 0, sizeof(uint32_t), h->stream));
     if (accepted) CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * (size_t)nc * kAccSlots, h->stream));
+    // the cluster-resident kernel adds every CTA's share into the log slots
+    const bool cluster_ok = h->clusterp.enabled && !s->correlator_every && !s->difference_every;
+    if (cluster_ok && n_meas) CU(cudaMemsetAsync(h->elog_d, 0, sizeof(long long) * (size_t)nc * h->elog_cap, h->stream));
+    if (cluster_ok && n_act) CU(cudaMemsetAsync(h->alog_d, 0, sizeof(long long) * (size_t)nc * h->alog_cap, h->stream));
 
     uint64_t cycle = 1;
     for (uint32_t f : {s->energy_every, s->normalize_every, s->action_every, s->correlator_every, s->difference_every})
@@ -1884,6 +1892,28 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_r
             ST(refresh_ghosts(h));  // leaving the 16-bit copy leaves the i32 ghost planes stale
         }
         const uint64_t seg_begin = step;
+        if (h->narrow_active && cluster_ok && seg_end - step >= 2) {
+            // the whole segment in one launch, the chains resident in shared memory (kernels_cluster.cuh)
+            ClusterArgs a{};
+            a.g = h->gn;
+            a.sweep_base = s->sweep_base;
+            a.first_step = step;
+            a.n_steps = seg_end - step;
+            a.energy_every = s->energy_every;
+            a.action_every = s->action_every;
+            a.normalize_every = s->normalize_every;
+            a.elog_cap = h->elog_cap;
+            a.alog_cap = h->alog_cap;
+            a.e_slot0 = (uint32_t)lqft_run_measurements(s->first_step, step - s->first_step, s->energy_every);
+            a.a_slot0 = (uint32_t)lqft_run_measurements(s->first_step, step - s->first_step, s->action_every);
+            a.n_cta = h->clusterp.n_cta;
+            a.tp = h->clusterp.tp;
+            a.max_thr = h->max_thr;
+            CU(cluster_launch(h->clusterp, a, nc, h->any_wilson, h->count_accepts, h->narrow[0], h->narrow[1], h->chains_d, h->thr_d,
+                              h->offset_d, h->ncentre_d, h->elog_d, h->alog_d, h->acc_d, h->stream));
+            h->launches += 1;
+            step = seg_end;
+        }
         // slabs replay graphs only on the narrow copy: the numbers of its flips live in device memory
         const bool use_graph = graph_ok && (h->g.ghost == 0 || h->narrow_active);
         const bool deep = h->narrow_active && h->gn.ghost != 0;
@@ -2054,7 +2084,7 @@ extern "C" lqft_status lqft_plan_info(lqft_handle* h, char* buf, size_t cap) {
     if (!h || !buf || cap == 0) return fail(LQFT_ERR_INVALID, "null argument");
     ST(use_device(h));
     ST(upload_params(h));
-    const char* path = h->is64 ? "f64" : h->resident_ok ? "resident" : h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream"
+    const char* path = h->is64 ? "f64" : h->resident_ok ? "resident" : h->clusterp.enabled ? "cluster" : h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream"
                        : h->tiled.enabled ? "march" : ((h->g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) ? "vec4" : "generic");
     uint32_t chunks = 0, rows = 0, groups = 0;
     int occ = 0;

@@ -164,7 +164,7 @@ def test_narrow_64cubed_many_chains_match_single_chain_runs():
             acc = eng.sweep(0, 6, want_accepted=True)[0]
             e, _, _ = eng.run(20, sweep_base=6, energy_every=5, normalize_every=10)
             single.append((acc, e[0].copy(), eng.download(0)))
-    with Engine(X, Y, T, n_chains=5) as eng:
+    with Engine(X, Y, T, n_chains=5, flags=NORES) as eng:   # NO_RESIDENT: the launch-per-half-sweep kernel, not the cluster one
         for c in range(5):
             eng.set_chain(c, betas[c], 64000 + c, 10 * c, 13 * c)
             eng.upload(c, v0[c])
