@@ -82,10 +82,12 @@ typedef struct lqft_config {
 #define LQFT_FLAG_FORCE_V1 8u     /* use the two-pass L1-cached kernels, not the tiled ones */
 #define LQFT_FLAG_NO_STREAM 16u   /* wide rows: marching kernel instead of the streaming one */
 #define LQFT_FLAG_NO_PDL 32u      /* no programmatic dependent launch between half-sweeps     */
-#define LQFT_FLAG_NO_RESIDENT 128u /* small lattices: multi-launch path instead of the one-launch
-                                     shared-memory resident kernel */
-#define LQFT_FLAG_NO_NARROW 256u   /* X in {256, 512, 1024}: keep the i32 kernels inside lqft_run / lqft_sweep instead of the
-                                     16-bit working copy (same results, used by the tests to cross-check) */
+#define LQFT_FLAG_NO_RESIDENT 128u /* multi-launch path instead of the one-launch kernels that keep a chain in shared
+                                     memory (one CTA up to 36^3, a thread-block cluster up to ~1.5 MB per chain) */
+#define LQFT_FLAG_NO_NARROW 256u   /* powers of two 16 <= X <= 1024: keep the field in the i32 arrays instead of the 16-bit
+                                     storage (same results, used by the tests to cross-check) */
+#define LQFT_FLAG_NO_FUSED_ENERGY 512u /* measure a due energy with the observe kernel instead of inside the colour-1
+                                     half-sweep of that step (same results, used by the tests to cross-check) */
 #define LQFT_FLAG_SELF_HALO 64u   /* world_size==1: ghost planes + the peer-memory halo path with
                                      this rank as its own neighbour (tests the multi-GPU kernel) */
 

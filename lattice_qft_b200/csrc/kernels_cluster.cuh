@@ -13,13 +13,7 @@
 // normalize is one thread.  The field returns to the 16-bit arrays in global memory when the call ends.
 // Same sites, same Philox counters, same packed arithmetic as k_sweep_n16 (n16_row_decide): bit-identical results.
 //
-// Energy / action without a pass of their own.  Every bond joins a colour-1 site and a colour-0 site, so
-//     sum_bonds s_b (h_x - h_y)^2 = sum_{x in colour 1} sum_{6 nbrs n} s (w - n)^2        (s = +1, or -1 for t bonds
-//                                                                                          of the energy, fields.rs:728-737)
-//   = sum_x [ c w^2 - 2 w (S4 +- S2) ] + c sum_{colour 0} h^2,   S4 = sum of the x, y neighbours, S2 = of the t ones,
-// c = 4 - 2 for the energy and 4 + 2 for the action (fields.rs:719-726): w, S4, S2 and the colour-0 row of the same
-// positions are in registers when a colour-1 row has been decided.  An exact integer identity, evaluated on the
-// stored (biased) heights: per row the eight terms are summed in 32 bits (|.| < 2^31), then widened.
+// Energy / action without a pass of their own: n16_obs_pair (kernels_narrow.cuh).
 #pragma once
 #include "kernels_narrow.cuh"
 
@@ -64,17 +58,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// acc += sum over the two 16-bit halves of  w (K w - s4 + SGN s2) + K oc^2:  K = 1, SGN = +1 is half the energy share of
-// two colour-1 sites, K = 3, SGN = -1 half their action share (see the header)
-template <int K, int SGN>
-__device__ __forceinline__ void cluster_obs_pair(uint32_t w, uint32_t s4, uint32_t s2, uint32_t oc, int& acc) {
-    const int w0 = (int)(w & 0xffffu), w1 = (int)(w >> 16);
-    const int o0 = (int)(oc & 0xffffu), o1 = (int)(oc >> 16);
-    const int t0 = K * w0 - (int)(s4 & 0xffffu) + SGN * (int)(s2 & 0xffffu);
-    const int t1 = K * w1 - (int)(s4 >> 16) + SGN * (int)(s2 >> 16);
-    acc += w0 * t0 + K * o0 * o0 + w1 * t1 + K * o1 * o1;
 }
 
 // grid = (n_cta, n_chains), cluster = (n_cta, 1, 1), block = 768 or 384 (a multiple of 32 and of XQ),
@@ -168,31 +151,15 @@ k_run_cluster(const ClusterArgs a, uint16_t* __restrict__ f0, uint16_t* __restri
                     if (rank * TP + pl < cd.wil_h && (y == 0u || y == y_one))
                         woff = n16_wilson(8u * k4, p, (y == 0u ? 1 : 0) - (y == y_one ? 1 : 0), cd.wil_w);
                 }
-                const uint4 w = n16_row_decide<WILSON, COUNT>(v, om, oc, on, ta, tb, sh, r0, r1, c_off, c_max, woff, accepted);
+                uint4 s4, s2;
+                n16_row_sums(om, oc, on, ta, tb, sh, s4, s2);
+                const uint4 w = n16_row_decide<WILSON, COUNT>(v, s4, s2, r0, r1, c_off, c_max, woff, accepted);
                 sts_v4(own + off, w);
                 if (pl == 0u) st_cluster_v4(r_lo + off, w);
                 if (pl + 1u == TP) st_cluster_v4(r_hi + off, w);
                 if (measure) {
-                    // energy: t bonds count negative, S = S4 - S2, c = 2; action: S = S4 + S2, c = 6 (see the header)
-                    const uint4 s4 = make_uint4(oc.x + sh.x + om.x + on.x, oc.y + sh.y + om.y + on.y, oc.z + sh.z + om.z + on.z,
-                                                oc.w + sh.w + om.w + on.w);
-                    const uint4 s2 = make_uint4(ta.x + tb.x, ta.y + tb.y, ta.z + tb.z, ta.w + tb.w);
-                    if (due_e) {
-                        int e = 0;
-                        cluster_obs_pair<1, 1>(w.x, s4.x, s2.x, oc.x, e);
-                        cluster_obs_pair<1, 1>(w.y, s4.y, s2.y, oc.y, e);
-                        cluster_obs_pair<1, 1>(w.z, s4.z, s2.z, oc.z, e);
-                        cluster_obs_pair<1, 1>(w.w, s4.w, s2.w, oc.w, e);
-                        sum_e += e;
-                    }
-                    if (due_a) {
-                        int e = 0;
-                        cluster_obs_pair<3, -1>(w.x, s4.x, s2.x, oc.x, e);
-                        cluster_obs_pair<3, -1>(w.y, s4.y, s2.y, oc.y, e);
-                        cluster_obs_pair<3, -1>(w.z, s4.z, s2.z, oc.z, e);
-                        cluster_obs_pair<3, -1>(w.w, s4.w, s2.w, oc.w, e);
-                        sum_a += e;
-                    }
+                    if (due_e) sum_e += n16_obs_row<1, 1>(w, s4, s2, oc);
+                    if (due_a) sum_a += n16_obs_row<3, -1>(w, s4, s2, oc);
                 }
                 off += off_step;
                 grp += grp_step;

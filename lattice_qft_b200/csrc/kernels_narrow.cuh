@@ -63,17 +63,15 @@ __device__ __forceinline__ int build_interleaved(uint2* s_tab, const uint32_t* _
 
 __shared__ uint2 s_n16_tab[2 * (2 * kN16KcMax + 1)];
 
-// Sums and decisions of one row of 8 sites per thread.  sh = the other x neighbour of site j (position j+1 or j-1 of
-// the other colour's row, by the row's x parity).
+// Decisions of one row of 8 sites per thread.  s4 = packed sum of the four x / y neighbours, s2 = of the two t neighbours.
 template <bool WILSON, bool COUNT>
-__device__ __forceinline__ uint4 n16_row_decide(const uint4 v, const uint4 om, const uint4 oc, const uint4 on, const uint4 to,
-                                                const uint4 ti, const uint4 sh, const u32x4 r0, const u32x4 r1,
+__device__ __forceinline__ uint4 n16_row_decide(const uint4 v, const uint4 s4, const uint4 s2, const u32x4 r0, const u32x4 r1,
                                                 const uint32_t c_off, const uint32_t c_max, const uint4 woff, int& accepted) {
     constexpr uint32_t C = 0x60006000u;
     uint4 w;
 #define LQFT_N16_PAIR(F, RA, RB)                                                                      \
     {                                                                                                 \
-        const uint32_t ns = oc.F + sh.F + om.F + on.F + to.F + ti.F;                                  \
+        const uint32_t ns = s4.F + s2.F;                                                              \
         uint32_t u = 6u * v.F + C - ns;                                                               \
         if (WILSON) u += woff.F;                                                                      \
         const uint32_t idx = __viaddmin_s16x2_relu(u, c_off, c_max);                                  \
@@ -91,11 +89,20 @@ __device__ __forceinline__ uint4 n16_row_decide(const uint4 v, const uint4 om, c
     return w;
 }
 
+// Packed neighbour sums of a row: sh = the other x neighbour of site j (position j+1 or j-1 of the other colour's row,
+// by the row's x parity).  Heights below 4096: a half never carries into the other.
+__device__ __forceinline__ void n16_row_sums(const uint4 om, const uint4 oc, const uint4 on, const uint4 to, const uint4 ti,
+                                             const uint4 sh, uint4& s4, uint4& s2) {
+    s4 = make_uint4(oc.x + sh.x + om.x + on.x, oc.y + sh.y + om.y + on.y, oc.z + sh.z + om.z + on.z, oc.w + sh.w + om.w + on.w);
+    s2 = make_uint4(to.x + ti.x, to.y + ti.y, to.z + ti.z, to.w + ti.w);
+}
+
 // The same with the x parity P of the row's sites known at compile time (warp uniform in k_sweep_n16).
 template <int P, bool WILSON, bool COUNT>
 __device__ __forceinline__ uint4 n16_row_update(const uint4 v, const uint4 om, const uint4 oc, const uint4 on, const uint4 to,
                                                 const uint4 ti, const uint32_t edge, const u32x4 r0, const u32x4 r1,
-                                                const uint32_t c_off, const uint32_t c_max, const uint4 woff, int& accepted) {
+                                                const uint32_t c_off, const uint32_t c_max, const uint4 woff, int& accepted,
+                                                uint4& s4, uint4& s2) {
     uint4 sh;
     if (P) {
         sh.x = __byte_perm(oc.x, oc.y, 0x5432); sh.y = __byte_perm(oc.y, oc.z, 0x5432);
@@ -104,7 +111,35 @@ __device__ __forceinline__ uint4 n16_row_update(const uint4 v, const uint4 om, c
         sh.x = __byte_perm(edge, oc.x, 0x5432); sh.y = __byte_perm(oc.x, oc.y, 0x5432);
         sh.z = __byte_perm(oc.y, oc.z, 0x5432); sh.w = __byte_perm(oc.z, oc.w, 0x5432);
     }
-    return n16_row_decide<WILSON, COUNT>(v, om, oc, on, to, ti, sh, r0, r1, c_off, c_max, woff, accepted);
+    n16_row_sums(om, oc, on, to, ti, sh, s4, s2);
+    return n16_row_decide<WILSON, COUNT>(v, s4, s2, r0, r1, c_off, c_max, woff, accepted);
+}
+
+// Energy / action from inside a colour-1 half-sweep.  Every bond joins a colour-1 site and a colour-0 site, so
+//     sum_bonds s_b (h_x - h_y)^2 = sum_{x in colour 1} sum_{6 nbrs n} s (w - n)^2        (s = +1, or -1 for t bonds
+//                                                                                          of the energy, fields.rs:728-737)
+//   = sum_x [ c w^2 - 2 w (S4 +- S2) ] + c sum_{colour 0} h^2,   S4 = sum of the x, y neighbours, S2 = of the t ones,
+// c = 4 - 2 for the energy and 4 + 2 for the action (fields.rs:719-726): w, S4, S2 and the colour-0 row of the same
+// positions are in registers when a colour-1 row has been decided.  An exact integer identity, evaluated on the
+// stored (biased) heights; the eight terms of a row are summed in 32 bits (|.| < 2^31), then widened.
+// acc += sum over the two 16-bit halves of  w (K w - s4 + SGN s2) + K oc^2:  K = 1, SGN = +1 gives half the energy share
+// of two colour-1 sites, K = 3, SGN = -1 half their action share.
+template <int K, int SGN>
+__device__ __forceinline__ void n16_obs_pair(uint32_t w, uint32_t s4, uint32_t s2, uint32_t oc, int& acc) {
+    const int w0 = (int)(w & 0xffffu), w1 = (int)(w >> 16);
+    const int o0 = (int)(oc & 0xffffu), o1 = (int)(oc >> 16);
+    const int t0 = K * w0 - (int)(s4 & 0xffffu) + SGN * (int)(s2 & 0xffffu);
+    const int t1 = K * w1 - (int)(s4 >> 16) + SGN * (int)(s2 >> 16);
+    acc += w0 * t0 + K * o0 * o0 + w1 * t1 + K * o1 * o1;
+}
+template <int K, int SGN>
+__device__ __forceinline__ int n16_obs_row(const uint4 w, const uint4 s4, const uint4 s2, const uint4 oc) {
+    int e = 0;
+    n16_obs_pair<K, SGN>(w.x, s4.x, s2.x, oc.x, e);
+    n16_obs_pair<K, SGN>(w.y, s4.y, s2.y, oc.y, e);
+    n16_obs_pair<K, SGN>(w.z, s4.z, s2.z, oc.z, e);
+    n16_obs_pair<K, SGN>(w.w, s4.w, s2.w, oc.w, e);
+    return e;
 }
 
 // Packed Wilson offsets of the 8 sites x = 2 (k0 + j) + p of a row next to the sheet (spec.cuh, wilson_offset).
@@ -179,20 +214,26 @@ __device__ __forceinline__ void slab_flip(const SlabArgs& sl, bool first_block, 
     __syncthreads();  // also where the compiler sees the block converge again: without it the sweep loop is compiled as divergent code
 }
 
-template <int XQ, bool WILSON, bool COUNT, bool SINGLE, bool SLAB>
+template <int XQ, bool WILSON, bool COUNT, bool SINGLE, bool SLAB, bool MEAS>
 __global__ void __launch_bounds__(kN16Threads, (COUNT || WILSON) ? 3 : 4)
 k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __restrict__ ctr, const int32_t tl_first,
             const uint32_t n_first, const int32_t tl_second, const uint32_t n_planes, const uint32_t n_chunks,
             uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
             const ChainDev* __restrict__ chains, const ChainDev chain0, const uint32_t* __restrict__ thr_all,
-            unsigned long long* __restrict__ acc, const uint32_t max_thr, const SlabArgs sl) {
+            unsigned long long* __restrict__ acc, const uint32_t max_thr, const SlabArgs sl,
+            unsigned long long* __restrict__ obs_e) {
     constexpr uint32_t ROWQ = XQ;                        // uint4 per row of one colour
     constexpr uint32_t LPR = XQ < 32 ? XQ : 32;          // lanes of a warp on one row
     constexpr uint32_t PPW = 32u / LPR;                  // planes per warp
     constexpr int SEGS = XQ / 32;                        // 512-site row segments (0: a row is narrower than a warp)
     __shared__ unsigned int s_cnt;
+    __shared__ unsigned long long s_obs;
     pdl_launch_dependents();
     const uint32_t chain = SINGLE ? 0u : blockIdx.z;
+    // MEAS: this launch is the colour-1 half-sweep of a step whose energy is due: accumulate it on the way (n16_obs_pair)
+    // into obs_e.  An instantiation of its own: the plain kernel must not carry the second loop (3.5 % slower, measured).
+    if (MEAS && threadIdx.x == 0) s_obs = 0;
+    long long sum_e = 0;
     const ChainDev cd = SINGLE ? chain0 : chains[chain];
     if (COUNT && threadIdx.x == 0) s_cnt = 0;
     const int kc = build_interleaved(s_n16_tab, thr_all + (size_t)chain * kThrStride, max_thr);
@@ -259,7 +300,7 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         // a warp without a live plane slot leaves after one row (the vote keeps the trip count warp uniform for the
         // compiler; an outright early exit costs the uniform registers, see above)
         uint32_t n = __all_sync(0xffffffffu, pl_raw >= n_planes) ? 1u : y1 - y0;
-#define LQFT_N16_STEP(OM, OC, ON, PUSH)                                                                                     \
+#define LQFT_N16_STEP(OM, OC, ON, PUSH, MEAS)                                                                               \
     {                                                                                                                    \
         const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;                                                                  \
         uint4* const po = q_own + (b_own + y * ROWQ);                                                                    \
@@ -280,19 +321,20 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
             if (wil_plane && (y == 0u || y == y_one))                                                                    \
                 woff = n16_wilson(8u * kq, p, (y == 0u ? 1 : 0) - (y == y_one ? 1 : 0), cd.wil_w);                       \
         }                                                                                                                \
-        uint4 w;                                                                                                         \
+        uint4 w, s4, s2;                                                                                                 \
         int acc_row = 0;                                                                                                 \
         if (p) {                                                                                                         \
             uint32_t edge = __shfl_sync(0xffffffffu, OC.x, src_r);                                                       \
             if (SEGS > 1) edge = e_lane ? e_ld : edge;                                                                   \
-            w = n16_row_update<1, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, c_off, c_max, woff, acc_row);      \
+            w = n16_row_update<1, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, c_off, c_max, woff, acc_row, s4, s2); \
         } else {                                                                                                         \
             uint32_t edge = __shfl_sync(0xffffffffu, OC.w, src_l);                                                       \
             if (SEGS > 1) edge = e_lane ? e_ld : edge;                                                                   \
-            w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, c_off, c_max, woff, acc_row);      \
+            w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, c_off, c_max, woff, acc_row, s4, s2); \
         }                                                                                                                \
         if (COUNT) accepted += owned ? acc_row : 0;                                                                      \
         if (live) *po = w;                                                                                               \
+        if (MEAS) sum_e += owned ? n16_obs_row<1, 1>(w, s4, s2, OC) : 0;                                                 \
         if (PUSH) {                                                                                                      \
             if (q_lo) q_lo[y * ROWQ] = w;                                                                                \
             if (q_hi) q_hi[y * ROWQ] = w;                                                                                \
@@ -304,20 +346,29 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         if (SLAB && sl.depth != 0u && grp_hi > 0 && grp_lo < (int32_t)g.Tl &&
             (grp_lo < (int32_t)sl.depth || grp_hi > (int32_t)(g.Tl - sl.depth))) {
             for (;;) {
-                LQFT_N16_STEP(wa, wb, wc, true)
+                LQFT_N16_STEP(wa, wb, wc, true, false)
                 if (--n == 0) break;
-                LQFT_N16_STEP(wb, wc, wa, true)
+                LQFT_N16_STEP(wb, wc, wa, true, false)
                 if (--n == 0) break;
-                LQFT_N16_STEP(wc, wa, wb, true)
+                LQFT_N16_STEP(wc, wa, wb, true, false)
+                if (--n == 0) break;
+            }
+        } else if (MEAS) {
+            for (;;) {
+                LQFT_N16_STEP(wa, wb, wc, false, true)
+                if (--n == 0) break;
+                LQFT_N16_STEP(wb, wc, wa, false, true)
+                if (--n == 0) break;
+                LQFT_N16_STEP(wc, wa, wb, false, true)
                 if (--n == 0) break;
             }
         } else {
             for (;;) {
-                LQFT_N16_STEP(wa, wb, wc, false)
+                LQFT_N16_STEP(wa, wb, wc, false, false)
                 if (--n == 0) break;
-                LQFT_N16_STEP(wb, wc, wa, false)
+                LQFT_N16_STEP(wb, wc, wa, false, false)
                 if (--n == 0) break;
-                LQFT_N16_STEP(wc, wa, wb, false)
+                LQFT_N16_STEP(wc, wa, wb, false, false)
                 if (--n == 0) break;
             }
         }
@@ -325,6 +376,14 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     }
     if (COUNT)
         block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
+    if (MEAS) {
+        // the block's share of the chain's energy sum (obs[chain][0]; logged and cleared by k_obs_finalize)
+        sum_e = warp_sum_ll(sum_e);
+        __syncthreads();
+        if ((threadIdx.x & 31u) == 0u && sum_e != 0) atomicAdd(&s_obs, (unsigned long long)sum_e);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_obs != 0) atomicAdd(obs_e + (size_t)chain * 2, 2ull * s_obs);
+    }
 }
 
 // ---- first fill of a ghost set ---------------------------------------------------------------------------------
@@ -491,30 +550,38 @@ struct NarrowArgs {
     bool pdl;
     bool slab = false;     // SLAB instantiation: push boundary planes and / or flip the ghost sets (sl)
     SlabArgs sl{};
+    unsigned long long* obs_e = nullptr;  // colour-1 half-sweep of a measured step: energy sums accumulate here ([chain][2])
 };
 
 template <int XQ, bool SLAB>
 inline const void* n16_variant_s(bool w, bool c, bool s) {
     if (w) {
-        if (c) return s ? (const void*)k_sweep_n16<XQ, true, true, true, SLAB> : (const void*)k_sweep_n16<XQ, true, true, false, SLAB>;
-        return s ? (const void*)k_sweep_n16<XQ, true, false, true, SLAB> : (const void*)k_sweep_n16<XQ, true, false, false, SLAB>;
+        if (c) return s ? (const void*)k_sweep_n16<XQ, true, true, true, SLAB, false> : (const void*)k_sweep_n16<XQ, true, true, false, SLAB, false>;
+        return s ? (const void*)k_sweep_n16<XQ, true, false, true, SLAB, false> : (const void*)k_sweep_n16<XQ, true, false, false, SLAB, false>;
     }
-    if (c) return s ? (const void*)k_sweep_n16<XQ, false, true, true, SLAB> : (const void*)k_sweep_n16<XQ, false, true, false, SLAB>;
-    return s ? (const void*)k_sweep_n16<XQ, false, false, true, SLAB> : (const void*)k_sweep_n16<XQ, false, false, false, SLAB>;
+    if (c) return s ? (const void*)k_sweep_n16<XQ, false, true, true, SLAB, false> : (const void*)k_sweep_n16<XQ, false, true, false, SLAB, false>;
+    return s ? (const void*)k_sweep_n16<XQ, false, false, true, SLAB, false> : (const void*)k_sweep_n16<XQ, false, false, false, SLAB, false>;
+}
+// measuring instantiations: one GPU, no acceptance counts
+template <int XQ>
+inline const void* n16_variant_m(bool w, bool s) {
+    if (w) return s ? (const void*)k_sweep_n16<XQ, true, false, true, false, true> : (const void*)k_sweep_n16<XQ, true, false, false, false, true>;
+    return s ? (const void*)k_sweep_n16<XQ, false, false, true, false, true> : (const void*)k_sweep_n16<XQ, false, false, false, false, true>;
 }
 template <int XQ>
-inline const void* n16_variant(bool w, bool c, bool s, bool slab) {
+inline const void* n16_variant(bool w, bool c, bool s, bool slab, bool meas) {
+    if (meas) return n16_variant_m<XQ>(w, s);
     return slab ? n16_variant_s<XQ, true>(w, c, s) : n16_variant_s<XQ, false>(w, c, s);
 }
-inline const void* n16_kernel(int xq, bool w, bool c, bool s, bool slab) {
+inline const void* n16_kernel(int xq, bool w, bool c, bool s, bool slab, bool meas = false) {
     switch (xq) {
-        case 1: return n16_variant<1>(w, c, s, slab);
-        case 2: return n16_variant<2>(w, c, s, slab);
-        case 4: return n16_variant<4>(w, c, s, slab);
-        case 8: return n16_variant<8>(w, c, s, slab);
-        case 16: return n16_variant<16>(w, c, s, slab);
-        case 32: return n16_variant<32>(w, c, s, slab);
-        case 64: return n16_variant<64>(w, c, s, slab);
+        case 1: return n16_variant<1>(w, c, s, slab, meas);
+        case 2: return n16_variant<2>(w, c, s, slab, meas);
+        case 4: return n16_variant<4>(w, c, s, slab, meas);
+        case 8: return n16_variant<8>(w, c, s, slab, meas);
+        case 16: return n16_variant<16>(w, c, s, slab, meas);
+        case 32: return n16_variant<32>(w, c, s, slab, meas);
+        case 64: return n16_variant<64>(w, c, s, slab, meas);
     }
     return nullptr;
 }
@@ -623,9 +690,10 @@ inline cudaError_t narrow_half(NarrowPlan& p, const NarrowArgs& a) {
     const uint32_t* thr = a.thr;
     unsigned long long* acc = a.acc;
     SlabArgs sl = a.sl;
+    unsigned long long* obs_e = a.obs_e;
     void* args[] = {&g, &colour, &sweep, &ctr, &tl_first, &n_first, &tl_second, &n_planes, &n_chunks, &own, &oth, &chains,
-                    &chain0, &thr, &acc, &max_thr, &sl};
-    return cudaLaunchKernelExC(&cfg, n16_kernel(p.xq, a.wilson, a.count, a.n_chains == 1, a.slab), args);
+                    &chain0, &thr, &acc, &max_thr, &sl, &obs_e};
+    return cudaLaunchKernelExC(&cfg, n16_kernel(p.xq, a.wilson, a.count, a.n_chains == 1, a.slab, a.obs_e != nullptr), args);
 }
 
 }  // namespace lqft

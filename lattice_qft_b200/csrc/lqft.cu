@@ -869,7 +869,7 @@ static void flip_args(lqft_handle* h, SlabArgs& sl) {
 // period (the kernel's prologue swaps the ghost sets with the neighbours), `push` sends the boundary planes of this
 // colour into the neighbours' other set.
 static lqft_status launch_half_narrow(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr, int32_t first,
-                                      uint32_t n_planes, bool flip = false, bool push = false) {
+                                      uint32_t n_planes, bool flip = false, bool push = false, bool measure = false) {
     NarrowArgs a{h->gn, colour, sweep, ctr, first, n_planes, 0, n_planes, h->cfg.n_chains, h->narrow[colour],
                  h->narrow[colour ^ 1], h->chains_d, h->chains_h[0], h->thr_d, h->acc_d, h->max_thr, h->any_wilson, h->count_accepts,
                  h->stream, !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
@@ -887,6 +887,7 @@ static lqft_status launch_half_narrow(lqft_handle* h, int colour, uint64_t sweep
             a.sl.hi_plane = peer_ghost_plane(h, 1, next);
         }
     }
+    if (measure) a.obs_e = h->obs_d;
     CU(narrow_half(h->narrowp, a));
     h->launches += 1;
     return LQFT_OK;
@@ -956,7 +957,12 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
 
 static lqft_status narrow_fill(lqft_handle* h);
 
-static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* ctr) {
+// The energy of a step can ride on its colour-1 half-sweep (kernels_narrow.cuh, n16_obs_pair): one GPU, 16-bit storage.
+static bool can_fuse_energy(const lqft_handle* h) {
+    return h->narrow_active && h->gn.ghost == 0 && !h->count_accepts && !(h->cfg.flags & LQFT_FLAG_NO_FUSED_ENERGY);
+}
+
+static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* ctr, bool fuse_energy = false) {
     const Geom& g = h->g;
     if (h->narrow_active) {
         // narrow copy.  Slabs: a period of `depth` half-sweeps per ghost set; each half-sweep also updates the ghost
@@ -965,7 +971,7 @@ static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* 
         const uint32_t depth = h->gn.ghost;
         for (int colour = 0; colour < 2; ++colour) {
             if (depth == 0) {
-                ST(launch_half_narrow(h, colour, sweep, ctr, 0, g.Tl));
+                ST(launch_half_narrow(h, colour, sweep, ctr, 0, g.Tl, false, false, fuse_energy && colour == 1));
                 continue;
             }
             bool flip = false;
@@ -1738,12 +1744,19 @@ static lqft_status launch_energy_log_f64(lqft_handle* h) {
 // due (computation.rs:267-269).
 static lqft_status launch_step(lqft_handle* h, const lqft_schedule* s, uint64_t step_arg,
                                uint64_t step_for_gating, const uint64_t* ctr) {
-    ST(launch_sweep(h, s->sweep_base + step_arg, ctr));
     uint32_t due = 0;
     if (s->energy_every && step_for_gating % s->energy_every == 0) due |= kObsEnergy;
     if (s->action_every && step_for_gating % s->action_every == 0) due |= kObsAction;
     if (s->correlator_every && step_for_gating % s->correlator_every == 0) due |= kObsCorr;
-    if (h->is64) {
+    const bool fused = due == kObsEnergy && can_fuse_energy(h);
+    ST(launch_sweep(h, s->sweep_base + step_arg, ctr, fused));
+    if (fused) {
+        // the colour-1 half-sweep has left the energy sums in obs_d: log them (and clear the accumulators)
+        ObsFin fin = h->run_fin;
+        k_obs_finalize<<<1, 256, 0, h->stream>>>(fin, due, s->sweep_base + step_arg, ctr, 0u, h->cfg.n_chains, h->obs_d);
+        CU(cudaGetLastError());
+        h->launches += 1;
+    } else if (h->is64) {
         if (due & kObsEnergy) ST(launch_energy_log_f64(h));
     } else if (due) {
         Measure m;

@@ -208,3 +208,30 @@ def test_one_sweep_per_call_and_standalone_observables_stay_on_the_16_bit_arrays
             assert (eng.download(0) == want).all(), s
         plan = eng.plan_info()
         assert plan["path"] == "narrow" and plan["storage"] == "u16" and plan["i32_allocated"] == 0, plan
+
+
+@pytest.mark.parametrize("size,wilson", [((256, 24, 6), (0, 0)), ((512, 10, 4), (300, 3)), ((1024, 6, 4), (0, 0)), ((64, 20, 10), (21, 7)),
+                                         ((16, 8, 12), (0, 0))])
+def test_energy_inside_the_colour_1_half_sweep_vs_observe_kernel_and_oracle(size, wilson):
+    """A step whose energy is due accumulates it inside its colour-1 half-sweep (n16_obs_pair: an exact integer
+    identity over the six bonds of every colour-1 site).  Same numbers as the separate observe kernel
+    (LQFT_FLAG_NO_FUSED_ENERGY) and as the oracle's literal loop (fields.rs:728-737), eager and graph-replayed, with
+    acceptance counts alongside."""
+    X, Y, T = size
+    beta, seed = 0.26, 0xE0 + X
+    lat = O.Lattice(list(size))
+    wil = O.Wilson(lat, *wilson) if wilson[0] else None
+    v0 = seeded_field(X * Y * T, seed=X + Y)
+    want = v0.copy()
+    we, wacc = O.run(lat, want, beta, seed, 0, 0, 40, 1, 10, order=1, wilson=wil)
+    for flags in (NORES, NORES | _lib.FLAG_NO_GRAPH, NORES | _lib.FLAG_NO_FUSED_ENERGY):
+        with Engine(X, Y, T, flags=flags) as eng:
+            eng.set_chain(0, beta, seed, *wilson)
+            eng.upload(0, v0)
+            launches = eng.kernel_launches()
+            e, e_int, acc = eng.run(40, energy_every=1, normalize_every=10, want_accepted=True)
+            per_step = (eng.kernel_launches() - launches) / 40
+            assert (e[0] == we).all(), flags
+            assert acc[0] == wacc
+            assert (eng.download(0) == want).all()
+            assert int(e_int[0][-1]) == O.integer_energy(lat, want)[0]
