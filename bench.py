@@ -354,11 +354,16 @@ def config5_leg(world: int, rank: int, device: int, barrier):
         out["efficiency_vs_single_gpu_slab"] = 1.0
         peak, _ = measured_peak_gbs()
         out["frac_hbm_roofline_8B_per_update"] = solo_rate * 8 / 1e9 / peak
-        out["frac_hbm_roofline_kernel_bytes_4B"] = solo_rate * 4 / 1e9 / peak
+        out["frac_hbm_roofline_kernel_bytes_6B"] = solo_rate * 6 / 1e9 / peak
         traffic, src = measured_traffic([x, y, tl], "k_sweep_n16")
         out["dram_bytes_per_half_sweep_ncu"] = traffic
         out["dram_bytes_source"] = src
-        out["algorithmic_bytes_per_half_sweep_4B"] = 4 * x * y * tl // 2
+        out["kernel_bytes_per_half_sweep_6B"] = 6 * x * y * tl // 2
+        out["kernel_bytes_note"] = ("the 512 MiB field does not fit L2: a half-sweep reads both colours and writes one, 6 B per "
+                                    "update; `dram_bytes_per_half_sweep_ncu` is what one launch moved under ncu")
+        if traffic:
+            out["dram_GBps_at_measured_rate"] = traffic * (solo_rate / (x * y * tl / 2)) / 1e9
+            out["frac_hbm_peak_measured_traffic"] = out["dram_GBps_at_measured_rate"] / peak
         return out
     eng = Engine(x, y, tl * world, device=device, world_size=world, rank=rank, nccl_id=fresh_nccl_id(world, rank))
     eng.set_chain(0, BETA, SEED)
@@ -379,13 +384,13 @@ def workload_config(n_gpus: int):
         "workload": f"{X}x{Y}x{t} periodic lattice, 1 chain, i32 heights, beta={BETA}, red-black Metropolis, "
                     f"{SWEEPS_PER_STEP} sweeps per step, pre-thermalised {THERMALISE} sweeps from seeded hot start",
         "lattice": [X, Y, t], "sweeps_per_step": SWEEPS_PER_STEP, "beta": BETA,
-        "decomposition": "none" if n_gpus == 1 else f"t-slabs of {T_PER_GPU} planes per GPU; 16-bit working copy with a deep halo "
-                         "(8 ghost planes at this plane size) exchanged over peer memory once per 8 half-sweeps",
-        "l2": "L2 flushed (256 MiB write) between timed steps; the 64 MiB/GPU field itself is L2-resident by nature",
-        "working_copy": "inside lqft_sweep / lqft_run the update kernels work on a u16 copy of the i32 field (heights biased "
-                        "around the normalisation offset; exact integers, bit-identical to the i32 kernels and the oracle; "
-                        "outside a +-1023 guard band the call stays on i32); host buffers and the device field between "
-                        "calls are i32",
+        "decomposition": "none" if n_gpus == 1 else f"t-slabs of {T_PER_GPU} planes per GPU; 8 ghost planes per side, redundantly "
+                         "updated for 8 half-sweeps; the last two half-sweeps of such a period push the boundary planes into "
+                         "the neighbours' other ghost set over peer memory (NVLink), the next kernel's prologue flips the sets",
+        "l2": "L2 flushed (256 MiB write) between timed steps; the 32 MiB/GPU field itself is L2-resident by nature",
+        "storage": "the device field is stored as u16 (heights biased around the chain's normalisation offset; exact integers, "
+                   "bit-identical to the i32 kernels and the oracle); it moves to i32 arrays only if a height leaves the "
+                   "+-1023 guard band; host buffers at the ABI are i32",
     }
 
 
@@ -539,7 +544,7 @@ def main():
         achieved = alg_bytes_per_launch / per_launch_s / 1e9
         # which kernel family did the sweeps: the 16-bit working copy (kernels_narrow.cuh) or the i32 streaming kernel
         kernel = "k_sweep_n16" if narrow_segments > 0 else "k_sweep_stream"
-        moved = (4 if narrow_segments > 0 else 8) * (n_local / 2)
+        moved = (6 if narrow_segments > 0 else 12) * (n_local / 2)
         traffic, traffic_src = measured_traffic([X, Y, T_PER_GPU], kernel) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -558,8 +563,11 @@ def main():
                          "algorithmic_bytes_note": "SURVEY.md 8(d): 8 B per update = one i32 read + one i32 write, the "
                                                    "reference's storage type; `achieved` and `frac` use this figure",
                          "kernel_bytes_per_launch": moved,
-                         "kernel_bytes_note": "own-colour heights the kernel itself must read + write: 4 B per update on "
-                                              "the 16-bit working copy, 8 B on i32; frac_kernel_bytes = that / time / peak",
+                         "kernel_bytes_note": "what a red-black half-sweep on two colour arrays must move: both colours "
+                                              "read, the own colour written = 6 B per update on the 16-bit storage (12 B on "
+                                              "i32); frac_kernel_bytes = that / time / peak.  At 256^3 the 32 MiB field is L2 "
+                                              "resident (`traffic`: the DRAM bytes of one cold launch); the 1024 x 1024 x 128 "
+                                              "leg under `configs` is the HBM-bound case",
                          "frac_kernel_bytes": moved / per_launch_s / 1e9 / peak,
                          "avg_launch_us": per_launch_s * 1e6},
         }
