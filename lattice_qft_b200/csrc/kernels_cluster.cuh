@@ -34,7 +34,6 @@ struct ClusterArgs {
     uint32_t max_thr;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -75,8 +74,7 @@ k_run_cluster(const ClusterArgs a, uint16_t* __restrict__ f0, uint16_t* __restri
     constexpr uint32_t ROWB = XQ * 16u;                  // bytes per row of one colour
     const uint32_t planeB = Y * ROWB, colB = (TP + 2u) * planeB;
     const ChainDev cd = chains[chain];
-    const int kc = build_interleaved(s_n16_tab, thr_all + (size_t)chain * kThrStride, a.max_thr);
-    const uint32_t c_off = (uint32_t)((kc - 24576) & 0xffff) * 0x10001u, c_max = (uint32_t)(2 * kc) * 0x10001u;
+    const N16Tab tab = build_interleaved(thr_all + (size_t)chain * kThrStride, a.max_thr, g.entry_bytes);
     const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
     const uint32_t s_col0 = smem_u32(s_field), s_col1 = s_col0 + colB;
 
@@ -153,7 +151,7 @@ k_run_cluster(const ClusterArgs a, uint16_t* __restrict__ f0, uint16_t* __restri
                 }
                 uint4 s4, s2;
                 n16_row_sums(om, oc, on, ta, tb, sh, s4, s2);
-                const uint4 w = n16_row_decide<WILSON, COUNT>(v, s4, s2, r0, r1, c_off, c_max, woff, accepted);
+                const uint4 w = n16_row_decide<WILSON, COUNT>(v, s4, s2, r0, r1, tab, woff, accepted);
                 sts_v4(own + off, w);
                 if (pl == 0u) st_cluster_v4(r_lo + off, w);
                 if (pl + 1u == TP) st_cluster_v4(r_hi + off, w);

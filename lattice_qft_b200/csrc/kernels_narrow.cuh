@@ -47,39 +47,83 @@ constexpr int kN16KcMax = 255;                   // threshold tables up to 256 e
 constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even); fewer for large planes
 constexpr uint32_t kN16FillBlocks = 32;          // per (side, colour, chain)
 
-// Table entry (i << 1) | coin for d = i - kc: coin 1 proposes +1 (m = d), coin 0 proposes -1 (m = -d);
-// same contents as build_two_sided (kernels_tiled.cuh), interleaved so that the coin can be shifted in.
-__device__ __forceinline__ int build_interleaved(uint2* s_tab, const uint32_t* __restrict__ thr, uint32_t n_thr) {
+// Decision table.  Entry (i << 1) | coin serves d = i - kc: coin 1 proposes +1 (m = d), coin 0 proposes -1 (m = -d); same
+// contents as build_two_sided (kernels_tiled.cuh), interleaved so that the coin can be shifted into the index; an entry
+// is {threshold | coin << 31, +-1}.  (The lanes of a warp look up different entries: a 4.4-way bank conflict per LDS.64
+// on average, ncu round 2.  Storing the table [entry][copy] with one copy per lane of a half-warp removes the conflicts
+// and made the kernel 2 % slower — 24 KB of table per block instead of 8 cost more L1 and prologue than the conflicts
+// cost LSU time, measured with 1, 8 and 16 copies.  One copy it is.)
+__shared__ uint2 s_n16_tab[2 * (2 * kN16KcMax + 1)];
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct N16Tab {
+    uint32_t base;     // shared-memory byte address of entry 0
+    uint32_t stride;   // bytes per entry, as a value the compiler cannot fold (n16_lookup)
+    uint32_t c_off;    // packed kc - 24576: u + c_off = d + kc per half
+    uint32_t c_max;    // packed 2 kc
+};
+
+__device__ __forceinline__ N16Tab build_interleaved(const uint32_t* __restrict__ thr, uint32_t n_thr, uint32_t entry_bytes) {
     const int kc = max((int)n_thr - 1, 3);
     for (int i = threadIdx.x; i < 2 * (2 * kc + 1); i += blockDim.x) {
         const int up = i & 1, d = (i >> 1) - kc;
         const int m = up ? d : -d;
         const int k = min(max(m + 3, 0), (int)n_thr - 1);
-        s_tab[i] = make_uint2(thr[k] | (up ? 0x80000000u : 0u), up ? 1u : 0xffffffffu);
+        s_n16_tab[i] = make_uint2(thr[k] | (up ? 0x80000000u : 0u), up ? 1u : 0xffffffffu);
     }
     __syncthreads();
-    return kc;
+    N16Tab t;
+    t.base = smem_u32(s_n16_tab);
+    t.stride = entry_bytes;
+    t.c_off = (uint32_t)((kc - 24576) & 0xffff) * 0x10001u;
+    t.c_max = (uint32_t)(2 * kc) * 0x10001u;
+    return t;
 }
 
-__shared__ uint2 s_n16_tab[2 * (2 * kN16KcMax + 1)];
+// Entry i.  With the entry size arriving as a kernel argument the address is an integer multiply-add (FMA pipe) where a
+// compile-time 8 gives a LEA: the ALU pipe is the loaded one (ncu: ALU 55 %, FMA 20 % of their peaks before the change).
+__device__ __forceinline__ uint2 n16_lookup(const N16Tab& tab, const uint32_t i) {
+    uint2 t;
+    const uint32_t a = i * tab.stride + tab.base;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t.x), "=r"(t.y) : "r"(a));
+    return t;
+}
+
+// w += (r <= t.x) ? t.y << SH : 0 as a compare and a predicated (multiply-)add; the compiler's own choice for the C
+// expression is two selects, a shift and a three-input add per pair.
+template <int SH>
+__device__ __forceinline__ void n16_step_if(uint32_t& w, const uint32_t r, const uint2 t) {
+    if (SH == 0)
+        asm("{\n\t.reg .pred p;\n\tsetp.ls.u32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(w) : "r"(r), "r"(t.x), "r"(t.y));
+    else
+        asm("{\n\t.reg .pred p;\n\tsetp.ls.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, 65536, %0;\n\t}" : "+r"(w) : "r"(r), "r"(t.x), "r"(t.y));
+}
 
 // Decisions of one row of 8 sites per thread.  s4 = packed sum of the four x / y neighbours, s2 = of the two t neighbours.
 template <bool WILSON, bool COUNT>
 __device__ __forceinline__ uint4 n16_row_decide(const uint4 v, const uint4 s4, const uint4 s2, const u32x4 r0, const u32x4 r1,
-                                                const uint32_t c_off, const uint32_t c_max, const uint4 woff, int& accepted) {
+                                                const N16Tab& tab, const uint4 woff, int& accepted) {
     constexpr uint32_t C = 0x60006000u;
     uint4 w;
 #define LQFT_N16_PAIR(F, RA, RB)                                                                      \
     {                                                                                                 \
-        const uint32_t ns = s4.F + s2.F;                                                              \
-        uint32_t u = 6u * v.F + C - ns;                                                               \
+        uint32_t u; /* 6 v + C - s4 - s2, the constant folded into the subtraction (one add less than the compiler's form) */ \
+        asm("{\n\t.reg .u32 t;\n\tsub.u32 t, %3, %1;\n\tsub.u32 t, t, %2;\n\tmad.lo.u32 %0, %4, 6, t;\n\t}"   \
+            : "=r"(u) : "r"(s4.F), "r"(s2.F), "n"(C), "r"(v.F));                                      \
         if (WILSON) u += woff.F;                                                                      \
-        const uint32_t idx = __viaddmin_s16x2_relu(u, c_off, c_max);                                  \
-        const uint2 ta = s_n16_tab[__funnelshift_l(RA, idx & 0xffffu, 1)];                            \
-        const uint2 tb = s_n16_tab[__funnelshift_l(RB, idx >> 16, 1)];                                \
-        const bool aa = (RA) <= ta.x, ab = (RB) <= tb.x;                                              \
-        if (COUNT) accepted += (int)aa + (int)ab;                                                     \
-        w.F = v.F + (aa ? ta.y : 0u) + ((ab ? tb.y : 0u) << 16);                                      \
+        const uint32_t idx = __viaddmin_s16x2_relu(u, tab.c_off, tab.c_max);                          \
+        const uint2 ta = n16_lookup(tab, __funnelshift_l(RA, idx & 0xffffu, 1));                      \
+        const uint2 tb = n16_lookup(tab, __funnelshift_l(RB, idx >> 16, 1));                          \
+        if (COUNT) {                                                                                  \
+            const bool aa = (RA) <= ta.x, ab = (RB) <= tb.x;                                          \
+            accepted += (int)aa + (int)ab;                                                            \
+            w.F = v.F + (aa ? ta.y : 0u) + ((ab ? tb.y : 0u) << 16);                                  \
+        } else {                                                                                      \
+            w.F = v.F;                                                                                \
+            n16_step_if<0>(w.F, RA, ta);                                                              \
+            n16_step_if<16>(w.F, RB, tb);                                                             \
+        }                                                                                             \
     }
     LQFT_N16_PAIR(x, r0.x, r0.y)
     LQFT_N16_PAIR(y, r0.z, r0.w)
@@ -101,7 +145,7 @@ __device__ __forceinline__ void n16_row_sums(const uint4 om, const uint4 oc, con
 template <int P, bool WILSON, bool COUNT>
 __device__ __forceinline__ uint4 n16_row_update(const uint4 v, const uint4 om, const uint4 oc, const uint4 on, const uint4 to,
                                                 const uint4 ti, const uint32_t edge, const u32x4 r0, const u32x4 r1,
-                                                const uint32_t c_off, const uint32_t c_max, const uint4 woff, int& accepted,
+                                                const N16Tab& tab, const uint4 woff, int& accepted,
                                                 uint4& s4, uint4& s2) {
     uint4 sh;
     if (P) {
@@ -112,7 +156,7 @@ __device__ __forceinline__ uint4 n16_row_update(const uint4 v, const uint4 om, c
         sh.z = __byte_perm(oc.y, oc.z, 0x5432); sh.w = __byte_perm(oc.z, oc.w, 0x5432);
     }
     n16_row_sums(om, oc, on, to, ti, sh, s4, s2);
-    return n16_row_decide<WILSON, COUNT>(v, s4, s2, r0, r1, c_off, c_max, woff, accepted);
+    return n16_row_decide<WILSON, COUNT>(v, s4, s2, r0, r1, tab, woff, accepted);
 }
 
 // Energy / action from inside a colour-1 half-sweep.  Every bond joins a colour-1 site and a colour-0 site, so
@@ -236,8 +280,7 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     long long sum_e = 0;
     const ChainDev cd = SINGLE ? chain0 : chains[chain];
     if (COUNT && threadIdx.x == 0) s_cnt = 0;
-    const int kc = build_interleaved(s_n16_tab, thr_all + (size_t)chain * kThrStride, max_thr);
-    const uint32_t c_off = (uint32_t)((kc - 24576) & 0xffff) * 0x10001u, c_max = (uint32_t)(2 * kc) * 0x10001u;
+    const N16Tab tab = build_interleaved(thr_all + (size_t)chain * kThrStride, max_thr, g.entry_bytes);
     pdl_wait();
     if (ctr) sweep += *ctr;
     // planes of this block's group: local numbers [grp_lo, grp_hi) of a launch with one range (every SLAB launch)
@@ -326,11 +369,11 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         if (p) {                                                                                                         \
             uint32_t edge = __shfl_sync(0xffffffffu, OC.x, src_r);                                                       \
             if (SEGS > 1) edge = e_lane ? e_ld : edge;                                                                   \
-            w = n16_row_update<1, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, c_off, c_max, woff, acc_row, s4, s2); \
+            w = n16_row_update<1, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, tab, woff, acc_row, s4, s2); \
         } else {                                                                                                         \
             uint32_t edge = __shfl_sync(0xffffffffu, OC.w, src_l);                                                       \
             if (SEGS > 1) edge = e_lane ? e_ld : edge;                                                                   \
-            w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, c_off, c_max, woff, acc_row, s4, s2); \
+            w = n16_row_update<0, WILSON, COUNT>(v, OM, OC, ON, ta, tb, edge, r0, r1, tab, woff, acc_row, s4, s2); \
         }                                                                                                                \
         if (COUNT) accepted += owned ? acc_row : 0;                                                                      \
         if (live) *po = w;                                                                                               \

@@ -21,7 +21,7 @@ struct Geom {
     uint32_t ghost;         // ghost planes per side (0: periodic wrap by index; slabs: 1, or the deep halo of the narrow copy)
     uint32_t plane;         // Xh*Y elements per plane per colour
     uint32_t gbuf;          // 16-bit copy on slabs: which of its two sets of ghost planes is current (kernels_narrow.cuh)
-    uint32_t pad_;
+    uint32_t entry_bytes;   // 8 = sizeof(uint2): stride of the 16-bit kernels' decision table, handed over as data (n16_lookup)
     uint64_t chain_stride;  // elements per chain per colour: plane * (Tl + 2*ghost); the 16-bit copy on slabs: Tl + 4*ghost
 };
 
