@@ -24,7 +24,6 @@
 #include "kernels_stream.cuh"
 #include "kernels_narrow.cuh"
 #include "kernels_cluster.cuh"
-#include "kernels_flow.cuh"
 #include "kernels_observe.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_v1.cuh"
@@ -213,8 +212,6 @@ struct lqft_handle {
     uint32_t* nworst_d = nullptr;               // validity word of k_narrow
     NarrowPlan narrowp{};
     ClusterPlan clusterp{};                     // chains resident in the shared memory of a cluster (kernels_cluster.cuh)
-    FlowPlan flowp{};                           // one persistent launch per run, half-sweeps ordered by data flow (kernels_flow.cuh)
-    bool flow_first = true;                     // where both one-launch paths are possible: the persistent one
     Geom gn{};                                  // geometry of the narrow arrays: slabs carry a deep halo (ghost > 1)
     uint32_t nvalid = 0;                        // ghost planes per side of the narrow copy that are valid right now
     unsigned long long* phase_d = nullptr;      // device copy of `phase` at the start of a graph replay (slabs, narrow copy)
@@ -277,8 +274,6 @@ static lqft_status upload_params(lqft_handle* h) {
                       !h->narrow[0] || h->resident_ok || (h->g.ghost != 0 && !h->p2p)));
     CU(cluster_prepare(h->clusterp, h->g, nc, h->sm_count, h->max_thr, h->smem_optin,
                        !h->narrowp.enabled || (h->cfg.flags & LQFT_FLAG_NO_RESIDENT) != 0));
-    CU(flow_prepare(h->flowp, h->narrowp, h->g, nc, (h->cfg.flags & LQFT_FLAG_NO_RESIDENT) != 0));
-    if (const char* e = getenv("LQFT_FLOW_FIRST")) h->flow_first = atoi(e) != 0;
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
     if (h->narrow_active && !h->narrowp.enabled) ST(narrow_exit(h));  // e.g. a coupling whose table the 16-bit kernel cannot hold
@@ -521,7 +516,6 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
             if (h->peer_base[side][k]) cudaIpcCloseMemHandle(h->peer_base[side][k]);
     }
     cudaFree(h->halo_d);
-    cudaFree(h->flowp.prog);
     cudaFree(h->narrow[0]); cudaFree(h->narrow[1]); cudaFree(h->ncentre_d); cudaFree(h->nworst_d); cudaFree(h->phase_d);
     tiled_release(h->tiled);
     cudaFree(h->field[0]); cudaFree(h->field[1]);
@@ -1861,10 +1855,9 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_r
     CU(cudaMemsetAsync(h->n_meas_d, 0, sizeof(uint32_t), h->stream));
     if (accepted) CU(cudaMemsetAsync(h->acc_d, 0, sizeof(unsigned long long) * (size_t)nc * kAccSlots, h->stream));
     // the cluster-resident kernel adds every CTA's share into the log slots
-    const bool flow_ok = h->flowp.enabled;
-    const bool cluster_ok = h->clusterp.enabled && !s->correlator_every && !s->difference_every && !(flow_ok && h->flow_first);
-    if ((cluster_ok || flow_ok) && n_meas) CU(cudaMemsetAsync(h->elog_d, 0, sizeof(long long) * (size_t)nc * h->elog_cap, h->stream));
-    if ((cluster_ok || flow_ok) && n_act) CU(cudaMemsetAsync(h->alog_d, 0, sizeof(long long) * (size_t)nc * h->alog_cap, h->stream));
+    const bool cluster_ok = h->clusterp.enabled && !s->correlator_every && !s->difference_every;
+    if (cluster_ok && n_meas) CU(cudaMemsetAsync(h->elog_d, 0, sizeof(long long) * (size_t)nc * h->elog_cap, h->stream));
+    if (cluster_ok && n_act) CU(cudaMemsetAsync(h->alog_d, 0, sizeof(long long) * (size_t)nc * h->alog_cap, h->stream));
 
     uint64_t cycle = 1;
     for (uint32_t f : {s->energy_every, s->normalize_every, s->action_every, s->correlator_every, s->difference_every})
@@ -1934,43 +1927,6 @@ static lqft_status run_impl(lqft_handle* h, const lqft_schedule* s, const lqft_r
                               h->offset_d, h->ncentre_d, h->elog_d, h->alog_d, h->acc_d, h->stream));
             h->launches += 1;
             step = seg_end;
-        }
-        while (h->narrow_active && flow_ok && seg_end - step >= 2) {
-            // one persistent launch (kernels_flow.cuh) for the steps up to and including the next one whose correlator
-            // or difference plot is due; those two are measured after it (they depend on height differences only, so
-            // the normalize of that step, already done inside the launch, does not change them)
-            uint64_t stop = seg_end;
-            for (uint32_t f : {s->correlator_every, s->difference_every})
-                if (f) stop = std::min<uint64_t>(stop, (step + f - 1) / f * f + 1);
-            FlowArgs a{};
-            a.g = h->gn;
-            a.sweep_base = s->sweep_base;
-            a.first_step = step;
-            a.n_steps = stop - step;
-            a.energy_every = s->energy_every;
-            a.action_every = s->action_every;
-            a.normalize_every = s->normalize_every;
-            a.elog_cap = h->elog_cap;
-            a.alog_cap = h->alog_cap;
-            a.e_slot0 = (uint32_t)lqft_run_measurements(s->first_step, step - s->first_step, s->energy_every);
-            a.a_slot0 = (uint32_t)lqft_run_measurements(s->first_step, step - s->first_step, s->action_every);
-            a.max_thr = h->max_thr;
-            CU(flow_launch(h->flowp, h->narrowp, a, h->any_wilson, h->count_accepts, h->narrow[0], h->narrow[1], h->chains_d, h->chains_h[0],
-                           h->thr_d, h->offset_d, h->ncentre_d, h->elog_d, h->alog_d, h->acc_d, h->stream));
-            h->launches += 1;
-            step = stop;
-            const uint64_t last = stop - 1;
-            if (s->correlator_every && last % s->correlator_every == 0) {
-                Measure m;
-                m.due = kObsCorr;
-                m.moments = m.fold = true;
-                m.sweep = s->sweep_base + last;
-                m.n = nc;
-                m.fin = h->run_fin;
-                ST(launch_measure(h, m));
-            }
-            if (s->difference_every && last % s->difference_every == 0)
-                for (uint32_t c = 0; c < nc; ++c) ST(launch_difference(h, c));
         }
         // slabs replay graphs only on the narrow copy: the numbers of its flips live in device memory
         const bool use_graph = graph_ok && (h->g.ghost == 0 || h->narrow_active);
@@ -2142,7 +2098,7 @@ extern "C" lqft_status lqft_plan_info(lqft_handle* h, char* buf, size_t cap) {
     if (!h || !buf || cap == 0) return fail(LQFT_ERR_INVALID, "null argument");
     ST(use_device(h));
     ST(upload_params(h));
-    const char* path = h->is64 ? "f64" : h->resident_ok ? "resident" : (h->flowp.enabled && (h->flow_first || !h->clusterp.enabled)) ? "flow" : h->clusterp.enabled ? "cluster" : h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream"
+    const char* path = h->is64 ? "f64" : h->resident_ok ? "resident" : h->clusterp.enabled ? "cluster" : h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream"
                        : h->tiled.enabled ? "march" : ((h->g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) ? "vec4" : "generic");
     uint32_t chunks = 0, rows = 0, groups = 0;
     int occ = 0;
@@ -2151,11 +2107,6 @@ extern "C" lqft_status lqft_plan_info(lqft_handle* h, char* buf, size_t cap) {
         rows = (h->g.Y + chunks - 1) / chunks;
         groups = narrow_groups(h->narrowp, h->g.Tl);
         occ = narrow_occupancy(h->narrowp, h->any_wilson, false, false, narrow_warps(h->narrowp, h->g.Tl));
-    }
-    if (h->flowp.enabled && (h->flow_first || !h->clusterp.enabled)) {
-        chunks = h->flowp.n_chunks;
-        rows = (h->g.Y + chunks - 1) / chunks;
-        occ = (int)h->flowp.blocks_per_sm;
     }
     snprintf(buf, cap, "path=%s chunks=%u rows_per_chunk=%u plane_blocks=%u blocks_per_sm=%d ghost_depth=%u p2p=%d storage=%s "
              "i32_allocated=%d budget=%u", path, chunks, rows, groups, occ, h->narrowp.enabled ? h->gn.ghost : h->g.ghost,
