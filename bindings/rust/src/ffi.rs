@@ -31,6 +31,7 @@ pub struct lqft_config {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy, Default)]
 pub struct lqft_schedule {
     pub sweep_base: u64,
     pub first_step: u64,

@@ -19,6 +19,7 @@ pub struct Gpu {
     raw: *mut lqft_handle,
     pub n_chains: u32,
     pub t: usize,
+    pub sites: usize,
 }
 
 impl Gpu {
@@ -30,7 +31,7 @@ impl Gpu {
         };
         let mut raw = std::ptr::null_mut();
         check(unsafe { lqft_create(&cfg, &mut raw) })?;
-        Ok(Gpu { raw, n_chains, t: size[2] })
+        Ok(Gpu { raw, n_chains, t: size[2], sites: size[0] * size[1] * size[2] })
     }
     pub fn raw(&self) -> *mut lqft_handle { self.raw }
     pub fn set_chain(&self, chain: u32, temp: f64, seed: u64, width: usize, height: usize) -> Result<(), Box<dyn Error>> {
@@ -81,6 +82,14 @@ impl Gpu {
         let mut c = vec![0f64; self.t];
         check(unsafe { lqft_correlator(self.raw, 0, std::ptr::null(), reps as u32, sweep, c.as_mut_ptr()) })?;
         Ok(c)
+    }
+    /// DifferencePlotOutputData::plot (outputdata.rs:258-276): mean[3][sites] of chain `chain` and the number of
+    /// configurations accumulated by `difference_every` / lqft_difference_update.
+    pub fn difference_read(&self, chain: u32) -> Result<(Vec<f64>, u64), Box<dyn Error>> {
+        let mut mean = vec![0f64; 3 * self.sites];
+        let mut count = 0u64;
+        check(unsafe { lqft_difference_read(self.raw, chain, mean.as_mut_ptr(), &mut count) })?;
+        Ok((mean, count))
     }
     pub fn download(&self, values: &mut [i32]) -> Result<(), Box<dyn Error>> {
         check(unsafe { lqft_download(self.raw, 0, values.as_mut_ptr() as *mut _) })
