@@ -651,7 +651,9 @@ inline cudaError_t narrow_prepare(NarrowPlan& p, const Geom& g, uint32_t n_chain
 // Blocks along the planes come in pairs (even / odd planes): as few pairs as kN16Warps warps per block allow, then as
 // few warps per block as those pairs need.  (Choosing the block size that leaves the fewest surplus warps — 17 pairs
 // of 4-warp blocks for the 270 planes of a slab with ghost planes in flight instead of 9 pairs of 8 — executes 5 %
-// fewer instructions and still runs 2 % slower: measured.)
+// fewer instructions and still runs 2 % slower: measured.  So does compiling the slab launches for 9-warp blocks — 270
+// planes in 8 pairs, 592 blocks of 7 rows instead of 576 of 8 — at the 56 registers that keeps 4 blocks per SM: 5 %
+// slower on 2 GPUs, the spills cost more than the eighth row.)
 inline uint32_t narrow_plane_warps(const NarrowPlan& p, uint32_t n_planes) {  // warps one parity needs
     const uint32_t w = ((n_planes + 1) / 2 + p.ppw() - 1) / p.ppw();
     return w < 1 ? 1 : w;
