@@ -142,6 +142,9 @@ def run_reference(args, rank: int, world: int):
                        f"i32 heights, beta={BETA}, lexicographic Metropolis, {per_step} sweeps per step; a bounded sample of "
                        f"the {X}x{Y}x{T_PER_GPU * args.gpus} workload of the b200 arm")
     cfg["lattice_per_core"] = [X, Y, t_sample]
+    cfg["sweeps_per_step"] = per_step
+    for k in ("decomposition", "l2", "storage"):  # properties of the b200 arm's run, not of this one
+        cfg.pop(k, None)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
