@@ -381,6 +381,38 @@ def config5_leg(world: int, rank: int, device: int, barrier):
     return out
 
 
+def replicas_leg(world: int, rank: int, device: int, barrier):
+    """The reference's own parallelism (sim.rs:90-93, action_sim.rs:60-71: one chain per rayon worker) over N GPUs:
+    a coupling scan of 64 chains of 64^3 per GPU, dealt round-robin (distributed.replica_engine), nothing exchanged.
+    Timed on the device, max over the ranks; the energies of the whole scan are gathered once at the end."""
+    import torch
+    import torch.distributed as dist
+    from lattice_qft_b200 import distributed as D
+    n = 64 * world
+    params = [(0.20 + 0.005 * (c % 64), 0xC0FFEE + c, 0, 0) for c in range(n)]
+    eng, mine = D.replica_engine(64, 64, 64, params, device=device)
+    eng.init_hot()
+    eng.run(200, energy_every=10)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", device))
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    reps = 3
+    for _ in range(reps):
+        e_obs, _, _ = eng.run(200, sweep_base=200, energy_every=10)
+    b.record(stream)
+    barrier()
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    table = D.gather_replicas(e_obs, mine, n)
+    eng.close()
+    rate = n * 64.0**3 * 200 * reps / (float(ms.item()) * 1e-3)
+    return {"chains": n, "chains_per_gpu": 64, "lattice_per_chain": [64, 64, 64], "site_updates_per_s": rate,
+            "per_gpu_updates_per_s": rate / world, "energies_gathered": int(table.shape[0] * table.shape[1]),
+            "what": "replicas only: chains dealt round-robin to the ranks, no data-path collective"}
+
+
 def workload_config(n_gpus: int):
     t = T_PER_GPU * n_gpus
     return {
@@ -539,6 +571,8 @@ def main():
         c5 = config5_leg(world, rank, local_rank, barrier)
         other = other_configs(local_rank) if world == 1 else {}
         other["config5_1024x1024x128g"] = c5
+        if world > 1:
+            other["coupling_scan_replicas_64x64^3_per_gpu"] = replicas_leg(world, rank, local_rank, barrier)
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         n_sweep_launches = 2 * SWEEPS_PER_STEP * args.steps  # per rank, dominant kernel: half-sweep

@@ -56,6 +56,39 @@ def chains_of_rank(n_chains: int, rank: int, world_size: int) -> List[int]:
     return list(range(rank, n_chains, world_size))
 
 
+def replica_engine(x: int, y: int, t: int, params: Sequence[Sequence], device: int = 0, flags: int = 0):
+    """Engine holding this rank's share of a scan of independent chains — sim.rs:90-93 / action_sim.rs:60-71 hand the
+    scan points to rayon workers; here `params[c] = (beta, seed, wilson_width, wilson_height)` of chain c goes to rank
+    c mod world_size.  Nothing is exchanged between the ranks.  Returns (engine, global ids of its chains) or
+    (None, []) for a rank without work."""
+    rank, ws = world()
+    mine = chains_of_rank(len(params), rank, ws)
+    if not mine:
+        return None, []
+    eng = Engine(x, y, t, n_chains=len(mine), device=device, flags=flags)
+    for slot, c in enumerate(mine):
+        beta, seed, *wil = params[c]
+        eng.set_chain(slot, beta, seed, *(wil if wil else (0, 0)))
+    return eng, mine
+
+
+def gather_replicas(per_chain: np.ndarray, mine: Sequence[int], n_chains: int) -> np.ndarray:
+    """Rows of `per_chain` (this rank's chains, in slot order) put at their global chain ids, summed over the ranks:
+    every rank gets the [n_chains, ...] table of the whole scan."""
+    import torch
+    import torch.distributed as dist
+    per_chain = np.asarray(per_chain, dtype=np.float64)
+    full = np.zeros((n_chains,) + per_chain.shape[1:], dtype=np.float64)
+    for slot, c in enumerate(mine):
+        full[c] = per_chain[slot]
+    if world()[1] > 1:
+        on_gpu = dist.get_backend() == "nccl"
+        tt = torch.from_numpy(full).cuda() if on_gpu else torch.from_numpy(full)
+        dist.all_reduce(tt)
+        full = tt.cpu().numpy()
+    return full
+
+
 def scatter_slab(values: np.ndarray, x: int, y: int, t: int, rank: int, world_size: int) -> np.ndarray:
     """This rank's slab of a global lexicographic field (t is the slowest index: a contiguous range)."""
     t0, nt = E.slab(t, world_size, rank)

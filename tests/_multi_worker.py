@@ -65,6 +65,32 @@ def check(size, beta, seed, wilson, n_sweeps, flags=0):
     dist.barrier()
 
 
+def check_replicas(size, n_chains, n_steps):
+    """Replicas only (sim.rs:90-93): the chains of a coupling / Wilson scan dealt round-robin to the ranks give the
+    energies of ONE handle holding all of them."""
+    rank, ws = D.world()
+    X, Y, T = size
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    params = [(0.20 + 0.01 * c, 100 + c, (5 * c) % X, (3 * c) % T) for c in range(n_chains)]
+    eng, mine = D.replica_engine(X, Y, T, params, device=dev)
+    e_int = np.zeros((0, D.E.run_measurements(0, n_steps, 2)))
+    if eng is not None:
+        eng.init_hot()
+        _, e_int, _ = eng.run(n_steps, energy_every=2, normalize_every=10)
+        eng.close()
+    table = D.gather_replicas(e_int, mine, n_chains)
+    if rank == 0:
+        ref = Engine(X, Y, T, n_chains=n_chains, device=dev)
+        for c, (beta, seed, w, h) in enumerate(params):
+            ref.set_chain(c, beta, seed, w, h)
+        ref.init_hot()
+        _, r_int, _ = ref.run(n_steps, energy_every=2, normalize_every=10)
+        ref.close()
+        assert (table == r_int.astype(np.float64)).all(), "replica energies differ from the single handle"
+        print(f"ok replicas {size} chains={n_chains} ws={ws}", flush=True)
+    dist.barrier()
+
+
 def main():
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
@@ -78,6 +104,8 @@ def main():
     check((256, 4, 40 * ws), 0.27, 13, (200, 50), 5)        # narrow kernel, several plane groups per slab, Wilson sheet
     check((256, 16, 4 * ws), 0.25, 11, (0, 0), 3, flags=2)  # scalar kernels on slabs
     check((512, 8, 2 * ws), 0.25, 12, (100, 3), 2)
+    check_replicas((64, 16, 16), 2 * ws + 1, 12)             # uneven deal: rank 0 holds one chain more
+    check_replicas((16, 16, 16), max(ws - 1, 1), 10)         # fewer chains than ranks: one rank has no work
     dist.destroy_process_group()
 
 

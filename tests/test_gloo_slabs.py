@@ -46,7 +46,14 @@ def _worker(rank, ws, port, out_path):
     total_acc = D.allreduce_sum([acc])[0]
     gathered = D.gather_slabs(buf[plane:(nt + 1) * plane])
     # replicas: chains dealt round-robin, nothing exchanged
-    assert D.chains_of_rank(7, rank, ws) == list(range(rank, 7, ws))
+    mine = D.chains_of_rank(7, rank, ws)
+    assert mine == list(range(rank, 7, ws))
+    # ... but the results: each rank's rows land at their global chain ids (oracle energies as the per-chain payload)
+    lat = O.Lattice([X, Y, T])
+    rows = np.array([[O.integer_energy(lat, seeded_field(X * Y * T, seed=c))[0], c] for c in mine], dtype=np.float64).reshape(len(mine), 2)
+    table = D.gather_replicas(rows, mine, 7)
+    assert table.shape == (7, 2) and (table[:, 1] == np.arange(7)).all()
+    assert all(table[c, 0] == O.integer_energy(lat, seeded_field(X * Y * T, seed=c))[0] for c in range(7))
     # the NCCL-id bootstrap path works on any backend
     got = D.broadcast_bytes(bytes(range(128)) if rank == 0 else None, 128)
     assert got == bytes(range(128))
