@@ -226,6 +226,7 @@ struct SlabArgs {
     uint32_t lo_stride8, hi_stride8;  // their uint4 per chain
     uint32_t lo_plane, hi_plane;      // storage plane there of my local plane 0 / of my local plane Tl - depth
     uint32_t depth;          // planes pushed per side
+    uint32_t extra;          // ghost planes per side this half-sweep updates as well (ghost tasks, below)
     uint32_t sync;           // 1: raise my flag at both neighbours and wait for theirs before touching a ghost plane
     HaloSync* mine;
     HaloSync* lo_sync;
@@ -256,6 +257,16 @@ __device__ __forceinline__ void slab_flip(const SlabArgs& sl, bool first_block, 
         }
     }
     __syncthreads();  // also where the compiler sees the block converge again: without it the sweep loop is compiled as divergent code
+}
+
+// The wait of slab_flip on its own: for a block that touches ghost planes only in its ghost tasks, after its own rows.
+__device__ __forceinline__ void slab_wait(const SlabArgs& sl) {
+    if (threadIdx.x == 0) {
+        const unsigned long long seq = (sl.seq_base ? *sl.seq_base : 0ull) + sl.seq_off;
+        halo_wait(&sl.mine->from_lo, seq, &sl.mine->error);
+        halo_wait(&sl.mine->from_hi, seq, &sl.mine->error);
+    }
+    __syncthreads();
 }
 
 template <int XQ, bool WILSON, bool COUNT, bool SINGLE, bool SLAB, bool MEAS>
@@ -300,49 +311,41 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     int accepted = 0;
     // (An early exit of warps without a live plane slot — `if (__all_sync(~0u, pl_raw >= n_planes)) return;` — compiles
     // without divergence handling but moves the Philox keys out of the uniform registers: 3.6 % slower at 256^3.)
-    const bool live = pl_raw < n_planes;              // surplus plane slots: plane 0 of the range, stores off
+    bool live = pl_raw < n_planes;                    // surplus plane slots: plane 0 of the range, stores off
     const uint32_t pl = live ? pl_raw : 0u;
     {
-        const uint32_t tl = pl < n_first ? (uint32_t)tl_first + pl : (uint32_t)tl_second + (pl - n_first);
-        const uint32_t tg = (g.t0 + g.T + tl) % g.T;
-        const bool owned = live && tl < g.Tl;
+        // The plane of a thread and what follows from it are variables set by set_plane: a SLAB launch first runs its
+        // ghost tasks on other planes (below); everywhere else they are assigned once.
         const uint32_t kq = SEGS ? seg * 32u + lane : lane & (LPR - 1u);  // uint4 column of this thread within the row
         const uint32_t planeq = g.Y * ROWQ;
         const uint32_t cq = chain * (uint32_t)(g.chain_stride / 8);
-        const uint32_t r_own = cq + plane_self(g, tl) * planeq;  // row 0 of this plane
-        const uint32_t b_own = r_own + kq;
-        const uint32_t b_ta = cq + plane_above(g, tl) * planeq + kq, b_tb = cq + plane_below(g, tl) * planeq + kq;
         uint4* const q_own = reinterpret_cast<uint4*>(own_base);
         const uint4* const q_oth = reinterpret_cast<const uint4*>(oth_base);
+        const uint32_t* const w_oth = reinterpret_cast<const uint32_t*>(oth_base);
+        uint32_t tl, tg, r_own, b_own, b_ta, b_tb, e_right, e_left, grp_base;
+        bool owned, wil_plane;
+        auto set_plane = [&](const uint32_t t) {
+            tl = t;
+            tg = (g.t0 + g.T + tl) % g.T;
+            r_own = cq + plane_self(g, tl) * planeq;  // row 0 of this plane
+            b_own = r_own + kq;
+            b_ta = cq + plane_above(g, tl) * planeq + kq;
+            b_tb = cq + plane_below(g, tl) * planeq + kq;
+            // 32-bit word of the other-colour row that holds the x neighbour across the segment edge (SEGS > 1):
+            // first word of the column to the right / last word of the column to the left, periodic in the row
+            e_right = (r_own + (kq + 1u) % ROWQ) * 4u;
+            e_left = (r_own + (kq + ROWQ - 1u) % ROWQ) * 4u + 3u;
+            grp_base = tg * g.Y * (2u * ROWQ) + kq * 2u;
+            wil_plane = WILSON && tg < cd.wil_h;
+        };
         // PUSH: this plane's rows also go to a neighbour's other ghost set (a thin slab may owe both neighbours)
         uint4* q_lo = nullptr;
         uint4* q_hi = nullptr;
-        if (SLAB) {
-            if (owned && sl.depth) {
-                if (tl < sl.depth && sl.lo)
-                    q_lo = reinterpret_cast<uint4*>(sl.lo) + (chain * sl.lo_stride8 + (sl.lo_plane + tl) * planeq + kq);
-                if (tl + sl.depth >= g.Tl && sl.hi)
-                    q_hi = reinterpret_cast<uint4*>(sl.hi) + (chain * sl.hi_stride8 + (sl.hi_plane + (tl + sl.depth - g.Tl)) * planeq + kq);
-            }
-        }
-        const uint32_t* const w_oth = reinterpret_cast<const uint32_t*>(oth_base);
-        // 32-bit word of the other-colour row that holds the x neighbour across the segment edge (SEGS > 1):
-        // first word of the column to the right / last word of the column to the left, periodic in the row
-        const uint32_t e_right = (r_own + (kq + 1u) % ROWQ) * 4u, e_left = (r_own + (kq + ROWQ - 1u) % ROWQ) * 4u + 3u;
         const RoundKeys rk = make_round_keys(cd.k0, cd.k1);
-        uint32_t y = y0;
-        const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
-        uint4 wa = __ldg(q_oth + (b_own + ym * ROWQ)), wb = __ldg(q_oth + (b_own + y * ROWQ)), wc;
-        // x parity of the first row, no thread-dependent term; the second range starts at the parity the first one
-        // would have continued with (launch_sweep: Tl is even)
-        uint32_t p = (y0 + g.t0 + (uint32_t)tl_first + (blockIdx.y & 1u) + (uint32_t)colour) & 1u;
+        uint32_t y, p;
+        uint4 wa, wb, wc;
         const uint32_t src_r = (lane & ~(LPR - 1u)) | ((lane + 1u) & (LPR - 1u)), src_l = (lane & ~(LPR - 1u)) | ((lane - 1u) & (LPR - 1u));
-        const uint32_t grp_base = tg * g.Y * (2u * ROWQ) + kq * 2u;
-        const bool wil_plane = WILSON && tg < cd.wil_h;
         const uint32_t y_one = 1u % g.Y;
-        // a warp without a live plane slot leaves after one row (the vote keeps the trip count warp uniform for the
-        // compiler; an outright early exit costs the uniform registers, see above)
-        uint32_t n = __all_sync(0xffffffffu, pl_raw >= n_planes) ? 1u : y1 - y0;
 #define LQFT_N16_STEP(OM, OC, ON, PUSH, MEAS)                                                                               \
     {                                                                                                                    \
         const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;                                                                  \
@@ -385,6 +388,30 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         y = yn;                                                                                                          \
         p ^= 1u;                                                                                                         \
     }
+        // the thread's own plane
+        live = pl_raw < n_planes;
+        set_plane(pl < n_first ? (uint32_t)tl_first + pl : (uint32_t)tl_second + (pl - n_first));
+        owned = live && tl < g.Tl;
+        if (SLAB) {
+            if (owned && sl.depth) {
+                if (tl < sl.depth && sl.lo)
+                    q_lo = reinterpret_cast<uint4*>(sl.lo) + (chain * sl.lo_stride8 + (sl.lo_plane + tl) * planeq + kq);
+                if (tl + sl.depth >= g.Tl && sl.hi)
+                    q_hi = reinterpret_cast<uint4*>(sl.hi) + (chain * sl.hi_stride8 + (sl.hi_plane + (tl + sl.depth - g.Tl)) * planeq + kq);
+            }
+        }
+        y = y0;
+        {
+            const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
+            wa = __ldg(q_oth + (b_own + ym * ROWQ));
+            wb = __ldg(q_oth + (b_own + y * ROWQ));
+        }
+        // x parity of the first row, no thread-dependent term; the second range starts at the parity the first one
+        // would have continued with (launch_sweep: Tl is even)
+        p = (y0 + g.t0 + (uint32_t)tl_first + (blockIdx.y & 1u) + (uint32_t)colour) & 1u;
+        // a warp without a live plane slot leaves after one row (the vote keeps the trip count warp uniform for the
+        // compiler; an outright early exit costs the uniform registers, see above)
+        uint32_t n = __all_sync(0xffffffffu, pl_raw >= n_planes) ? 1u : y1 - y0;
         // only the blocks whose group holds one of the first / last `depth` owned planes carry the push stores
         if (SLAB && sl.depth != 0u && grp_hi > 0 && grp_lo < (int32_t)g.Tl &&
             (grp_lo < (int32_t)sl.depth || grp_hi > (int32_t)(g.Tl - sl.depth))) {
@@ -413,6 +440,39 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
                 if (--n == 0) break;
                 LQFT_N16_STEP(wc, wa, wb, false, false)
                 if (--n == 0) break;
+            }
+        }
+        // Ghost tasks (slabs).  The ghost planes this half-sweep updates redundantly (sl.extra per side) do not get
+        // blocks of their own: 14 planes beside 256 owned ones made a ninth, mostly empty pair of plane groups — 576
+        // blocks of 8 rows where the owned planes alone fill 592 blocks of 7 (and 130 planes of 1024^2 nine pairs
+        // where 128 fill eight).  Instead their rows are dealt, one (plane slot, row) at a time, to the warps that
+        // hold the same y chunk and plane parity: task k goes to warp k mod W of the W warps of this chunk and parity,
+        // which runs it as a row step with a cold register window (rows y - 1 and y loaded instead of kept) after its
+        // own rows.  (Before its own rows: 2 - 3 % slower, measured on 2 GPUs — every block then waits for the
+        // neighbours' flags at the start of a period instead of after its rows.)
+        if (SLAB) {
+            if (sl.extra != 0u) {
+                const bool at_edge = grp_lo <= 0 || grp_hi >= (int32_t)g.Tl;
+                if (sl.sync && !at_edge) slab_wait(sl);  // (edge blocks have waited in the prologue)
+                const uint32_t E = sl.extra, par = blockIdx.y & 1u;
+                const uint32_t n_lo = (E + par) >> 1;                      // ghost planes of this parity below plane 0
+                const uint32_t nw = blockDim.x >> 5, W = (gridDim.y >> 1) * nw;
+                const uint32_t wid = (blockIdx.y >> 1) * nw + __reduce_min_sync(0xffffffffu, warp);  // uniform for the compiler
+                const uint32_t rows = y1 - y0, n_tasks = ((E + PPW - 1u) / PPW) * rows;
+                owned = false;
+#pragma unroll 1
+                for (uint32_t k = wid; k < n_tasks; k += W) {
+                    const uint32_t s = k / rows, q = s * PPW + lane / LPR;   // ghost plane number q of this parity
+                    live = q < E;
+                    // local plane: -(2 q + 2 - par) below, Tl + 2 (q - n_lo) + par above (Tl is even)
+                    set_plane(!live ? 0u : (q < n_lo ? (uint32_t)(-(int32_t)(2u * q + 2u - par)) : g.Tl + 2u * (q - n_lo) + par));
+                    y = y0 + (k - s * rows);
+                    p = (y + g.t0 + par + (uint32_t)colour) & 1u;
+                    const uint32_t yb = (y == 0) ? g.Y - 1 : y - 1;
+                    wa = __ldg(q_oth + (b_own + yb * ROWQ));
+                    wb = __ldg(q_oth + (b_own + y * ROWQ));
+                    LQFT_N16_STEP(wa, wb, wc, false, false)
+                }
             }
         }
 #undef LQFT_N16_STEP

@@ -870,12 +870,14 @@ static void flip_args(lqft_handle* h, SlabArgs& sl) {
 // period (the kernel's prologue swaps the ghost sets with the neighbours), `push` sends the boundary planes of this
 // colour into the neighbours' other set.
 static lqft_status launch_half_narrow(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr, int32_t first,
-                                      uint32_t n_planes, bool flip = false, bool push = false, bool measure = false) {
+                                      uint32_t n_planes, bool flip = false, bool push = false, bool measure = false,
+                                      uint32_t extra = 0) {
     NarrowArgs a{h->gn, colour, sweep, ctr, first, n_planes, 0, n_planes, h->cfg.n_chains, h->narrow[colour],
                  h->narrow[colour ^ 1], h->chains_d, h->chains_h[0], h->thr_d, h->acc_d, h->max_thr, h->any_wilson, h->count_accepts,
                  h->stream, !(h->cfg.flags & LQFT_FLAG_NO_PDL)};
-    if (flip || push) {
+    if (flip || push || extra) {
         a.slab = true;
+        a.sl.extra = extra;  // ghost planes per side updated along with the owned ones (ghost tasks of k_sweep_n16)
         if (flip) flip_args(h, a.sl);
         if (push) {
             const uint32_t d = h->gn.ghost, next = h->gn.gbuf ^ 1u;
@@ -987,7 +989,7 @@ static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* 
             const uint32_t extra = h->nvalid - 1;  // ghost planes per side this half-sweep may still update
             const bool push = h->nvalid <= 2;       // nvalid 2: colour 0 for the last time in this period, 1: colour 1
             h->nvalid -= 1;
-            ST(launch_half_narrow(h, colour, sweep, ctr, -(int32_t)extra, g.Tl + 2 * extra, flip, push));
+            ST(launch_half_narrow(h, colour, sweep, ctr, 0, g.Tl, flip, push, false, extra));
             if (h->nvalid == 0) h->next_ready = true;
         }
         return LQFT_OK;
