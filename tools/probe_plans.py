@@ -1,0 +1,30 @@
+"""Times the secondary configs on the cluster-resident path and on the launch path (LQFT_FLAG_NO_RESIDENT) side by side."""
+import sys, time
+sys.path.insert(0, ".")
+import torch
+from lattice_qft_b200 import Engine, _lib
+
+
+def timed(eng, fn, reps):
+    stream = torch.cuda.ExternalStream(eng.stream())
+    fn(); eng.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(reps):
+        fn()
+    b.record(stream); eng.synchronize()
+    return a.elapsed_time(b) * 1e-3 / reps
+
+
+shapes = [(w, h) for h in (16, 32, 64) for w in (10, 21, 32, 42, 53)] + [(0, 0)]
+for name, n, every, wil in (("wilson16", 16, 1, True), ("scan16", 16, 10, False), ("scan32", 32, 10, False), ("scan64", 64, 10, False)):
+    for flags in (0, _lib.FLAG_NO_RESIDENT):
+        eng = Engine(64, 64, 64, n_chains=n, flags=flags)
+        for c in range(n):
+            w, h = shapes[c % 16] if wil else (0, 0)
+            eng.set_chain(c, 0.26 if wil else 0.20 + 0.005 * c, 0xBEEF + c, w, h)
+        eng.init_hot()
+        eng.run(100, energy_every=0)
+        sec = timed(eng, lambda: eng.run(100, sweep_base=100, energy_every=every), 3)
+        print(f"{name} flags={flags} path={eng.plan_info()['path']} {n * 64**3 * 100 / sec:.4g} upd/s", flush=True)
+        eng.close()
