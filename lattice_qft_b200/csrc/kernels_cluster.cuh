@@ -21,7 +21,6 @@ namespace lqft {
 
 constexpr int kClusterMaxThreads = 768;              // 24 warps at 80 registers: the run loop keeps more state live than a half-sweep launch
 constexpr int kClusterMaxCtas = 8;                   // portable cluster size
-constexpr size_t kClusterSmemTwo = 100u << 10;       // field bytes per CTA up to which two CTAs share an SM
 
 struct ClusterArgs {
     Geom g;                // geometry of the 16-bit arrays (one GPU: ghost == 0)
@@ -255,11 +254,14 @@ inline const void* cluster_kernel(int xq, bool w, bool c) {
     return nullptr;
 }
 
-// One chain per cluster of 1, 2, 4 or 8 CTAs (T divisible), X = 16 ... 128.  The path is taken when every chain of the
-// handle is resident at once, with the largest cluster that allows it: CTAs that fit twice per SM (384 threads each)
-// first — measured on 16 chains of 64^3: 8 x 384 threads beats 4 x 768 and 8 x 768, of which only 15 clusters fit at a
-// time — else CTAs that fit once per SM (768 threads).  With more chains than fit at once the kernel runs them in
-// waves at about the rate of the launch path (64 chains of 64^3: 0.95x), so those handles stay on k_sweep_n16.
+// One chain per cluster of 1, 2, 4 or 8 CTAs (T divisible), X = 16 ... 128, one 768-thread CTA per SM.  Where the path
+// pays was measured against the launch path (k_sweep_n16 with the energy inside the half-sweep), chains of 64^3,
+// site updates/s, cluster / launch:  1 chain 3.1 / 4.7e10,  4: 1.25 / 1.42e11,  8: 2.49 / 2.20e11,  12: 3.74 / 3.01e11,
+// 16 (two 384-thread CTAs per SM, as only 15 clusters of 8 x 768 threads fit the GPCs): 2.97 / 3.96e11,  32: 5.05 /
+// 5.23e11;  one chain of 128 x 64 x 64: 3.7 / 8.3e10.  A few chains leave most SMs idle in a cluster while the launch
+// path spreads them over the device; many chains fill the device either way and the launch path has more warps per SM.
+// So: every chain resident at once, the largest cluster that allows it, and the clusters together on at least 3/8 of
+// the SMs; otherwise the handle stays on k_sweep_n16.
 inline cudaError_t cluster_prepare(ClusterPlan& p, const Geom& g, uint32_t n_chains, int sm_count, uint32_t max_thr,
                                    size_t smem_optin, bool force_off) {
     p = ClusterPlan{};
@@ -269,7 +271,6 @@ inline cudaError_t cluster_prepare(ClusterPlan& p, const Geom& g, uint32_t n_cha
     const size_t budget = smem_optin > (12u << 10) ? smem_optin - (12u << 10) : 0;  // table + reduction scratch + slack
     const size_t plane_bytes = (size_t)g.plane * sizeof(uint16_t);
     uint32_t pick = 0;
-    bool two_per_sm = false;
     if (const char* e = getenv("LQFT_CLUSTER_CTAS")) {  // tests: force the cluster size (must divide T and fit)
         const uint32_t c = (uint32_t)atoi(e);
         if (c >= 1 && c <= (uint32_t)kClusterMaxCtas && (c & (c - 1)) == 0 && g.T % c == 0 &&
@@ -277,25 +278,46 @@ inline cudaError_t cluster_prepare(ClusterPlan& p, const Geom& g, uint32_t n_cha
             pick = c;
         else
             return cudaSuccess;
-        two_per_sm = 2 * (size_t)(g.T / c + 2) * plane_bytes <= kClusterSmemTwo && (uint64_t)c * n_chains > (uint64_t)sm_count;
     }
-    for (int pass = 0; pass < 2 && !pick; ++pass)
-        for (uint32_t c = (uint32_t)kClusterMaxCtas; c >= 1; c /= 2) {  // as many SMs per chain as stay resident together
-            if (g.T % c) continue;
-            const size_t need = 2 * (size_t)(g.T / c + 2) * plane_bytes;
-            const uint64_t slots = (uint64_t)sm_count * (pass == 0 ? 2 : 1) * 7 / 8;  // cluster placement leaves some SMs out
-            if (need <= (pass == 0 ? kClusterSmemTwo : budget) && (uint64_t)c * n_chains <= slots) {
-                pick = c;
-                two_per_sm = pass == 0;
-                break;
-            }
+    // clusters of c CTAs that the device holds at once (the GPC layout decides, so ask: 15 of 8 x 768 threads on a B200)
+    auto resident = [&](uint32_t c, size_t smem) -> int {
+        const void* fn = cluster_kernel((int)(g.X / 16), true, true);  // the instantiation with the most registers
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
         }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(c, n_chains, 1);
+        cfg.blockDim = dim3(kClusterMaxThreads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = c;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        return n;
+    };
+    for (uint32_t c = (uint32_t)kClusterMaxCtas; c >= 1 && !pick; c /= 2) {  // as many SMs per chain as stay resident together
+        if (g.T % c) continue;
+        const size_t need = 2 * (size_t)(g.T / c + 2) * plane_bytes;
+        if (need > budget || (uint64_t)c * n_chains > (uint64_t)sm_count) continue;
+        if ((uint64_t)c * n_chains * 8 < (uint64_t)sm_count * 3) return cudaSuccess;  // too few SMs busy: launch path
+        if (resident(c, need) < (int)n_chains) return cudaSuccess;  // (smaller clusters of more chains measured slower still)
+        pick = c;
+    }
     if (!pick) return cudaSuccess;
     p.xq = (int)(g.X / 16);
     p.n_cta = pick;
     p.tp = g.T / pick;
     p.smem = 2 * (size_t)(p.tp + 2) * plane_bytes;
-    p.threads = two_per_sm ? (uint32_t)kClusterMaxThreads / 2 : (uint32_t)kClusterMaxThreads;
+    p.threads = (uint32_t)kClusterMaxThreads;
     if (const char* e = getenv("LQFT_CLUSTER_THREADS")) p.threads = (uint32_t)atoi(e);  // experiments
     const uint64_t units = (uint64_t)p.tp * g.Y * p.xq;  // 8-site rows per colour and CTA
     while (p.threads > 96u && units < p.threads) p.threads /= 2;

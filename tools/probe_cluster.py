@@ -1,9 +1,9 @@
-"""Small driver for ncu: one k_run_cluster launch (Wilson scan shape: 16 chains of 64^3, energy after every sweep)."""
+"""Small driver for ncu: one k_run_cluster launch (Wilson sheets on 12 chains of 64^3, energy after every sweep)."""
 import sys
 sys.path.insert(0, ".")
 from lattice_qft_b200 import Engine
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 shapes = [(w, h) for h in (16, 32, 64) for w in (10, 21, 32, 42, 53)] + [(0, 0)]
 eng = Engine(64, 64, 64, n_chains=n)
 for c in range(n):
