@@ -17,6 +17,12 @@ cap r2_n16_slab1024 k_sweep_n16 16 python tools/probe_slab.py
 python tools/probe_obs.py energy || exit 1
 cap r2_observe_256 k_observe_rows 0 python tools/probe_obs.py energy
 cap r2_n16_meas_256 k_sweep_n16 9 python tools/probe_obs.py energy
-python tools/probe_cluster.py 16 || exit 1
-cap r2_cluster_16x64 k_run_cluster 0 python tools/probe_cluster.py 16
+python tools/probe_cluster.py 12 || exit 1
+cap r2_cluster_12x64 k_run_cluster 0 python tools/probe_cluster.py 12
 ls -la gpurun_out | tail -12
+# warm-cache capture of the headline kernel (what the timed run sees: the field stays in L2)
+name=r2_n16_256_warm
+ncu --set full --clock-control none --cache-control none --import-source on -k regex:k_sweep_n16 --launch-skip 450 -c 1 -o gpurun_out/$name $B > gpurun_out/$name.log 2>&1
+{ echo "# ncu --set full --clock-control none --cache-control none --import-source on -k regex:k_sweep_n16 --launch-skip 450 -c 1 $B"
+  python tools/ncu_summary.py raw gpurun_out/$name.ncu-rep; echo; python tools/ncu_hot.py gpurun_out/$name.ncu-rep 25; } > gpurun_out/${name}_ncu.txt 2>&1
+rm -f gpurun_out/$name.ncu-rep
