@@ -579,8 +579,8 @@ def main():
         per_launch_s = (ms * 1e-3) / n_sweep_launches
         alg_bytes_per_launch = BYTES_PER_UPDATE * (n_local / 2)
         achieved = alg_bytes_per_launch / per_launch_s / 1e9
-        # which kernel family did the sweeps: the 16-bit working copy (kernels_narrow.cuh) or the i32 streaming kernel
-        kernel = "k_sweep_n16" if narrow_segments > 0 else "k_sweep_stream"
+        # which kernel family did the sweeps: the 16-bit storage (kernels_narrow.cuh) or the i32 fallback kernel
+        kernel = "k_sweep_n16" if narrow_segments > 0 else "k_sweep_vec4"
         moved = (6 if narrow_segments > 0 else 12) * (n_local / 2)
         traffic, traffic_src = measured_traffic([X, Y, T_PER_GPU], kernel) if world == 1 else (None, None)
         line = {

@@ -77,10 +77,9 @@ typedef struct lqft_config {
 #define LQFT_FLAG_NONE 0u
 #define LQFT_FLAG_NO_GRAPH 1u     /* launch sweeps eagerly instead of through CUDA graphs   */
 #define LQFT_FLAG_FORCE_GENERIC 2u/* always use the scalar kernels (test cross-check)       */
-#define LQFT_FLAG_HALO_NCCL 4u    /* world_size>1: ncclSend/Recv halos (default: peer stores
-                                     fused into the boundary kernel when P2P is available)  */
-#define LQFT_FLAG_FORCE_V1 8u     /* use the two-pass L1-cached kernels, not the tiled ones */
-#define LQFT_FLAG_NO_STREAM 16u   /* wide rows: marching kernel instead of the streaming one */
+#define LQFT_FLAG_HALO_NCCL 4u    /* world_size>1: i32 field with ncclSend/Recv halos (default: 16-bit storage
+                                     whose boundary planes travel over peer memory, CUDA IPC) */
+/* 8u and 16u selected the round-1 i32 marching / streaming kernels; those are gone, the bits are ignored */
 #define LQFT_FLAG_NO_PDL 32u      /* no programmatic dependent launch between half-sweeps     */
 #define LQFT_FLAG_NO_RESIDENT 128u /* multi-launch path instead of the one-launch kernels that keep a chain in shared
                                      memory (one CTA up to 36^3, a thread-block cluster up to ~1.5 MB per chain) */

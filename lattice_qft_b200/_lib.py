@@ -9,7 +9,8 @@ LIB_PATH = os.environ.get("LQFT_LIB") or os.path.join(PKG, "liblqft.so")  # LQFT
 
 LQFT_OK, LQFT_ERR_INVALID, LQFT_ERR_CUDA, LQFT_ERR_NCCL, LQFT_ERR_STATE, LQFT_ERR_NOMEM = range(6)
 LQFT_I32, LQFT_F64 = 0, 1
-FLAG_NONE, FLAG_NO_GRAPH, FLAG_FORCE_GENERIC, FLAG_HALO_NCCL, FLAG_FORCE_V1, FLAG_NO_STREAM, FLAG_NO_PDL, FLAG_SELF_HALO, FLAG_NO_RESIDENT, FLAG_NO_NARROW = 0, 1, 2, 4, 8, 16, 32, 64, 128, 256
+FLAG_NONE, FLAG_NO_GRAPH, FLAG_FORCE_GENERIC, FLAG_HALO_NCCL, FLAG_NO_PDL, FLAG_SELF_HALO, FLAG_NO_RESIDENT, FLAG_NO_NARROW = 0, 1, 2, 4, 32, 64, 128, 256
+FLAG_I32_VECTOR = FLAG_NO_RESIDENT | FLAG_NO_NARROW  # the i32 vector kernel (X % 8 == 0) instead of the one-launch / 16-bit paths
 FLAG_NO_FUSED_ENERGY = 512
 STREAM_COLOUR0, STREAM_COLOUR1, STREAM_NORMALIZE, STREAM_HOTSTART, STREAM_CORRELATOR = range(5)
 MAX_THRESHOLDS = 2048

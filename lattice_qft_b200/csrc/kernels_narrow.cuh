@@ -33,7 +33,7 @@
 // kN16Segment sweeps; a sweep moves a site by at most one, so no height can leave [0, 4096) (host logic in
 // lqft.cu, narrow_enter / narrow_exit).
 #pragma once
-#include "kernels_stream.cuh"
+#include "kernels_common.cuh"
 
 namespace lqft {
 
@@ -48,7 +48,7 @@ constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a s
 constexpr uint32_t kN16FillBlocks = 32;          // per (side, colour, chain)
 
 // Decision table.  Entry (i << 1) | coin serves d = i - kc: coin 1 proposes +1 (m = d), coin 0 proposes -1 (m = -d); same
-// contents as build_two_sided (kernels_tiled.cuh), interleaved so that the coin can be shifted into the index; an entry
+// contents as build_two_sided (kernels_common.cuh), interleaved so that the coin can be shifted into the index; an entry
 // is {threshold | coin << 31, +-1}.  (The lanes of a warp look up different entries: a 4.4-way bank conflict per LDS.64
 // on average, ncu round 2.  Storing the table [entry][copy] with one copy per lane of a half-warp removes the conflicts
 // and made the kernel 2 % slower — 24 KB of table per block instead of 8 cost more L1 and prologue than the conflicts

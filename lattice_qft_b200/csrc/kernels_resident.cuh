@@ -11,7 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "kernels_tiled.cuh"
+#include "kernels_common.cuh"
 
 namespace lqft {
 

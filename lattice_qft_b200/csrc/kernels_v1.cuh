@@ -1,6 +1,6 @@
 // kernels_v1.cuh — two-pass red-black kernels on the colour-split layout (global loads,
-// L1/L2 reuse only).  They are the general path (any even extents, any slab) and the
-// cross-check for the tiled kernels in kernels_tiled.cuh.
+// L1/L2 reuse only).  They are the general path (any even extents, any slab, i32 heights) and the
+// cross-check for the 16-bit kernels of kernels_narrow.cuh / kernels_cluster.cuh.
 //
 // Device layout (per chain, per colour c in {0,1}):
 //     field[c][chain][plane p][row y][k]      k < Xh = X/2, element = site x = 2k + ((y+t+c)&1)

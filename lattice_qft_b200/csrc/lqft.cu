@@ -1,7 +1,7 @@
 // lqft.cu — the C ABI of include/lqft.h: handle management, launch schedules, CUDA graphs,
 // NCCL / peer-memory halo exchange.  All arithmetic that touches the field runs in the CUDA
-// kernels of kernels_v1.cuh / kernels_tiled.cuh; this file contains no CPU implementation of
-// the sweep or of the observables.
+// kernels of the kernels_*.cuh headers; this file contains no CPU implementation of the sweep or of
+// the observables.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -21,11 +21,9 @@
 #include "../../include/lqft.h"
 #include "kernels_f64.cuh"
 #include "kernels_resident.cuh"
-#include "kernels_stream.cuh"
 #include "kernels_narrow.cuh"
 #include "kernels_cluster.cuh"
 #include "kernels_observe.cuh"
-#include "kernels_tiled.cuh"
 #include "kernels_v1.cuh"
 #include "spec.cuh"
 
@@ -193,8 +191,6 @@ struct lqft_handle {
     ncclComm_t comm = nullptr;
     int sm_count = 148;
     std::map<GraphKey, GraphVal> graphs;
-    TiledPlan tiled{};
-    StreamPlan streamp{};
     bool resident_ok = false;   // small lattice: whole runs inside one launch (kernels_resident.cuh)
     size_t smem_optin = 0;
     // peer-memory halo (world_size > 1)
@@ -252,14 +248,11 @@ static lqft_status upload_params(lqft_handle* h) {
         h->max_thr = std::max(h->max_thr, h->chains_h[c].n_thr);
     }
     h->params_dirty = false;
-    CU(stream_prepare(h->streamp, h->g, h->sm_count, h->max_thr,
-                      h->is64 || (h->cfg.flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_STREAM)) != 0,
-                      h->p2p));
     if (h->is64) {
         CU(cudaMemcpyAsync(h->beta_d, h->beta.data(), sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
-    h->resident_ok = !h->is64 && !(h->cfg.flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_RESIDENT)) &&
+    h->resident_ok = !h->is64 && !(h->cfg.flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_NO_RESIDENT)) &&
                      resident_fits(h->g, h->max_thr, h->smem_optin);
     if (h->resident_ok) {
         const int smem = (int)resident_smem_bytes(h->g, h->max_thr);
@@ -277,11 +270,6 @@ static lqft_status upload_params(lqft_handle* h) {
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
     if (h->narrow_active && !h->narrowp.enabled) ST(narrow_exit(h));  // e.g. a coupling whose table the 16-bit kernel cannot hold
-    if (getenv("LQFT_DEBUG"))
-        fprintf(stderr, "[lqft] %ux%ux%u chains=%u path=%s (stream: segs=%d blocks/SM=%d chunks=%u; march: g=%d rows=%d)\n",
-                h->g.X, h->g.Y, h->g.T, nc, h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream" : (h->tiled.enabled ? "march" : "v1"),
-                h->streamp.segs, h->streamp.blocks_per_sm,
-                h->streamp.enabled ? stream_chunks(h->streamp, h->g, h->g.Tl, nc) : 0u, h->tiled.g, h->tiled.march);
     return LQFT_OK;
 }
 
@@ -457,27 +445,6 @@ static lqft_status setup_p2p(lqft_handle* h) {
     return LQFT_OK;
 }
 
-// The streaming kernel carries the peer-memory halo; every other kernel uses the NCCL exchange.
-static bool halo_fused(const lqft_handle* h) { return h->p2p && h->streamp.enabled; }
-
-// Operations other than sweeps that read or rewrite ghost planes are phases too: wait until both
-// neighbours have finished the previous phase, run, then publish.
-static lqft_status ghost_op_begin(lqft_handle* h) {
-    if (!halo_fused(h)) return LQFT_OK;
-    k_halo_wait<<<1, 1, 0, h->stream>>>(h->halo_d, h->phase);
-    CU(cudaGetLastError());
-    h->launches += 1;
-    return LQFT_OK;
-}
-static lqft_status ghost_op_end(lqft_handle* h) {
-    if (!halo_fused(h)) return LQFT_OK;
-    h->phase += 1;
-    k_halo_signal<<<1, 1, 0, h->stream>>>((HaloSync*)h->peer_base[0][2], (HaloSync*)h->peer_base[1][2], h->phase);
-    CU(cudaGetLastError());
-    h->launches += 1;
-    return LQFT_OK;
-}
-
 static lqft_status set_halo_timeout() {
     if (const char* e = getenv("LQFT_HALO_TIMEOUT_S")) {
         const double sec = atof(e);
@@ -489,7 +456,7 @@ static lqft_status set_halo_timeout() {
     return LQFT_OK;
 }
 
-// A halo wait that expired has set the error word and trapped (kernels_stream.cuh, halo_wait): the context is
+// A halo wait that expired has set the error word and trapped (kernels_common.cuh, halo_wait): the context is
 // gone, so the copy below fails with LQFT_ERR_CUDA; the word itself is reported when the trap has not landed yet.
 static lqft_status check_halo_error(lqft_handle* h) {
     if (!h->halo_d) return LQFT_OK;
@@ -517,7 +484,6 @@ extern "C" lqft_status lqft_destroy(lqft_handle* h) {
     }
     cudaFree(h->halo_d);
     cudaFree(h->narrow[0]); cudaFree(h->narrow[1]); cudaFree(h->ncentre_d); cudaFree(h->nworst_d); cudaFree(h->phase_d);
-    tiled_release(h->tiled);
     cudaFree(h->field[0]); cudaFree(h->field[1]);
     cudaFree(h->field64[0]); cudaFree(h->field64[1]); cudaFree(h->beta_d); cudaFree(h->offset64_d);
     cudaFree(h->obs64_d); cudaFree(h->mom64_d); cudaFree(h->part_d); cudaFree(h->elog64_d); cudaFree(h->gathered64_d);
@@ -676,8 +642,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
     h->diff_comp.assign(nc, nullptr);
     h->diff_count.assign(nc, 0);
 
-    const uint32_t no_narrow = LQFT_FLAG_NO_NARROW | LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1 | LQFT_FLAG_NO_STREAM |
-                               LQFT_FLAG_HALO_NCCL;
+    const uint32_t no_narrow = LQFT_FLAG_NO_NARROW | LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_HALO_NCCL;
     h->gn = g;
     if (g.ghost) {
         // deep halo of the narrow copy: as many planes as the thinnest slab allows, at most kN16GhostDepth, even
@@ -711,7 +676,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
             CU(cudaMalloc(&h->phase_d, sizeof(unsigned long long)));
         }
     }
-    // i32 arrays: always on slabs (their boundary planes are mapped by the neighbours for the i32 halo path); on one
+    // i32 arrays: always on slabs (the fallback of a slab whose heights leave the band, halos by ncclSend/Recv); on one
     // GPU only where the 16-bit copy cannot be the storage — otherwise need_i32 allocates them if a field ever
     // leaves the band
     if (!h->is64 && (g.ghost != 0 || !h->narrow[0])) ST(need_i32(h));
@@ -739,7 +704,6 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         h->self_halo = true;
         h->p2p = true;
     }
-    CU(tiled_prepare(h->tiled, g, nc, h->sm_count, h->is64 || (cfg->flags & (LQFT_FLAG_FORCE_GENERIC | LQFT_FLAG_FORCE_V1)) != 0));
     if (!h->is64 && !h->field[0]) ST(narrow_zero(h));  // the field of zeros lives in the 16-bit arrays from the start
     CU(cudaStreamSynchronize(h->stream));
     return LQFT_OK;
@@ -818,10 +782,8 @@ static lqft_status exchange_halo_nccl(lqft_handle* h, int colour, cudaStream_t s
 
 static lqft_status refresh_ghosts(lqft_handle* h) {
     if (h->g.ghost == 0 || h->ghosts_valid) return LQFT_OK;
-    ST(ghost_op_begin(h));
     ST(exchange_halo_nccl(h, 0, h->stream));
     ST(exchange_halo_nccl(h, 1, h->stream));
-    ST(ghost_op_end(h));
     h->ghosts_valid = true;
     return LQFT_OK;
 }
@@ -898,7 +860,7 @@ static lqft_status launch_half_narrow(lqft_handle* h, int colour, uint64_t sweep
 
 // One half-sweep of colour `colour` over local planes tl_first .. tl_first + n_planes - 1.
 static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const uint64_t* ctr,
-                               uint32_t tl_first, uint32_t n_planes, cudaStream_t s, bool halo_now = false) {
+                               uint32_t tl_first, uint32_t n_planes, cudaStream_t s) {
     if (n_planes == 0) return LQFT_OK;
     const Geom& g = h->g;
     if (h->is64) {
@@ -916,28 +878,6 @@ static lqft_status launch_half(lqft_handle* h, int colour, uint64_t sweep, const
     }
     int32_t* own = h->field[colour];
     const int32_t* oth = h->field[colour ^ 1];
-    if (h->streamp.enabled || h->tiled.enabled) {
-        MarchArgs a{g, colour, sweep, ctr, tl_first, n_planes, h->cfg.n_chains, own, oth, h->chains_d, h->thr_d,
-                    h->acc_d, h->max_thr, h->any_wilson, h->count_accepts, s,
-                    !(h->cfg.flags & LQFT_FLAG_NO_PDL), HaloP2P{}};
-        if (halo_now) {
-            // colour-c boundary rows go to the neighbours' colour-c ghost planes: my first owned plane is the
-            // lower neighbour's upper ghost (storage plane Tl+1), my last owned plane the upper neighbour's
-            // lower ghost (storage plane 0)
-            a.halo.lo_ghost = (int32_t*)h->peer_base[0][colour] + (size_t)(g.Tl + 1) * g.plane;
-            a.halo.hi_ghost = (int32_t*)h->peer_base[1][colour];
-            a.halo.lo_sync = (HaloSync*)h->peer_base[0][2];
-            a.halo.hi_sync = (HaloSync*)h->peer_base[1][2];
-            a.halo.mine = h->halo_d;
-            a.halo.wait_for = h->phase;
-            a.halo.phase = ++h->phase;
-            a.halo.enabled = 1;
-        }
-        if (h->streamp.enabled) CU(stream_half(h->streamp, a));
-        else CU(tiled_half(h->tiled, a));
-        h->launches += 1;
-        return LQFT_OK;
-    }
     const bool vec = (g.X % 8 == 0) && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC);
     const uint32_t units = vec ? g.plane / 4 : g.plane;
     const uint32_t bd = block_for(units);
@@ -997,13 +937,6 @@ static lqft_status launch_sweep(lqft_handle* h, uint64_t sweep, const uint64_t* 
     if (g.ghost == 0) {
         ST(launch_half(h, 0, sweep, ctr, 0, g.Tl, h->stream));
         ST(launch_half(h, 1, sweep, ctr, 0, g.Tl, h->stream));
-        return LQFT_OK;
-    }
-    if (halo_fused(h)) {
-        // slab, peer memory: one launch per colour; its boundary rows are pushed into the neighbours' ghost
-        // planes by the kernel itself, flags order the phases (kernels_stream.cuh)
-        ST(launch_half(h, 0, sweep, ctr, 0, g.Tl, h->stream, true));
-        ST(launch_half(h, 1, sweep, ctr, 0, g.Tl, h->stream, true));
         return LQFT_OK;
     }
     // slab, NCCL: boundary planes first, exchange on the comm stream while the interior updates
@@ -1115,9 +1048,8 @@ static lqft_status launch_measure(lqft_handle* h, const Measure& m) {
         ST(narrow_need_ghost(h));  // the last owned plane looks one plane up
         return launch_measure_t<uint16_t>(h, h->gn, h->narrow[0], h->narrow[1], m);
     }
-    ST(ghost_op_begin(h));
     ST(launch_measure_t<int32_t>(h, h->g, h->field[0], h->field[1], m));
-    return ghost_op_end(h);
+    return LQFT_OK;
 }
 
 // DifferencePlotOutputData::update of one chain on whichever copy is live (bond differences need no offset).
@@ -1134,7 +1066,6 @@ static lqft_status launch_difference(lqft_handle* h, uint32_t chain) {
         h->launches += 1;
         return LQFT_OK;
     }
-    ST(ghost_op_begin(h));
     if (h->is64)
         k_difference_update_f64<<<grid, bd, 0, h->stream>>>(g, h->field64[0] + (size_t)chain * g.chain_stride,
                                                             h->field64[1] + (size_t)chain * g.chain_stride,
@@ -1145,7 +1076,7 @@ static lqft_status launch_difference(lqft_handle* h, uint32_t chain) {
                                                                   h->diff_sum[chain], h->diff_comp[chain]);
     CU(cudaGetLastError());
     h->launches += 1;
-    return ghost_op_end(h);
+    return LQFT_OK;
 }
 
 static lqft_status need_difference(lqft_handle* h, uint32_t chain) {
@@ -2100,8 +2031,8 @@ extern "C" lqft_status lqft_plan_info(lqft_handle* h, char* buf, size_t cap) {
     if (!h || !buf || cap == 0) return fail(LQFT_ERR_INVALID, "null argument");
     ST(use_device(h));
     ST(upload_params(h));
-    const char* path = h->is64 ? "f64" : h->resident_ok ? "resident" : h->clusterp.enabled ? "cluster" : h->narrowp.enabled ? "narrow" : h->streamp.enabled ? "stream"
-                       : h->tiled.enabled ? "march" : ((h->g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) ? "vec4" : "generic");
+    const char* path = h->is64 ? "f64" : h->resident_ok ? "resident" : h->clusterp.enabled ? "cluster" : h->narrowp.enabled ? "narrow"
+                       : ((h->g.X % 8 == 0 && !(h->cfg.flags & LQFT_FLAG_FORCE_GENERIC)) ? "vec4" : "generic");
     uint32_t chunks = 0, rows = 0, groups = 0;
     int occ = 0;
     if (h->narrowp.enabled) {

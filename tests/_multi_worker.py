@@ -99,8 +99,8 @@ def main():
     check((16, 16, 8 * ws), 0.25, 77, (0, 0), 4)
     check((8, 6, 4 * ws), 0.3, 5, (5, 3), 5)
     check((64, 32, 4 * ws), 0.22, 9, (21, 6), 3)
-    check((256, 16, 4 * ws), 0.25, 11, (0, 0), 3)           # streaming kernel (3 sweeps), narrow kernel (the run) on slabs
-    check((256, 16, 4 * ws), 0.25, 11, (0, 0), 3, flags=256)  # LQFT_FLAG_NO_NARROW: i32 streaming kernel throughout
+    check((256, 16, 4 * ws), 0.25, 11, (0, 0), 3)           # 16-bit kernel on slabs: pushes over peer memory, ghost tasks
+    check((256, 16, 4 * ws), 0.25, 11, (0, 0), 3, flags=256)  # LQFT_FLAG_NO_NARROW: i32 kernels, halos by ncclSend/Recv
     check((256, 4, 40 * ws), 0.27, 13, (200, 50), 5)        # narrow kernel, several plane groups per slab, Wilson sheet
     check((256, 16, 4 * ws), 0.25, 11, (0, 0), 3, flags=2)  # scalar kernels on slabs
     check((512, 8, 2 * ws), 0.25, 12, (100, 3), 2)

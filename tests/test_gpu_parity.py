@@ -31,7 +31,7 @@ def oracle_sweeps(size, v, beta, seed, first, n, wilson=(0, 0)):
     return acc
 
 
-@pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC, _lib.FLAG_FORCE_V1])
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC, _lib.FLAG_I32_VECTOR])
 @pytest.mark.parametrize("name", sorted(_golden()))
 def test_sweep_matches_golden_vectors(name, flags):
     g = _golden()[name]
@@ -77,13 +77,13 @@ def test_sweep_bit_exact_vs_oracle(size, beta, wilson):
     ((1024, 2, 4), 0.28, (1000, 3)), ((256, 36, 2), 0.25, (0, 0)),
 ])
 def test_wide_row_kernels_bit_exact_vs_oracle(size, beta, wilson):
-    """Streaming (cp.async ring, X = 256/512/1024), marching, vector and scalar kernels all equal the oracle."""
+    """Wide rows: the 16-bit kernel, the i32 vector kernel and the scalar kernel all equal the oracle."""
     X, Y, T = size
     seed = 0xBEEF + X + Y
     v0 = seeded_field(X * Y * T, seed=X + 7 * Y)
     want = v0.copy()
     want_acc = oracle_sweeps(size, want, beta, seed, 10, 3, wilson)
-    for flags in (0, _lib.FLAG_NO_STREAM, _lib.FLAG_FORCE_V1, _lib.FLAG_FORCE_GENERIC):
+    for flags in (0, _lib.FLAG_I32_VECTOR, _lib.FLAG_FORCE_GENERIC):
         with Engine(X, Y, T, flags=flags) as eng:
             eng.set_chain(0, beta, seed, *wilson)
             eng.upload(0, v0)
@@ -232,8 +232,8 @@ def test_narrow_many_chains_match_single_chain_runs():
                                          ((16, 16, 8), (5, 8)), ((10, 6, 4), (0, 0)), ((256, 4, 40), (200, 33)),
                                          ((256, 2, 2), (0, 0)), ((512, 2, 40), (400, 30)), ((1024, 2, 24), (0, 0))])
 def test_self_halo_slab_path_on_one_gpu(size, wilson):
-    """LQFT_FLAG_SELF_HALO: ghost planes + the multi-GPU code path (peer-memory pushes and phase flags fused in
-    the streaming kernel for wide rows, boundary-first + exchange otherwise) with this rank as its own
+    """LQFT_FLAG_SELF_HALO: ghost planes + the multi-GPU code path (16-bit storage: ghost sets, pushes, flips and
+    ghost tasks of k_sweep_n16; other extents: boundary planes first + exchange) with this rank as its own
     neighbour.  Must equal the oracle bit for bit: sweeps, fused schedule, observables, normalize."""
     X, Y, T = size
     beta, seed = 0.24, 4321
@@ -526,7 +526,7 @@ def test_difference_plot_matches_welford():
 def test_generic_and_vector_kernels_agree_at_64cubed():
     X = Y = T = 64
     with Engine(X, Y, T) as a, Engine(X, Y, T, flags=_lib.FLAG_FORCE_GENERIC) as b, \
-            Engine(X, Y, T, flags=_lib.FLAG_FORCE_V1) as c:
+            Engine(X, Y, T, flags=_lib.FLAG_I32_VECTOR) as c:
         for e in (a, b, c):
             e.set_chain(0, 0.25, 2024, 21, 32)
             e.init_hot()
