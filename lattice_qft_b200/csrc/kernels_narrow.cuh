@@ -749,7 +749,9 @@ inline uint32_t narrow_chunks(NarrowPlan& p, const Geom& g, uint32_t n_planes, u
                               bool count = false, bool slab = false) {
     const uint64_t slots = (uint64_t)p.sm_count * narrow_occupancy(p, wilson, count, slab, narrow_warps(p, n_planes));
     const uint64_t base = narrow_groups(p, n_planes) * (uint64_t)(p.segs() ? p.segs() : 1) * n_chains;  // blocks per chunk
-    const uint32_t max_chunks = g.Y / 2 ? g.Y / 2 : 1;
+    // down to one row per chunk: a small lattice (128^3: 4 096 warp-rows per half-sweep) is short of warps, not of
+    // prologue instructions — 128 chunks of one row run 25 % faster there than 64 chunks of two (tools/probe_chunks.py)
+    const uint32_t max_chunks = g.Y;
     if (p.forced_chunks) return p.forced_chunks < g.Y ? p.forced_chunks : g.Y;
     uint32_t best = 1;
     double best_cost = 1e300;

@@ -59,6 +59,27 @@ def test_narrow_rows_per_chunk_ge_3_vs_oracle(size, wilson, chunks, monkeypatch)
         assert (got == want).all(), f"{int((got != want).sum())} sites differ (chunks={chunks}, flags={flags})"
 
 
+@pytest.mark.parametrize("size,wilson,self_halo", [
+    ((256, 10, 6), (100, 5), False), ((128, 16, 40), (0, 0), False), ((64, 12, 64), (21, 32), False), ((1024, 6, 4), (700, 2), False),
+    ((16, 6, 1100), (5, 16), False), ((256, 10, 36), (255, 20), True), ((512, 6, 8), (0, 0), True),
+])
+def test_narrow_one_row_per_chunk_vs_oracle(size, wilson, self_halo):
+    """The plan of a small lattice: as many y-chunks as rows (128^3 runs 128 chunks of one row).  The register window is
+    loaded, used once and dropped; first rows of both parities; on slabs the ghost tasks of a one-row chunk."""
+    X, Y, T = size
+    beta, seed = 0.26, 0x1205 + X
+    v0 = seeded_field(X * Y * T, seed=5 * Y + T)
+    want, wacc, we = _oracle_trajectory(size, v0, beta, seed, wilson)
+    for flags in (NORES, NORES | _lib.FLAG_NO_GRAPH):
+        with Engine(X, Y, T, flags=flags | (_lib.FLAG_SELF_HALO if self_halo else 0)) as eng:
+            got, acc, e = _engine_trajectory(eng, v0, beta, seed, wilson)
+            plan = eng.plan_info()
+            assert plan["path"] == "narrow" and plan["chunks"] == Y and plan["rows_per_chunk"] == 1, plan
+        assert acc == wacc
+        assert (e == we).all()
+        assert (got == want).all(), f"{int((got != want).sum())} sites differ (flags={flags})"
+
+
 @pytest.mark.parametrize("chunks", [1, 3])
 @pytest.mark.parametrize("size,wilson", [((256, 10, 40), (77, 33)), ((512, 14, 24), (0, 0)), ((1024, 10, 20), (600, 9))])
 def test_self_halo_rows_per_chunk_ge_3_vs_oracle(size, wilson, chunks, monkeypatch):
