@@ -6,7 +6,7 @@ mkdir -p build/tune
 for cfg in "$@"; do
   name=${cfg%%:*}; defs=${cfg#*:}; defs=${defs//,/ }
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -I include \
-    -DLQFT_G32_ONLY $defs -o build/tune/liblqft_$name.so lattice_qft_b200/csrc/lqft.cu -lcudart_static -ldl -lpthread -lrt &
+    $defs -o build/tune/liblqft_$name.so lattice_qft_b200/csrc/lqft.cu -lcudart_static -ldl -lpthread -lrt &
 done
 wait
 ls build/tune
