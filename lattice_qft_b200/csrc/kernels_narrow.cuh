@@ -1,10 +1,11 @@
-// kernels_narrow.cuh — red-black Metropolis half-sweep on 16-bit heights (X = 256, 512, 1024).
+// kernels_narrow.cuh — red-black Metropolis half-sweep on 16-bit heights (X a power of two, 16 ... 1024).
 //
-// The reference keeps heights in i32 (Field<i32>, fields.rs:63-67) and so does the ABI; between API calls the
-// device field is i32 too.  Inside lqft_run / lqft_sweep the engine may hold a *narrow* working copy instead:
-// u16 heights biased by kN16Bias relative to a per-chain centre (the chain's normalisation offset).  Half the
-// bytes per site, and — what matters more on this latency/issue-bound kernel — half the registers per site:
-// one thread owns 8 same-colour sites (one 16-byte load), 16 lanes a row segment of 128 positions.
+// The reference keeps heights in i32 (Field<i32>, fields.rs:63-67) and so does the ABI.  On the device the field of an
+// admitted lattice is STORED as u16: heights biased by kN16Bias relative to a per-chain centre (the chain's
+// normalisation offset when the arrays were last centred); hot start, upload, download and every observable work on
+// these arrays, i32 arrays exist only for a field that has left the band (lqft.cu).  Half the bytes per site, and —
+// what matters more on this instruction-bound kernel — half the registers per site: one thread owns 8 same-colour
+// sites (one 16-byte load), 16 lanes a row segment of 128 positions.
 //
 // Same decision spec as every other kernel family (spec.cuh: Philox keying by global index, integer
 // threshold table), so results are bit-identical to the i32 kernels and to the oracle; what differs is the
@@ -29,9 +30,11 @@
 // cannot flip ahead without this rank's flag), where it reads and redundantly updates its current set only.
 // k_n16_fill copies the boundary planes for the first period after the copy was (re)built.
 //
-// Validity: a narrow segment starts only if every height is within kN16Guard of the centre and lasts at most
-// kN16Segment sweeps; a sweep moves a site by at most one, so no height can leave [0, 4096) (host logic in
-// lqft.cu, narrow_enter / narrow_exit).
+// The ghost planes a half-sweep updates redundantly are dealt to the warps as ghost tasks (k_sweep_n16, below).
+//
+// Validity: a conversion or re-centring measures the largest |height - centre| = w; a sweep moves a site by at most
+// one, so the arrays are good for kN16Bias - 1 - w more sweeps (the sweep budget, host logic in lqft.cu: narrow_enter /
+// narrow_recheck / narrow_exit); they are entered or re-centred only with every height within kN16Guard of the centre.
 #pragma once
 #include "kernels_common.cuh"
 
@@ -41,7 +44,7 @@ constexpr int kN16Warps = 8;                     // per block, at most (9 warps 
 constexpr int kN16Threads = kN16Warps * 32;
 constexpr int kN16Bias = 2048;
 constexpr int kN16Guard = 1023;
-constexpr uint32_t kN16Segment = 1000;           // kN16Guard + kN16Segment < kN16Bias
+constexpr uint32_t kN16Segment = 1000;           // sweeps a refused field stays on i32 before the band is tried again
 constexpr int kN16KcMax = 255;                   // threshold tables up to 256 entries (beta >= ~0.045)
 
 constexpr uint32_t kN16GhostDepth = 8;           // ghost planes per side of a slab's narrow copy (even); fewer for large planes

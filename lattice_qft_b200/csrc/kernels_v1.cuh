@@ -280,7 +280,7 @@ __global__ void k_init_hot(Geom g, H* __restrict__ c0_base, H* __restrict__ c1_b
 // and normalize_random (subtract the TRUE height of the picked site) simply sets offset := stored[site].
 // The offset is applied where absolute heights leave the device (k_merge, lqft_slice_moments).
 // Step 1: one thread per chain reads the stored height of the picked site (0 if another rank owns it).
-// H = uint16_t reads the narrow working copy: stored = biased - bias + centre[chain] (`rebase` = centre, bias).
+// H = uint16_t reads the 16-bit storage: stored = biased - bias + centre[chain] (`rebase` = centre, bias).
 template <typename H>
 __global__ void k_pick_shift(Geom g, const H* __restrict__ c0_base,
                              const H* __restrict__ c1_base,
@@ -396,7 +396,7 @@ k_observe(Geom g, const int32_t* __restrict__ c0_base, const int32_t* __restrict
 // Vectorised form of k_observe for X % 8 == 0: one thread per quad position owns four colour-0 and four
 // colour-1 sites (6 LDG.128 + 1 LDG for 8 sites).  Same exact int64 sums.
 // grid = (ceil(plane/4/bd), Tl, n_chains)
-// H = int32_t, or uint16_t for the narrow working copy (kernels_narrow.cuh): the bias cancels in every
+// H = int32_t, or uint16_t for the 16-bit storage (kernels_narrow.cuh): the bias cancels in every
 // difference, so the energy sums are the same; slice moments need true heights and are i32 only.
 __device__ __forceinline__ int4 load_h4(const int32_t* p) { return *reinterpret_cast<const int4*>(p); }
 __device__ __forceinline__ int4 load_h4(const uint16_t* p) {

@@ -405,7 +405,7 @@ static lqft_status setup_p2p(lqft_handle* h) {
     cudaFree(all_d);
     const int lo = (r + ws - 1) % ws, hi = (r + 1) % ws;
     h->peer_same = lo == hi;
-    bool narrow_ok = true;  // the narrow working copy needs every rank to have one (slabs may differ in shape)
+    bool narrow_ok = true;  // the 16-bit storage needs every rank to have it (slabs may differ in shape)
     for (int k = 0; k < ws; ++k) narrow_ok = narrow_ok && all[k].has_narrow;
     if (ok && !(h->cfg.flags & LQFT_FLAG_HALO_NCCL)) {
         for (int side = 0; side < 2 && ok; ++side) {
@@ -664,7 +664,7 @@ static lqft_status create_impl(const lqft_config* cfg, lqft_handle* h) {
         h->gn.chain_stride = (uint64_t)g.plane * (g.Tl + 4 * h->gn.ghost);  // two sets of ghost planes (kernels_narrow.cuh)
     }
     if (!h->is64 && !(cfg->flags & no_narrow) && narrow_geometry_ok(g, 2, nc)) {
-        // 16-bit working copy (+50 % field memory); without it the i32 kernels do all the work
+        // 16-bit storage of the field; without it the i32 kernels do all the work
         const size_t nbytes = sizeof(uint16_t) * h->gn.chain_stride * nc;
         if (cudaMalloc(&h->narrow[0], nbytes) != cudaSuccess || cudaMalloc(&h->narrow[1], nbytes) != cudaSuccess) {
             cudaGetLastError();
@@ -1522,7 +1522,7 @@ extern "C" lqft_status lqft_difference_read(lqft_handle* h, uint32_t chain, doub
 }
 
 // ---------------------------------------------------------------------------------------------
-// narrow working copy (kernels_narrow.cuh)
+// 16-bit storage (kernels_narrow.cuh)
 // ---------------------------------------------------------------------------------------------
 // The 16-bit arrays are the storage of the field wherever they can be (also between calls); the i32 arrays take over
 // only while some height lies outside the band.  Bookkeeping: a sweep moves a height by at most one, so after a
