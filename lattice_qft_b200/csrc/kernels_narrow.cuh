@@ -37,6 +37,7 @@
 // narrow_recheck / narrow_exit); they are entered or re-centred only with every height within kN16Guard of the centre.
 #pragma once
 #include "kernels_common.cuh"
+#include "kernels_observe.cuh"
 
 namespace lqft {
 
@@ -279,13 +280,14 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
             uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
             const ChainDev* __restrict__ chains, const ChainDev chain0, const uint32_t* __restrict__ thr_all,
             unsigned long long* __restrict__ acc, const uint32_t max_thr, const SlabArgs sl,
-            unsigned long long* __restrict__ obs_e) {
+            unsigned long long* __restrict__ obs_e, const ObsFin fin) {
     constexpr uint32_t ROWQ = XQ;                        // uint4 per row of one colour
     constexpr uint32_t LPR = XQ < 32 ? XQ : 32;          // lanes of a warp on one row
     constexpr uint32_t PPW = 32u / LPR;                  // planes per warp
     constexpr int SEGS = XQ / 32;                        // 512-site row segments (0: a row is narrower than a warp)
     __shared__ unsigned int s_cnt;
     __shared__ unsigned long long s_obs;
+    __shared__ bool s_last;
     pdl_launch_dependents();
     const uint32_t chain = SINGLE ? 0u : blockIdx.z;
     // MEAS: this launch is the colour-1 half-sweep of a step whose energy is due: accumulate it on the way (n16_obs_pair)
@@ -483,12 +485,24 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     if (COUNT)
         block_count_flush(&s_cnt, (unsigned int)accepted, acc + (size_t)chain * kAccSlots + (blockIdx.x % kAccSlots));
     if (MEAS) {
-        // the block's share of the chain's energy sum (obs[chain][0]; logged and cleared by k_obs_finalize)
+        // the block's share of the chain's energy sum (obs[chain][0])
         sum_e = warp_sum_ll(sum_e);
         __syncthreads();
         if ((threadIdx.x & 31u) == 0u && sum_e != 0) atomicAdd(&s_obs, (unsigned long long)sum_e);
         __syncthreads();
-        if (threadIdx.x == 0 && s_obs != 0) atomicAdd(obs_e + (size_t)chain * 2, 2ull * s_obs);
+        // the last block of the launch to get here logs the energies of all chains into their slots and clears the
+        // sums (as the observe kernel does, kernels_observe.cuh): no finalising launch after the half-sweep
+        if (threadIdx.x == 0) {
+            if (s_obs != 0) atomicAdd(obs_e + (size_t)chain * 2, 2ull * s_obs);
+            __threadfence();
+            s_last = atomicAdd(fin.ticket, 1u) + 1u == gridDim.x * gridDim.y * gridDim.z;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            obs_log_sums(fin, kObsEnergy, sweep, 0u, SINGLE ? 1u : gridDim.z, obs_e);
+            if (threadIdx.x == 0) *fin.ticket = 0;
+        }
     }
 }
 
@@ -657,6 +671,7 @@ struct NarrowArgs {
     bool slab = false;     // SLAB instantiation: push boundary planes and / or flip the ghost sets (sl)
     SlabArgs sl{};
     unsigned long long* obs_e = nullptr;  // colour-1 half-sweep of a measured step: energy sums accumulate here ([chain][2])
+    ObsFin fin{};                         //   ... and are logged by the launch's last block as `fin` says
 };
 
 template <int XQ, bool SLAB>
@@ -801,8 +816,9 @@ inline cudaError_t narrow_half(NarrowPlan& p, const NarrowArgs& a) {
     unsigned long long* acc = a.acc;
     SlabArgs sl = a.sl;
     unsigned long long* obs_e = a.obs_e;
+    ObsFin fin = a.fin;
     void* args[] = {&g, &colour, &sweep, &ctr, &tl_first, &n_first, &tl_second, &n_planes, &n_chunks, &own, &oth, &chains,
-                    &chain0, &thr, &acc, &max_thr, &sl, &obs_e};
+                    &chain0, &thr, &acc, &max_thr, &sl, &obs_e, &fin};
     return cudaLaunchKernelExC(&cfg, n16_kernel(p.xq, a.wilson, a.count, a.n_chains == 1, a.slab, a.obs_e != nullptr), args);
 }
 

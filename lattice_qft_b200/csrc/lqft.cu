@@ -852,7 +852,11 @@ static lqft_status launch_half_narrow(lqft_handle* h, int colour, uint64_t sweep
             a.sl.hi_plane = peer_ghost_plane(h, 1, next);
         }
     }
-    if (measure) a.obs_e = h->obs_d;
+    if (measure) {
+        a.obs_e = h->obs_d;
+        a.fin = h->run_fin;  // where the running schedule logs its energies; the launch's last block does it
+        a.fin.ticket = h->ticket_d;
+    }
     CU(narrow_half(h->narrowp, a));
     h->launches += 1;
     return LQFT_OK;
@@ -1685,11 +1689,7 @@ static lqft_status launch_step(lqft_handle* h, const lqft_schedule* s, uint64_t 
     const bool fused = due == kObsEnergy && can_fuse_energy(h);
     ST(launch_sweep(h, s->sweep_base + step_arg, ctr, fused));
     if (fused) {
-        // the colour-1 half-sweep has left the energy sums in obs_d: log them (and clear the accumulators)
-        ObsFin fin = h->run_fin;
-        k_obs_finalize<<<1, 256, 0, h->stream>>>(fin, due, s->sweep_base + step_arg, ctr, 0u, h->cfg.n_chains, h->obs_d);
-        CU(cudaGetLastError());
-        h->launches += 1;
+        // the colour-1 half-sweep has accumulated the energies and its last block has logged them
     } else if (h->is64) {
         if (due & kObsEnergy) ST(launch_energy_log_f64(h));
     } else if (due) {
