@@ -221,6 +221,18 @@ def other_configs(device: int):
         "in_run_measurements_per_s": 200 / max(sec1 - sec0, 1e-9),
         "in_run_us_per_measurement": 1e6 * (sec1 - sec0) / 200}
     eng.close()
+    # config 3 as SURVEY 8(d) states it: the three couplings 0.22, 0.25, 0.28, which sim.rs:90-93 runs side by side
+    # under rayon — here three chains of one handle, every half-sweep one launch over all of them
+    eng = Engine(128, 128, 128, n_chains=3, device=device)
+    for c, b in enumerate((0.22, 0.25, 0.28)):
+        eng.set_chain(c, b, 0xABCD + c)
+    eng.init_hot()
+    eng.run(100, energy_every=0)
+    sec10 = timed(eng, lambda: eng.run_observables(200, sweep_base=100, correlator_every=10, correlator_reps=100), 3)
+    out["correlator_128^3_100_sites"]["sim_rs_workload_3_couplings"] = {
+        "what": "the same call on three chains (beta 0.22, 0.25, 0.28) in one handle: sim.rs:90-93's par_iter over the couplings",
+        "site_updates_per_s": 3 * 128**3 * 200 / sec10, "measurements_per_s": 3 * 20 / sec10}
+    eng.close()
     # config 1: the reference's own run — 16^3, one chain per coupling of INVESTIGATE_ARY9 (lib.rs:50), energy every
     # 10th sweep; small enough to live in shared memory: the whole schedule is one launch (kernels_resident.cuh)
     for name, n_chains in (("reference_case_16^3_1_chain", 1), ("reference_run_16^3_10_couplings", 10)):
