@@ -280,7 +280,7 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
             uint16_t* __restrict__ own_base, const uint16_t* __restrict__ oth_base,
             const ChainDev* __restrict__ chains, const ChainDev chain0, const uint32_t* __restrict__ thr_all,
             unsigned long long* __restrict__ acc, const uint32_t max_thr, const SlabArgs sl,
-            unsigned long long* __restrict__ obs_e, const ObsFin fin) {
+            unsigned long long* __restrict__ obs_e, const ObsFin fin, const uint32_t rows_base, const uint32_t rows_rem) {
     constexpr uint32_t ROWQ = XQ;                        // uint4 per row of one colour
     constexpr uint32_t LPR = XQ < 32 ? XQ : 32;          // lanes of a warp on one row
     constexpr uint32_t PPW = 32u / LPR;                  // planes per warp
@@ -297,8 +297,13 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     const ChainDev cd = SINGLE ? chain0 : chains[chain];
     if (COUNT && threadIdx.x == 0) s_cnt = 0;
     const N16Tab tab = build_interleaved(thr_all + (size_t)chain * kThrStride, max_thr, g.entry_bytes);
-    pdl_wait();
-    if (ctr) sweep += *ctr;
+    // The wait for the previous launch: a slab launch needs it before the flip; every other launch takes it as late as
+    // possible, after the index arithmetic and right before the first load of the field — what precedes it runs under
+    // the previous launch's drain (128^3: 3.03 -> 3.49e11, 256^3: 7.59 -> 7.73e11, profiles/r2_late_wait.txt)
+    if (SLAB) {
+        pdl_wait();
+        if (ctr) sweep += *ctr;
+    }
     // planes of this block's group: local numbers [grp_lo, grp_hi) of a launch with one range (every SLAB launch)
     const int32_t grp_lo = tl_first + (int32_t)((blockIdx.y >> 1) * (2u * PPW * (blockDim.x >> 5)));
     const int32_t grp_hi = grp_lo + (int32_t)(2u * PPW * (blockDim.x >> 5));
@@ -312,7 +317,8 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     // all planes of a block have the parity of blockIdx.y (see above)
     const uint32_t slot = PPW * warp + lane / LPR;   // plane slot within the block
     const uint32_t pl_raw = (blockIdx.y >> 1) * (2u * PPW * (blockDim.x >> 5)) + 2u * slot + (blockIdx.y & 1u);
-    const uint32_t y0 = chunk * g.Y / n_chunks, y1 = (chunk + 1u) * g.Y / n_chunks;
+    // rows [y0, y1) of this y chunk: Y = n_chunks * rows_base + rows_rem, the first rows_rem chunks one row longer
+    const uint32_t y0 = chunk * rows_base + min(chunk, rows_rem), y1 = y0 + rows_base + (chunk < rows_rem ? 1u : 0u);
     int accepted = 0;
     // (An early exit of warps without a live plane slot — `if (__all_sync(~0u, pl_raw >= n_planes)) return;` — compiles
     // without divergence handling but moves the Philox keys out of the uniform registers: 3.6 % slower at 256^3.)
@@ -331,7 +337,12 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         bool owned, wil_plane;
         auto set_plane = [&](const uint32_t t) {
             tl = t;
-            tg = (g.t0 + g.T + tl) % g.T;
+            if (SLAB) {
+                tg = (g.t0 + g.T + tl) % g.T;  // ghost planes: tl < 0 or >= Tl
+            } else {
+                tg = g.t0 + tl;                // own planes only
+                tg = tg >= g.T ? tg - g.T : tg;
+            }
             r_own = cq + plane_self(g, tl) * planeq;  // row 0 of this plane
             b_own = r_own + kq;
             b_ta = cq + plane_above(g, tl) * planeq + kq;
@@ -406,17 +417,21 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
             }
         }
         y = y0;
-        {
-            const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
-            wa = __ldg(q_oth + (b_own + ym * ROWQ));
-            wb = __ldg(q_oth + (b_own + y * ROWQ));
-        }
         // x parity of the first row, no thread-dependent term; the second range starts at the parity the first one
         // would have continued with (launch_sweep: Tl is even)
         p = (y0 + g.t0 + (uint32_t)tl_first + (blockIdx.y & 1u) + (uint32_t)colour) & 1u;
         // a warp without a live plane slot leaves after one row (the vote keeps the trip count warp uniform for the
         // compiler; an outright early exit costs the uniform registers, see above)
         uint32_t n = __all_sync(0xffffffffu, pl_raw >= n_planes) ? 1u : y1 - y0;
+        if (!SLAB) {
+            pdl_wait();
+            if (ctr) sweep += *ctr;
+        }
+        {
+            const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
+            wa = __ldg(q_oth + (b_own + ym * ROWQ));
+            wb = __ldg(q_oth + (b_own + y * ROWQ));
+        }
         // only the blocks whose group holds one of the first / last `depth` owned planes carry the push stores
         if (SLAB && sl.depth != 0u && grp_hi > 0 && grp_lo < (int32_t)g.Tl &&
             (grp_lo < (int32_t)sl.depth || grp_hi > (int32_t)(g.Tl - sl.depth))) {
@@ -817,8 +832,9 @@ inline cudaError_t narrow_half(NarrowPlan& p, const NarrowArgs& a) {
     SlabArgs sl = a.sl;
     unsigned long long* obs_e = a.obs_e;
     ObsFin fin = a.fin;
+    uint32_t rows_base = a.g.Y / n_chunks, rows_rem = a.g.Y % n_chunks;
     void* args[] = {&g, &colour, &sweep, &ctr, &tl_first, &n_first, &tl_second, &n_planes, &n_chunks, &own, &oth, &chains,
-                    &chain0, &thr, &acc, &max_thr, &sl, &obs_e, &fin};
+                    &chain0, &thr, &acc, &max_thr, &sl, &obs_e, &fin, &rows_base, &rows_rem};
     return cudaLaunchKernelExC(&cfg, n16_kernel(p.xq, a.wilson, a.count, a.n_chains == 1, a.slab, a.obs_e != nullptr), args);
 }
 
