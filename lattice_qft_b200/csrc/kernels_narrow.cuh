@@ -362,14 +362,15 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         uint4 wa, wb, wc;
         const uint32_t src_r = (lane & ~(LPR - 1u)) | ((lane + 1u) & (LPR - 1u)), src_l = (lane & ~(LPR - 1u)) | ((lane - 1u) & (LPR - 1u));
         const uint32_t y_one = 1u % g.Y;
-#define LQFT_N16_STEP(OM, OC, ON, PUSH, MEAS)                                                                               \
+        uint4 v_pre, on_pre, ta_pre, tb_pre;  // the first row's loads, issued right behind the wait (PRE)
+#define LQFT_N16_STEP(OM, OC, ON, PUSH, MEAS, PRE)                                                                          \
     {                                                                                                                    \
         const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;                                                                  \
         uint4* const po = q_own + (b_own + y * ROWQ);                                                                    \
-        const uint4 v = *po;                                                                                             \
-        ON = __ldg(q_oth + (b_own + yn * ROWQ));                                                                         \
-        const uint4 ta = __ldg(q_oth + (b_ta + y * ROWQ));                                                               \
-        const uint4 tb = __ldg(q_oth + (b_tb + y * ROWQ));                                                               \
+        const uint4 v = PRE ? v_pre : *po;                                                                               \
+        ON = PRE ? on_pre : __ldg(q_oth + (b_own + yn * ROWQ));                                                          \
+        const uint4 ta = PRE ? ta_pre : __ldg(q_oth + (b_ta + y * ROWQ));                                                \
+        const uint4 tb = PRE ? tb_pre : __ldg(q_oth + (b_tb + y * ROWQ));                                                \
         uint32_t e_ld = 0;                                                                                               \
         const bool e_lane = SEGS > 1 && (p ? lane == 31u : lane == 0u);                                                  \
         if (SEGS > 1) {                                                                                                  \
@@ -431,36 +432,49 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
             const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
             wa = __ldg(q_oth + (b_own + ym * ROWQ));
             wb = __ldg(q_oth + (b_own + y * ROWQ));
+            // ... and the four loads of the first row step: in the step itself they would be scheduled behind the
+            // round keys and the rest of the set-up, a hundred instructions after the wait
+            const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;
+            v_pre = q_own[b_own + y * ROWQ];
+            on_pre = __ldg(q_oth + (b_own + yn * ROWQ));
+            ta_pre = __ldg(q_oth + (b_ta + y * ROWQ));
+            tb_pre = __ldg(q_oth + (b_tb + y * ROWQ));
         }
         // only the blocks whose group holds one of the first / last `depth` owned planes carry the push stores
         if (SLAB && sl.depth != 0u && grp_hi > 0 && grp_lo < (int32_t)g.Tl &&
             (grp_lo < (int32_t)sl.depth || grp_hi > (int32_t)(g.Tl - sl.depth))) {
-            for (;;) {
-                LQFT_N16_STEP(wa, wb, wc, true, false)
-                if (--n == 0) break;
-                LQFT_N16_STEP(wb, wc, wa, true, false)
-                if (--n == 0) break;
-                LQFT_N16_STEP(wc, wa, wb, true, false)
-                if (--n == 0) break;
-            }
+            LQFT_N16_STEP(wa, wb, wc, true, false, true)
+            if (--n != 0)
+                for (;;) {
+                    LQFT_N16_STEP(wb, wc, wa, true, false, false)
+                    if (--n == 0) break;
+                    LQFT_N16_STEP(wc, wa, wb, true, false, false)
+                    if (--n == 0) break;
+                    LQFT_N16_STEP(wa, wb, wc, true, false, false)
+                    if (--n == 0) break;
+                }
         } else if (MEAS) {
-            for (;;) {
-                LQFT_N16_STEP(wa, wb, wc, false, true)
-                if (--n == 0) break;
-                LQFT_N16_STEP(wb, wc, wa, false, true)
-                if (--n == 0) break;
-                LQFT_N16_STEP(wc, wa, wb, false, true)
-                if (--n == 0) break;
-            }
+            LQFT_N16_STEP(wa, wb, wc, false, true, true)
+            if (--n != 0)
+                for (;;) {
+                    LQFT_N16_STEP(wb, wc, wa, false, true, false)
+                    if (--n == 0) break;
+                    LQFT_N16_STEP(wc, wa, wb, false, true, false)
+                    if (--n == 0) break;
+                    LQFT_N16_STEP(wa, wb, wc, false, true, false)
+                    if (--n == 0) break;
+                }
         } else {
-            for (;;) {
-                LQFT_N16_STEP(wa, wb, wc, false, false)
-                if (--n == 0) break;
-                LQFT_N16_STEP(wb, wc, wa, false, false)
-                if (--n == 0) break;
-                LQFT_N16_STEP(wc, wa, wb, false, false)
-                if (--n == 0) break;
-            }
+            LQFT_N16_STEP(wa, wb, wc, false, false, true)
+            if (--n != 0)
+                for (;;) {
+                    LQFT_N16_STEP(wb, wc, wa, false, false, false)
+                    if (--n == 0) break;
+                    LQFT_N16_STEP(wc, wa, wb, false, false, false)
+                    if (--n == 0) break;
+                    LQFT_N16_STEP(wa, wb, wc, false, false, false)
+                    if (--n == 0) break;
+                }
         }
         // Ghost tasks (slabs).  The ghost planes this half-sweep updates redundantly (sl.extra per side) do not get
         // blocks of their own: 14 planes beside 256 owned ones made a ninth, mostly empty pair of plane groups — 576
@@ -491,7 +505,7 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
                     const uint32_t yb = (y == 0) ? g.Y - 1 : y - 1;
                     wa = __ldg(q_oth + (b_own + yb * ROWQ));
                     wb = __ldg(q_oth + (b_own + y * ROWQ));
-                    LQFT_N16_STEP(wa, wb, wc, false, false)
+                    LQFT_N16_STEP(wa, wb, wc, false, false, false)
                 }
             }
         }
