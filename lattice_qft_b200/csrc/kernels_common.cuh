@@ -13,6 +13,25 @@ namespace lqft {
 // once, and touches field data / the device sweep counter only after its predecessor has completed.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Loads that follow the wait for the previous launch directly.  A non-coherent load (__ldg, or any load through a
+// const __restrict__ pointer) may be hoisted above griddepcontrol.wait — ptxas does it (seen in the SASS of a slab
+// instantiation: five LDG.E.128.CONSTANT in front of ACQBULK, wrong acceptance counts) — so the first loads behind the wait
+// are plain coherent ones, issued by volatile statements; the loads of the later row steps sit behind a branch.
+__device__ __forceinline__ uint4 ld_after_wait(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_after_wait(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_after_wait(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // Round keys of Philox4x32-10 (key + r * W), computed once per thread and kept in registers.
 struct RoundKeys {

@@ -297,12 +297,13 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     const ChainDev cd = SINGLE ? chain0 : chains[chain];
     if (COUNT && threadIdx.x == 0) s_cnt = 0;
     const N16Tab tab = build_interleaved(thr_all + (size_t)chain * kThrStride, max_thr, g.entry_bytes);
-    // The wait for the previous launch: a slab launch needs it before the flip; every other launch takes it as late as
+    // The wait for the previous launch: a slab launch that flips the ghost sets needs it before the flip; every other launch takes it as late as
     // possible, after the index arithmetic and right before the first load of the field — what precedes it runs under
     // the previous launch's drain (128^3: 3.03 -> 3.49e11, 256^3: 7.59 -> 7.73e11, profiles/r2_late_wait.txt)
-    if (SLAB) {
+    const bool flips = SLAB && sl.sync != 0u;
+    if (flips) {
         pdl_wait();
-        if (ctr) sweep += *ctr;
+        if (ctr) sweep += ld_after_wait(ctr);
     }
     // planes of this block's group: local numbers [grp_lo, grp_hi) of a launch with one range (every SLAB launch)
     const int32_t grp_lo = tl_first + (int32_t)((blockIdx.y >> 1) * (2u * PPW * (blockDim.x >> 5)));
@@ -374,7 +375,8 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         uint32_t e_ld = 0;                                                                                               \
         const bool e_lane = SEGS > 1 && (p ? lane == 31u : lane == 0u);                                                  \
         if (SEGS > 1) {                                                                                                  \
-            if (e_lane) e_ld = __ldg(w_oth + ((p ? e_right : e_left) + y * (ROWQ * 4u)));                                \
+            if (e_lane) e_ld = PRE ? ld_after_wait(w_oth + ((p ? e_right : e_left) + y * (ROWQ * 4u)))                   \
+                                   : __ldg(w_oth + ((p ? e_right : e_left) + y * (ROWQ * 4u)));                          \
         }                                                                                                                \
         const uint32_t grp = grp_base + y * (2u * ROWQ);                                                                 \
         const u32x4 r0 = philox4x32_rk(grp, (uint32_t)colour, (uint32_t)sweep, (uint32_t)(sweep >> 32), rk);             \
@@ -424,21 +426,20 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
         // a warp without a live plane slot leaves after one row (the vote keeps the trip count warp uniform for the
         // compiler; an outright early exit costs the uniform registers, see above)
         uint32_t n = __all_sync(0xffffffffu, pl_raw >= n_planes) ? 1u : y1 - y0;
-        if (!SLAB) {
+        if (!flips) {
             pdl_wait();
-            if (ctr) sweep += *ctr;
+            if (ctr) sweep += ld_after_wait(ctr);
         }
         {
-            const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1;
-            wa = __ldg(q_oth + (b_own + ym * ROWQ));
-            wb = __ldg(q_oth + (b_own + y * ROWQ));
-            // ... and the four loads of the first row step: in the step itself they would be scheduled behind the
-            // round keys and the rest of the set-up, a hundred instructions after the wait
-            const uint32_t yn = (y + 1 == g.Y) ? 0 : y + 1;
-            v_pre = q_own[b_own + y * ROWQ];
-            on_pre = __ldg(q_oth + (b_own + yn * ROWQ));
-            ta_pre = __ldg(q_oth + (b_ta + y * ROWQ));
-            tb_pre = __ldg(q_oth + (b_tb + y * ROWQ));
+            // the window rows and the four loads of the first row step (in the step itself they would be scheduled behind
+            // the round keys and the rest of the set-up, a hundred instructions after the wait); coherent loads: ld_after_wait
+            const uint32_t ym = (y == 0) ? g.Y - 1 : y - 1, yn = (y + 1 == g.Y) ? 0 : y + 1;
+            wa = ld_after_wait(q_oth + (b_own + ym * ROWQ));
+            wb = ld_after_wait(q_oth + (b_own + y * ROWQ));
+            v_pre = ld_after_wait(q_own + (b_own + y * ROWQ));
+            on_pre = ld_after_wait(q_oth + (b_own + yn * ROWQ));
+            ta_pre = ld_after_wait(q_oth + (b_ta + y * ROWQ));
+            tb_pre = ld_after_wait(q_oth + (b_tb + y * ROWQ));
         }
         // only the blocks whose group holds one of the first / last `depth` owned planes carry the push stores
         if (SLAB && sl.depth != 0u && grp_hi > 0 && grp_lo < (int32_t)g.Tl &&
