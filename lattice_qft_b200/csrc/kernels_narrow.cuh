@@ -297,9 +297,10 @@ k_sweep_n16(const Geom g, const int colour, uint64_t sweep, const uint64_t* __re
     const ChainDev cd = SINGLE ? chain0 : chains[chain];
     if (COUNT && threadIdx.x == 0) s_cnt = 0;
     const N16Tab tab = build_interleaved(thr_all + (size_t)chain * kThrStride, max_thr, g.entry_bytes);
-    // The wait for the previous launch: a slab launch that flips the ghost sets needs it before the flip; every other launch takes it as late as
-    // possible, after the index arithmetic and right before the first load of the field — what precedes it runs under
-    // the previous launch's drain (128^3: 3.03 -> 3.49e11, 256^3: 7.59 -> 7.73e11, profiles/r2_late_wait.txt)
+    // The wait for the previous launch: a slab launch that flips the ghost sets needs it before the flip; every other
+    // launch takes it as late as possible, after the index arithmetic and right before the first load of the field —
+    // what precedes it runs under the previous launch's drain (128^3: 3.03 -> 3.49e11, 256^3: 7.59 -> 7.73e11,
+    // profiles/r2_late_wait.txt)
     const bool flips = SLAB && sl.sync != 0u;
     if (flips) {
         pdl_wait();
